@@ -1,0 +1,169 @@
+/*
+ * sdb200.h -- C ABI of libsdb200.so, the B200-native (sm_100a) implementation of the
+ * SceneDreamer per-pixel render hot path.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; nothing is allocated,
+ *     freed or retained by the library (no ownership transfer, re-entrant, no global state);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every entry point returns 0 on success, a positive cudaError_t on a CUDA failure, or a
+ *     negative SDB_E* code for an argument error; no exceptions cross the ABI.  The Python
+ *     mirrors turn non-zero codes into RuntimeError like the reference's TORCH_CHECKs do;
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points return an error.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the binding a maintainer would add on the reference
+ * side.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_OK 0
+#define SDB_EINVAL (-1)      /* bad argument (null pointer, size <= 0, ...)            */
+#define SDB_EUNSUPPORTED (-2) /* valid in the reference, not supported here (see docs) */
+
+/* Library / build information.  Safe to call without a GPU. */
+int sdb_version(void);                 /* 10000*major + 100*minor + patch                 */
+const char *sdb_build_info(void);      /* "sm_100a nvcc X.Y ..." -- static string          */
+const char *sdb_error_string(int code);/* cudaGetErrorString for >0, own text for <0      */
+
+/* --------------------------------------------------------------------------------------------
+ * a1. Ray / voxel intersection, perspective camera.
+ * Replaces voxlib.ray_voxel_intersection_perspective
+ *   (imaginaire/model_utils/gancraft/voxlib/voxlib.cpp:11,26;
+ *    ray_voxel_intersection.cu:253-325 host wrapper, :52-235 kernel).
+ * The camera frame (fwd/side/up) is derived on the host from cam_dir/cam_up exactly as the
+ * reference does (:279-284); cam_* are HOST pointers to 3 floats.
+ *   d_voxel      int32, dims[3] with element strides[3] (any strides, like the reference)
+ *   d_voxel_id   int32  [H, W, M]        (reference shape [H,W,M,1])
+ *   d_depth2     float  [2, H, W, M]     (entry t, exit t; NaN in unfilled slots)
+ *   d_raydirs    float  [H, W, 3]
+ * ------------------------------------------------------------------------------------------ */
+int sdb_ray_voxel_intersection_perspective(
+    const int32_t *d_voxel, const int64_t dims[3], const int64_t strides[3],
+    const float cam_ori[3], const float cam_dir[3], const float cam_up[3],
+    float cam_f, const float cam_c[2], const int32_t img_dims[2], int32_t max_samples,
+    int32_t *d_voxel_id, float *d_depth2, float *d_raydirs, void *stream);
+
+/* Host-only helper (no GPU needed): the camera frame the call above derives. */
+void sdb_camera_frame(const float cam_dir[3], const float cam_up[3], float fwd[3], float side[3], float up[3]);
+
+/* --------------------------------------------------------------------------------------------
+ * a6/a7. Multi-resolution hash / tiled grid encoding, float32.
+ * Replace _gridencoder.grid_encode_forward / grid_encode_backward
+ *   (gridencoder/src/bindings.cpp:5-8, gridencoder.h:12-13, gridencoder.cu:423-478).
+ * Same argument meaning as the reference: caller pre-allocates everything;
+ *   d_inputs [B,D] in [0,1]; d_embeddings [sum T_l, C]; d_offsets int32 [L+1];
+ *   d_outputs [L,B,C]; d_dy_dx [B, L*D*C] (only touched when calc_grad_inputs);
+ *   backward: d_grad [L,B,C], d_grad_embeddings pre-zeroed, d_grad_inputs [B,D].
+ * D in {2,3,4,5}, C in {1,2,4,8} (else SDB_EUNSUPPORTED, the reference throws).
+ * Unlike the reference (legacy default stream, gridencoder.cu:351) the launch goes to `stream`.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_grid_encode_forward(
+    const float *d_inputs, const float *d_embeddings, const int32_t *d_offsets, float *d_outputs,
+    uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, float *d_dy_dx, uint32_t gridtype, int align_corners, void *stream);
+
+int sdb_grid_encode_backward(
+    const float *d_grad, const float *d_inputs, const float *d_embeddings, const int32_t *d_offsets,
+    float *d_grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, const float *d_dy_dx, float *d_grad_inputs, uint32_t gridtype,
+    int align_corners, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * a9. Positional encoding along one dimension of a contiguous tensor viewed as [pre, post]
+ * -> [pre, stride, post], stride = 2*ndegrees (+1 if incl_orig).
+ * Replace voxlib.positional_encoding / positional_encoding_backward
+ *   (voxlib.cpp:20,22,29-30; positional_encoding_kernel.cu:40-118).
+ * ------------------------------------------------------------------------------------------ */
+int sdb_positional_encoding(const float *d_in, float *d_out, int64_t pre, int64_t post,
+                            int32_t ndegrees, int incl_orig, void *stream);
+int sdb_positional_encoding_backward(const float *d_out_grad, const float *d_out, float *d_in_grad,
+                                     int64_t pre, int64_t post, int32_t ndegrees, int incl_orig,
+                                     void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * a2-a5, a8, a10-a12. Fused per-pixel render: sampling -> labels -> hash-grid features ->
+ * style-modulated sigma/colour MLP (tcgen05 tensor cores) -> front-to-back compositing + sky
+ * blend.  Replaces the body of Generator._forward_perpix and the tile loop around it
+ *   (imaginaire/generators/scenedreamer.py:285-428, :600-628; mc_utils.py:82-161;
+ *    model_utils/layers.py:92-126, :241-271; gridencoder.cu:75-224).
+ * See sdb_render_params below and DESIGN.md for layouts.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdb_render_params {
+    /* rays (outputs of a1), R = number of rays */
+    int64_t R;
+    int32_t M;                   /* slots per ray (num_blocks_early_stop)                     */
+    int32_t S;                   /* samples per ray (num_samples); S+1 stratification points  */
+    const int32_t *d_voxel_id;   /* [R, M]                                                    */
+    const float *d_depth2;       /* [2, R, M]                                                 */
+    const float *d_raydirs;      /* [R, 3]                                                    */
+    float cam_ori[3];
+    float voxel_dims[3];         /* normalisation of world coords (scenedreamer.py:298-299)   */
+    float global_enc[2];         /* scene code appended as dims 3,4 (scenedreamer.py:300-302) */
+    float sample_depth;          /* mc_utils.py:107                                           */
+    float dists_scale;           /* scenedreamer.py:373                                       */
+    /* sampling positions: S+1 fractions in (0,1) (deterministic linspace, mc_utils.py:118-120)
+       or NULL with d_uniforms [R, S+1] given (stratified branch, :122-125)                    */
+    const float *d_fractions;
+    const float *d_uniforms;
+    /* label translation: reduced label per Minecraft id, ignore already mapped to dirt
+       (mc_utils.py:241-246), n_lut entries                                                    */
+    const int32_t *d_label_lut;
+    int32_t n_lut;
+    /* hash grid (D=5, C=8, all levels hashed with T = 2^log2_T): either the raw 5-D table
+       [L*T, 8] (d_table, exact reference arithmetic, 32 corners) or the per-scene pre-blended
+       3-D table from sdb_preblend_table (d_table3, 8 corners).  Exactly one is non-NULL.      */
+    const float *d_table;
+    const float *d_table3;
+    int32_t L;
+    int32_t log2_T;
+    float level_S;               /* log2(per_level_scale)                                     */
+    int32_t base_res;
+    /* MLP weights, packed by sdb_pack_mlp() for one style code                                */
+    const void *d_mlp_pack;
+    /* sky features per ray [R, 64] (SKYMLP output) and the frame-global mean [64]             */
+    const float *d_sky;
+    const float *d_sky_avg;
+    /* outputs */
+    float *d_net_out;            /* [R, 64]                                                   */
+    float *d_depth_out;          /* [R] sum w*t (scenedreamer.py:816) or NULL                 */
+    float *d_total_weight;       /* [R] or NULL                                               */
+    int32_t precision;           /* 0: fp16 x1 tensor pass, 1: bf16 x3 split (fp32-grade)     */
+} sdb_render_params;
+
+int sdb_render_rays_forward(const sdb_render_params *p, void *stream);
+
+/* Per-scene collapse of the two constant encoder dimensions (inference only):
+ * table3[l][i] = sum_j w_j(l) * table[l][i ^ K_j(l)], j over the 4 (dim3,dim4) corners.
+ * d_table [L*T, 8] -> d_table3 [L*T, 8].  ("parity-preserving work
+ * reductions"; valid because every level is hashed and T is a power of two.)                  */
+int sdb_preblend_table(const float *d_table, float *d_table3, int32_t L, int32_t log2_T, float level_S,
+                       int32_t base_res, const float global_enc[2], void *stream);
+
+/* Size in bytes of the packed MLP image, and the packer.  Inputs are DEVICE fp32 row-major
+ * matrices of the style-modulated network for ONE style code:
+ *   w1 [256,128] b1 [256]; emb [12,256] (= fc_m_a.weight^T rows per label);
+ *   wh [5][256,256] (fc_2..fc_6 weight * alpha, per input column) bh [5][256] (beta);
+ *   wsig [256] bsig [1]; wout [64,256] bout [64].                                             */
+int64_t sdb_mlp_pack_bytes(void);
+int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, const float *d_wh,
+                 const float *d_bh, const float *d_wsig, const float *d_bsig, const float *d_wout,
+                 const float *d_bout, void *d_pack, void *stream);
+
+/* tcgen05 / TMEM self test: C[128,N] = A[128,K] * B[N,K]^T with the exact smem descriptors the
+ * fused kernel uses.  d_a, d_b fp32 inputs (rounded to fp16/bf16 inside), d_c fp32 output.
+ * variant 0 = the layout the library uses; 1 = LBO/SBO swapped (diagnostic only).              */
+int sdb_tc_selftest(const float *d_a, const float *d_b, float *d_c, int32_t N, int32_t K,
+                    int32_t use_bf16, int32_t variant, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

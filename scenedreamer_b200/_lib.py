@@ -1,0 +1,63 @@
+"""ctypes loader for libsdb200.so (include/sdb200.h).  Fails loudly: there is no fallback path."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsdb200.so')
+_lib = None
+
+c_void_p, c_int, c_i32, c_u32, c_i64, c_f32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_uint32,
+                                               ctypes.c_int64, ctypes.c_float)
+_F3 = ctypes.POINTER(ctypes.c_float)
+
+# every symbol include/sdb200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    'sdb_version': (c_int, []),
+    'sdb_build_info': (ctypes.c_char_p, []),
+    'sdb_error_string': (ctypes.c_char_p, [c_int]),
+    'sdb_camera_frame': (None, [_F3, _F3, _F3, _F3, _F3]),
+    'sdb_ray_voxel_intersection_perspective': (c_int, [
+        c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), _F3, _F3, _F3, c_f32, _F3,
+        ctypes.POINTER(c_i32), c_i32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sdb_grid_encode_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_f32,
+                                        c_u32, c_int, c_void_p, c_u32, c_int, c_void_p]),
+    'sdb_grid_encode_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32,
+                                         c_u32, c_f32, c_u32, c_int, c_void_p, c_void_p, c_u32, c_int, c_void_p]),
+    'sdb_positional_encoding': (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_int, c_void_p]),
+    'sdb_positional_encoding_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_int, c_void_p]),
+    'sdb_render_rays_forward': (c_int, [c_void_p, c_void_p]),
+    'sdb_preblend_table': (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_f32, c_i32, _F3, c_void_p]),
+    'sdb_mlp_pack_bytes': (c_i64, []),
+    'sdb_pack_mlp': (c_int, [c_void_p] * 10 + [c_void_p]),
+    'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
+}
+
+
+_PENDING = ('sdb_render_rays_forward', 'sdb_preblend_table', 'sdb_mlp_pack_bytes', 'sdb_pack_mlp')
+
+
+def lib():
+    """The loaded library; builds it first if the .so is missing and nvcc is available."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('scenedreamer_b200: %s is missing and could not be built; '
+                               'this package has no CPU or PyTorch fallback' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            if name in _PENDING and not hasattr(L, name):
+                continue
+            fn = getattr(L, name)          # AttributeError here == header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().sdb_error_string(int(code)).decode()
+        raise RuntimeError('%s failed: %s (code %d)' % (what, msg, code))

@@ -1,0 +1,290 @@
+// a6/a7: stand-alone multi-resolution hash / tiled grid encoder, float32, sm_100a.
+//
+// Behavioural contract = _gridencoder.grid_encode_forward / grid_encode_backward of the reference
+// (gridencoder/src/gridencoder.cu:423-478 wrappers; :75-224 kernel_grid, :227-314
+// kernel_grid_backward, :317-343 kernel_input_backward; index math :35-72).  This is the drop-in
+// boundary op; the render hot path itself uses the fused kernel in render_fused.cu.
+//
+// B200 mapping (HBM/L2-gather bound, no tensor cores): one thread per (sample, level); the C
+// features of a corner are fetched with ONE vector load (2x LDG.128 for C=8) instead of C scalar
+// loads; the backward scatters with vector reductions (red.global.add.v4.f32, sm_90+) -- 2 per
+// corner for C=8 instead of 8 scalar atomics; blocks are level-major (blockIdx.y = level) so a
+// wave of CTAs keeps one level's table slice hot in the 126 MB L2.
+#include "common.cuh"
+
+namespace {
+
+__device__ __constant__ uint32_t kPrimes[7] = {1u, 2654435761u, 805459861u, 3674653429u,
+                                               2097192037u, 1434869437u, 2165219737u};
+
+template <uint32_t D>
+__device__ __forceinline__ uint32_t grid_index(uint32_t gridtype, bool align_corners, uint32_t hashmap_size,
+                                               uint32_t resolution, const uint32_t (&pg)[D]) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        if (stride <= hashmap_size) {
+            index += pg[d] * stride;
+            stride *= align_corners ? resolution : (resolution + 1);
+        }
+    }
+    if (gridtype == 0 && stride > hashmap_size) {
+        uint32_t h = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) h ^= pg[d] * kPrimes[d];
+        index = h;
+    }
+    return index % hashmap_size;
+}
+
+template <uint32_t C>
+__device__ __forceinline__ void load_feat(const float *__restrict__ g, float (&v)[C]) {
+    if constexpr (C == 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(g) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if constexpr (C == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else if constexpr (C == 2) {
+        const float2 a = __ldg(reinterpret_cast<const float2 *>(g));
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = __ldg(g);
+    }
+}
+
+template <uint32_t D>
+__device__ __forceinline__ bool locate(const float *__restrict__ x, float scale, bool align_corners,
+                                       float (&pos)[D], uint32_t (&pg)[D]) {
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const float v = x[d];
+        if (v < 0 || v > 1) oob = true;
+        pos[d] = v * scale + (align_corners ? 0.0f : 0.5f);
+        const float fl = floorf(pos[d]);
+        pg[d] = (uint32_t)fl;
+        pos[d] -= (float)pg[d];
+    }
+    return oob;
+}
+
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+grid_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ grid,
+                    const int *__restrict__ offsets, float *__restrict__ outputs, uint32_t B, uint32_t L,
+                    float S, uint32_t H, bool calc_grad_inputs, float *__restrict__ dy_dx, uint32_t gridtype,
+                    bool align_corners)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    grid += (size_t)(uint32_t)offsets[level] * C;
+    float *out = outputs + ((size_t)level * B + b) * C;
+    const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+    const float scale = exp2f(level * S) * H - 1.0f;
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+
+    float pos[D];
+    uint32_t pg[D];
+    const bool oob = locate<D>(inputs + (size_t)b * D, scale, align_corners, pos, pg);
+    if (oob) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) out[c] = 0;
+        if (calc_grad_inputs) {
+            float *dd = dy_dx + ((size_t)b * L + level) * D * C;
+#pragma unroll
+            for (uint32_t k = 0; k < D * C; k++) dd[k] = 0;
+        }
+        return;
+    }
+    float res[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) res[c] = 0;
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1;
+        uint32_t pl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+            else { w *= pos[d]; pl[d] = pg[d] + 1; }
+        }
+        const uint32_t index = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+        float v[C];
+        load_feat<C>(grid + (size_t)index * C, v);
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) res[c] += w * v[c];
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) out[c] = res[c];
+
+    if (calc_grad_inputs) {
+        float *dd = dy_dx + ((size_t)b * L + level) * D * C;
+#pragma unroll
+        for (uint32_t gd = 0; gd < D; gd++) {
+            float rg[C];
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) rg[c] = 0;
+#pragma unroll
+            for (uint32_t idx = 0; idx < (1u << (D - 1)); idx++) {
+                float w = scale;
+                uint32_t pl[D];
+#pragma unroll
+                for (uint32_t nd = 0; nd < D - 1; nd++) {
+                    const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                    if ((idx & (1u << nd)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                    else { w *= pos[d]; pl[d] = pg[d] + 1; }
+                }
+                pl[gd] = pg[gd];
+                const uint32_t il = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+                pl[gd] = pg[gd] + 1;
+                const uint32_t ir = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+                float vl[C], vr[C];
+                load_feat<C>(grid + (size_t)il * C, vl);
+                load_feat<C>(grid + (size_t)ir * C, vr);
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) rg[c] += w * (vr[c] - vl[c]);
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) dd[gd * C + c] = rg[c];
+        }
+    }
+}
+
+template <uint32_t C>
+__device__ __forceinline__ void red_add(float *__restrict__ g, const float (&v)[C]) {
+    if constexpr (C == 8) {
+        atomicAdd(reinterpret_cast<float4 *>(g), make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(reinterpret_cast<float4 *>(g) + 1, make_float4(v[4], v[5], v[6], v[7]));
+    } else if constexpr (C == 4) {
+        atomicAdd(reinterpret_cast<float4 *>(g), make_float4(v[0], v[1], v[2], v[3]));
+    } else if constexpr (C == 2) {
+        atomicAdd(reinterpret_cast<float2 *>(g), make_float2(v[0], v[1]));
+    } else {
+        atomicAdd(g, v[0]);
+    }
+}
+
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+grid_backward_kernel(const float *__restrict__ grad, const float *__restrict__ inputs,
+                     const int *__restrict__ offsets, float *__restrict__ grad_grid, uint32_t B, uint32_t L,
+                     float S, uint32_t H, uint32_t gridtype, bool align_corners)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    grad_grid += (size_t)(uint32_t)offsets[level] * C;
+    const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+    const float scale = exp2f(level * S) * H - 1.0f;
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+    float pos[D];
+    uint32_t pg[D];
+    if (locate<D>(inputs + (size_t)b * D, scale, align_corners, pos, pg)) return;  // grad pre-zeroed
+    float g[C];
+    load_feat<C>(grad + ((size_t)level * B + b) * C, g);
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1;
+        uint32_t pl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+            else { w *= pos[d]; pl[d] = pg[d] + 1; }
+        }
+        const uint32_t index = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+        float v[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) v[c] = w * g[c];
+        red_add<C>(grad_grid + (size_t)index * C, v);
+    }
+}
+
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+input_backward_kernel(const float *__restrict__ grad, const float *__restrict__ dy_dx,
+                      float *__restrict__ grad_inputs, uint32_t B, uint32_t L)
+{
+    const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const float *dd = dy_dx + (size_t)b * L * D * C;
+    float r = 0;
+    for (uint32_t l = 0; l < L; l++) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) r += grad[((size_t)l * B + b) * C + c] * dd[(l * D + d) * C + c];
+    }
+    grad_inputs[t] = r;
+}
+
+template <uint32_t D, uint32_t C>
+int launch_fwd(const float *in, const float *emb, const int *off, float *out, uint32_t B, uint32_t L, float S,
+               uint32_t H, bool calc, float *dy_dx, uint32_t gt, bool ac, cudaStream_t st) {
+    dim3 grid(sdb_div_up(B, 256u), L);
+    grid_forward_kernel<D, C><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}
+template <uint32_t D, uint32_t C>
+int launch_bwd(const float *grad, const float *in, const int *off, float *gg, uint32_t B, uint32_t L, float S,
+               uint32_t H, bool calc, const float *dy_dx, float *gi, uint32_t gt, bool ac, cudaStream_t st) {
+    dim3 grid(sdb_div_up(B, 256u), L);
+    grid_backward_kernel<D, C><<<grid, 256, 0, st>>>(grad, in, off, gg, B, L, S, H, gt, ac);
+    SDB_CHECK_LAUNCH();
+    if (calc) {
+        input_backward_kernel<D, C><<<sdb_div_up(B * D, 256u), 256, 0, st>>>(grad, dy_dx, gi, B, L);
+        SDB_CHECK_LAUNCH();
+    }
+    return SDB_OK;
+}
+
+}  // namespace
+
+#define SDB_DISPATCH_DC(FN, ...)                                          \
+    switch (D * 16 + C) {                                                 \
+        case 2 * 16 + 1: return FN<2, 1>(__VA_ARGS__);                    \
+        case 2 * 16 + 2: return FN<2, 2>(__VA_ARGS__);                    \
+        case 2 * 16 + 4: return FN<2, 4>(__VA_ARGS__);                    \
+        case 2 * 16 + 8: return FN<2, 8>(__VA_ARGS__);                    \
+        case 3 * 16 + 1: return FN<3, 1>(__VA_ARGS__);                    \
+        case 3 * 16 + 2: return FN<3, 2>(__VA_ARGS__);                    \
+        case 3 * 16 + 4: return FN<3, 4>(__VA_ARGS__);                    \
+        case 3 * 16 + 8: return FN<3, 8>(__VA_ARGS__);                    \
+        case 4 * 16 + 1: return FN<4, 1>(__VA_ARGS__);                    \
+        case 4 * 16 + 2: return FN<4, 2>(__VA_ARGS__);                    \
+        case 4 * 16 + 4: return FN<4, 4>(__VA_ARGS__);                    \
+        case 4 * 16 + 8: return FN<4, 8>(__VA_ARGS__);                    \
+        case 5 * 16 + 1: return FN<5, 1>(__VA_ARGS__);                    \
+        case 5 * 16 + 2: return FN<5, 2>(__VA_ARGS__);                    \
+        case 5 * 16 + 4: return FN<5, 4>(__VA_ARGS__);                    \
+        case 5 * 16 + 8: return FN<5, 8>(__VA_ARGS__);                    \
+        default: return SDB_EUNSUPPORTED;                                 \
+    }
+
+extern "C" int sdb_grid_encode_forward(
+    const float *d_inputs, const float *d_embeddings, const int32_t *d_offsets, float *d_outputs,
+    uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, float *d_dy_dx, uint32_t gridtype, int align_corners, void *stream)
+{
+    if (!d_inputs || !d_embeddings || !d_offsets || !d_outputs) return SDB_EINVAL;
+    if (calc_grad_inputs && !d_dy_dx) return SDB_EINVAL;
+    if (B == 0 || L == 0) return SDB_OK;
+    SDB_DISPATCH_DC(launch_fwd, d_inputs, d_embeddings, d_offsets, d_outputs, B, L, S, H, calc_grad_inputs != 0,
+                    d_dy_dx, gridtype, align_corners != 0, (cudaStream_t)stream)
+}
+
+extern "C" int sdb_grid_encode_backward(
+    const float *d_grad, const float *d_inputs, const float *d_embeddings, const int32_t *d_offsets,
+    float *d_grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, const float *d_dy_dx, float *d_grad_inputs, uint32_t gridtype,
+    int align_corners, void *stream)
+{
+    (void)d_embeddings;
+    if (!d_grad || !d_inputs || !d_offsets || !d_grad_embeddings) return SDB_EINVAL;
+    if (calc_grad_inputs && (!d_dy_dx || !d_grad_inputs)) return SDB_EINVAL;
+    if (B == 0 || L == 0) return SDB_OK;
+    SDB_DISPATCH_DC(launch_bwd, d_grad, d_inputs, d_offsets, d_grad_embeddings, B, L, S, H, calc_grad_inputs != 0,
+                    d_dy_dx, d_grad_inputs, gridtype, align_corners != 0, (cudaStream_t)stream)
+}

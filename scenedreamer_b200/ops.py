@@ -1,0 +1,173 @@
+"""Python mirrors of the reference's native entry points, over libsdb200's C ABI.
+
+Same names, argument meaning and error behaviour as the pybind functions of the reference:
+  voxlib.*          imaginaire/model_utils/gancraft/voxlib/voxlib.cpp:25-31
+  _gridencoder.*    gridencoder/src/bindings.cpp:5-8
+Tensors are torch CUDA tensors; only their data pointers, shapes and the current CUDA stream
+cross into the library (PyTorch is the allocator / stream plumbing, not the compute path).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor' % name)
+
+
+def _check_input(t, name, dtype=None):
+    _check_cuda(t, name)
+    if not t.is_contiguous():
+        raise RuntimeError('%s must be contiguous' % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError('%s must be a %s tensor' % (name, str(dtype).replace('torch.', '')))
+
+
+def _f3(t):
+    a = torch.as_tensor(t).detach().to('cpu', torch.float32).reshape(-1)
+    if a.numel() != 3:
+        raise RuntimeError('camera vectors must have 3 elements')
+    return (ctypes.c_float * 3)(*[float(v) for v in a])
+
+
+# ------------------------------------------------------------------------------------------------
+# voxlib
+# ------------------------------------------------------------------------------------------------
+def ray_voxel_intersection_perspective(in_voxel, cam_ori, cam_dir, cam_up, cam_f, cam_c, img_dims, max_samples):
+    """-> [voxel_id int32 [H,W,M,1], depth2 f32 [2,H,W,M,1], raydirs f32 [H,W,1,3]]  (voxlib.cpp:11)."""
+    _check_cuda(in_voxel, 'in_voxel')
+    if in_voxel.dtype != torch.int32 or in_voxel.dim() != 3:
+        raise RuntimeError('in_voxel must be a 3-D int32 tensor')
+    H, W, M = int(img_dims[0]), int(img_dims[1]), int(max_samples)
+    dev = in_voxel.device
+    with torch.cuda.device(dev):
+        voxel_id = torch.empty(H, W, M, 1, dtype=torch.int32, device=dev)
+        depth2 = torch.empty(2, H, W, M, 1, dtype=torch.float32, device=dev)
+        raydirs = torch.empty(H, W, 1, 3, dtype=torch.float32, device=dev)
+        dims = (ctypes.c_int64 * 3)(*in_voxel.shape)
+        strides = (ctypes.c_int64 * 3)(*in_voxel.stride())
+        cc = (ctypes.c_float * 2)(float(cam_c[0]), float(cam_c[1]))
+        im = (ctypes.c_int32 * 2)(H, W)
+        code = _lib.lib().sdb_ray_voxel_intersection_perspective(
+            _ptr(in_voxel), dims, strides, _f3(cam_ori), _f3(cam_dir), _f3(cam_up), float(cam_f), cc, im, M,
+            _ptr(voxel_id), _ptr(depth2), _ptr(raydirs), _stream(in_voxel))
+    _lib.check(code, 'ray_voxel_intersection_perspective')
+    return [voxel_id, depth2, raydirs]
+
+
+def _pe_shape(t, dim):
+    dim = dim % t.dim()
+    pre = int(np.prod(t.shape[:dim])) if dim > 0 else 1
+    post = int(np.prod(t.shape[dim:]))
+    return dim, pre, post
+
+
+def positional_encoding(in_feature, ndegrees, dim, incl_orig):
+    _check_input(in_feature, 'in_feature', torch.float32)
+    dim, pre, post = _pe_shape(in_feature, dim)
+    stride = 2 * int(ndegrees) + (1 if incl_orig else 0)
+    shape = list(in_feature.shape)
+    shape[dim] *= stride
+    out = torch.empty(shape, dtype=torch.float32, device=in_feature.device)
+    with torch.cuda.device(in_feature.device):
+        code = _lib.lib().sdb_positional_encoding(_ptr(in_feature), _ptr(out), pre, post, int(ndegrees),
+                                                  int(bool(incl_orig)), _stream(in_feature))
+    _lib.check(code, 'positional_encoding')
+    return out
+
+
+def positional_encoding_backward(out_feature_grad, out_feature, ndegrees, dim, incl_orig):
+    _check_input(out_feature_grad, 'out_feature_grad', torch.float32)
+    _check_input(out_feature, 'out_feature', torch.float32)
+    stride = 2 * int(ndegrees) + (1 if incl_orig else 0)
+    d = dim % out_feature.dim()
+    shape = list(out_feature.shape)
+    shape[d] //= stride
+    in_grad = torch.empty(shape, dtype=torch.float32, device=out_feature.device)
+    _, pre, post = _pe_shape(in_grad, d)
+    with torch.cuda.device(out_feature.device):
+        code = _lib.lib().sdb_positional_encoding_backward(_ptr(out_feature_grad), _ptr(out_feature), _ptr(in_grad),
+                                                           pre, post, int(ndegrees), int(bool(incl_orig)),
+                                                           _stream(out_feature))
+    _lib.check(code, 'positional_encoding_backward')
+    return in_grad
+
+
+def sp_trilinear_worldcoord(*args, **kwargs):
+    raise RuntimeError('sp_trilinear_worldcoord is not part of the SceneDreamer render path '
+                       '(only gancraft_base.py:442 calls it) and is not implemented by scenedreamer_b200')
+
+
+sp_trilinear_worldcoord_backward = sp_trilinear_worldcoord
+
+
+# ------------------------------------------------------------------------------------------------
+# _gridencoder
+# ------------------------------------------------------------------------------------------------
+def _check_ge(t, name, floating=True):
+    _check_input(t, name)
+    if floating and t.dtype != torch.float32:
+        raise RuntimeError('%s must be a float32 tensor (scenedreamer_b200 implements the fp32 path; '
+                           'the SceneDreamer configs run with AMP disabled)' % name)
+    if not floating and t.dtype != torch.int32:
+        raise RuntimeError('%s must be an int tensor' % name)
+
+
+def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, gridtype,
+                        align_corners):
+    """Caller-allocated outputs [L,B,C] / dy_dx, returns None (gridencoder.h:12)."""
+    for t, n in ((inputs, 'inputs'), (embeddings, 'embeddings'), (outputs, 'outputs'), (dy_dx, 'dy_dx')):
+        _check_ge(t, n)
+    _check_ge(offsets, 'offsets', floating=False)
+    with torch.cuda.device(inputs.device):
+        code = _lib.lib().sdb_grid_encode_forward(
+            _ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(outputs), int(B), int(D), int(C), int(L), float(S),
+            int(H), int(bool(calc_grad_inputs)), _ptr(dy_dx), int(gridtype), int(bool(align_corners)),
+            _stream(inputs))
+    if code == -2:
+        raise RuntimeError('GridEncoding: D must be 2..5 and C must be 1, 2, 4, or 8.')
+    _lib.check(code, 'grid_encode_forward')
+
+
+def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs,
+                         dy_dx, grad_inputs, gridtype, align_corners):
+    for t, n in ((grad, 'grad'), (inputs, 'inputs'), (embeddings, 'embeddings'), (grad_embeddings, 'grad_embeddings'),
+                 (dy_dx, 'dy_dx'), (grad_inputs, 'grad_inputs')):
+        _check_ge(t, n)
+    _check_ge(offsets, 'offsets', floating=False)
+    with torch.cuda.device(inputs.device):
+        code = _lib.lib().sdb_grid_encode_backward(
+            _ptr(grad), _ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(grad_embeddings), int(B), int(D), int(C),
+            int(L), float(S), int(H), int(bool(calc_grad_inputs)), _ptr(dy_dx), _ptr(grad_inputs), int(gridtype),
+            int(bool(align_corners)), _stream(inputs))
+    if code == -2:
+        raise RuntimeError('GridEncoding: D must be 2..5 and C must be 1, 2, 4, or 8.')
+    _lib.check(code, 'grid_encode_backward')
+
+
+# ------------------------------------------------------------------------------------------------
+# diagnostics
+# ------------------------------------------------------------------------------------------------
+def tc_selftest(a, b, bf16=False, variant=0):
+    """C = A @ B^T through the library's tcgen05 path.  a [128,K], b [N,K] fp32 CUDA."""
+    _check_input(a, 'a', torch.float32)
+    _check_input(b, 'b', torch.float32)
+    N, K = b.shape
+    c = torch.empty(128, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        code = _lib.lib().sdb_tc_selftest(_ptr(a), _ptr(b), _ptr(c), int(N), int(K), int(bool(bf16)), int(variant),
+                                          _stream(a))
+    _lib.check(code, 'tc_selftest')
+    return c

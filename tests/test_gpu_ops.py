@@ -1,0 +1,212 @@
+"""GPU parity tests for the boundary ops (DDA, hash-grid encoder, positional encoding) and the
+tcgen05 self test.  Everything is called through the C ABI (scenedreamer_b200.ops -> libsdb200.so)
+and compared with (1) the CPU oracle and (2) the reference's own CUDA extension prebuilt into
+oracle/_ref/ (when present)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from scenedreamer_b200 import ops, synth
+
+from _ref_ext import load as load_ref
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def bits(t):
+    return t.detach().cpu().contiguous().view(torch.int32)
+
+
+@pytest.fixture(scope='module')
+def world():
+    return synth.SyntheticVoxelWorld(size=256, seed=11)
+
+
+def _frame(world, k, hw=(60, 100), pad=6, pattern=0):
+    pose = synth.eval_camera_poses(world, maxstep=8, pattern=pattern)[k]
+    return synth.frame_camera(world, pose, resolution_hw=hw, pad=pad)
+
+
+@pytest.mark.parametrize('k,pattern', [(0, 0), (3, 0), (5, 4)])
+def test_dda_bit_exact_vs_oracle(world, k, pattern):
+    o, d, u, f, c, res = _frame(world, k, pattern=pattern)
+    vox = world.voxel_t.to(DEV)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(vox, o, d, u, f, c, res, 6)
+    evid, edep, erd = oracle.ray_voxel_intersection_perspective(world.voxel_t, o, d, u, f, c, res, 6)
+    assert vid.shape == (res[0], res[1], 6, 1) and dep.shape == (2, res[0], res[1], 6, 1) and rd.shape == (res[0], res[1], 1, 3)
+    assert torch.equal(vid.cpu(), evid)                       # voxel ids / hit mask: bit exact
+    assert torch.equal(bits(rd), bits(erd))                   # ray directions: bit exact
+    assert torch.equal(torch.isnan(dep.cpu()), torch.isnan(edep))
+    assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(edep, nan=-1.0)))
+    assert (evid[..., 0, 0] != 0).float().mean() > 0.2        # the frame really hits the scene
+
+
+def test_dda_strided_volume_and_edge_cases(world):
+    o, d, u, f, c, res = _frame(world, 2, hw=(17, 23), pad=0)
+    base = torch.zeros(world.voxel_t.shape[0], world.voxel_t.shape[1], world.voxel_t.shape[2] * 2, dtype=torch.int32)
+    base[:, :, ::2] = world.voxel_t
+    strided = base[:, :, ::2]
+    assert not strided.is_contiguous()
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(base.to(DEV)[:, :, ::2], o, d, u, f, c, res, 4)
+    evid, edep, erd = oracle.ray_voxel_intersection_perspective(strided, o, d, u, f, c, res, 4)
+    assert torch.equal(vid.cpu(), evid)
+    assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(edep, nan=-1.0)))
+    # camera looking away from the volume: everything empty, NaN depths, id 0
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV), [500., 128., 128.], [1., 0., 0.],
+                                                           [0., 1., 0.], 30.0, [7.5, 9.5], [16, 20], 6)
+    assert int(vid.abs().sum()) == 0 and bool(torch.isnan(dep).all())
+    # axis-aligned ray (zero direction components -> HUGE_VALF axis times)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV), [200., 100.5, 77.5], [-1., 0., 0.],
+                                                           [0., 1., 0.], 1.0, [0.0, 0.0], [1, 1], 6)
+    evid, edep, _ = oracle.ray_voxel_intersection_perspective(world.voxel_t, [200., 100.5, 77.5], [-1., 0., 0.],
+                                                              [0., 1., 0.], 1.0, [0.0, 0.0], [1, 1], 6)
+    assert torch.equal(vid.cpu(), evid)
+    assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(edep, nan=-1.0)))
+    with pytest.raises(RuntimeError):
+        ops.ray_voxel_intersection_perspective(world.voxel_t, o, d, u, f, c, res, 4)      # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV).float(), o, d, u, f, c, res, 4)
+
+
+def test_dda_bit_exact_vs_reference_cuda(world):
+    ref = load_ref('ref_voxlib')
+    if ref is None:
+        pytest.skip('oracle/_ref/ref_voxlib not built')
+    vox = world.voxel_t.to(DEV)
+    for k, pattern in ((1, 0), (6, 4)):
+        o, d, u, f, c, res = _frame(world, k, hw=(135, 240), pad=30, pattern=pattern)
+        vid, dep, rd = ops.ray_voxel_intersection_perspective(vox, o, d, u, f, c, res, 6)
+        rvid, rdep, rrd = ref.ray_voxel_intersection_perspective(vox, o, d, u, float(f), [float(c[0]), float(c[1])],
+                                                                 [int(res[0]), int(res[1])], 6)
+        assert torch.equal(vid, rvid)
+        assert torch.equal(bits(rd), bits(rrd))
+        assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(rdep, nan=-1.0)))
+
+
+GE_CASES = [
+    # D, C, L, base, log2T, desired, gridtype, B
+    (5, 8, 16, 16, 19, 2048, 0, 4096),      # the SceneDreamer encoder
+    (3, 2, 8, 4, 12, 64, 0, 3000),          # dense + hashed levels mixed
+    (3, 4, 6, 4, 10, 48, 1, 1025),          # tiled
+    (2, 1, 4, 8, 14, 64, 0, 777),
+    (4, 2, 5, 4, 12, 40, 0, 513),
+]
+
+
+def _ge_setup(D, C, L, base, log2T, desired, seed=0, table_scale=0.1):
+    offsets, pls = oracle.grid_offsets(D, L, None, base, log2T, desired)
+    g = torch.Generator().manual_seed(seed)
+    emb = (torch.rand(int(offsets[-1]), C, generator=g) * 2 - 1) * table_scale
+    return offsets, pls, emb, g
+
+
+@pytest.mark.parametrize('D,C,L,base,log2T,desired,gridtype,B', GE_CASES)
+def test_grid_encode_forward_backward_vs_oracle(D, C, L, base, log2T, desired, gridtype, B):
+    offsets, pls, emb, g = _ge_setup(D, C, L, base, log2T, desired)
+    x = torch.rand(B, D, generator=g)
+    x[::97] = 1.2        # out-of-range rows -> zero output, no gradient
+    x[5] = 0.0
+    x[6] = 1.0
+    S = np.log2(pls)
+    out = torch.empty(L, B, C, device=DEV)
+    dy_dx = torch.empty(B, L * D * C, device=DEV)
+    xe, ee, oe = x.to(DEV), emb.to(DEV), offsets.to(DEV)
+    ops.grid_encode_forward(xe, ee, oe, out, B, D, C, L, S, base, True, dy_dx, gridtype, False)
+    eout, edy = oracle.grid_encode_forward(x, emb, offsets, pls, base, True, gridtype, False)
+    np.testing.assert_allclose(out.cpu().numpy(), eout.numpy(), rtol=1e-5, atol=2e-7)
+    np.testing.assert_allclose(dy_dx.cpu().numpy(), edy.numpy(), rtol=1e-4, atol=1e-4 * float(edy.abs().max()))
+    assert float(out[:, ::97].abs().max()) == 0.0
+    grad = torch.randn(L, B, C, generator=g)
+    ge = torch.zeros_like(ee)
+    gi = torch.zeros(B, D, device=DEV)
+    ops.grid_encode_backward(grad.to(DEV), xe, ee, oe, ge, B, D, C, L, S, base, True, dy_dx, gi, gridtype, False)
+    ege, egi = oracle.grid_encode_backward(grad, x, emb, offsets, pls, base, edy, gridtype, False)
+    np.testing.assert_allclose(ge.cpu().numpy(), ege.numpy(), rtol=1e-4, atol=1e-5 * max(1.0, float(ege.abs().max())))
+    np.testing.assert_allclose(gi.cpu().numpy(), egi.numpy(), rtol=1e-3, atol=1e-4 * max(1.0, float(egi.abs().max())))
+    # size-independent properties: linearity of the gradient scatter and conservation of mass
+    ge2 = torch.zeros_like(ee)
+    ops.grid_encode_backward((2 * grad).to(DEV), xe, ee, oe, ge2, B, D, C, L, S, base, False, dy_dx, gi, gridtype, False)
+    np.testing.assert_allclose(ge2.cpu().numpy(), 2 * ge.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    inb = ((x >= 0) & (x <= 1)).all(-1)
+    np.testing.assert_allclose(float(ge.sum()), float(grad[:, inb].sum()), rtol=1e-3, atol=1e-2)
+
+
+def test_grid_encode_unsupported_and_errors():
+    offsets, pls, emb, g = _ge_setup(3, 2, 4, 4, 10, 32)
+    x = torch.rand(16, 3, device=DEV)
+    out = torch.empty(4, 16, 2, device=DEV)
+    dd = torch.empty(1, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.grid_encode_forward(x.cpu(), emb.to(DEV), offsets.to(DEV), out, 16, 3, 2, 4, 1.0, 4, False, dd, 0, False)
+    with pytest.raises(RuntimeError):
+        ops.grid_encode_forward(x, emb.to(DEV), offsets.to(DEV), out, 16, 6, 2, 4, 1.0, 4, False, dd, 0, False)
+    with pytest.raises(RuntimeError):
+        ops.grid_encode_forward(x, emb.to(DEV), offsets.to(DEV), out, 16, 3, 3, 4, 1.0, 4, False, dd, 0, False)
+    with pytest.raises(RuntimeError):
+        ops.grid_encode_forward(x.t().contiguous().t(), emb.to(DEV), offsets.to(DEV), out, 16, 3, 2, 4, 1.0, 4, False, dd, 0, False)
+
+
+def test_grid_encode_vs_reference_cuda():
+    ref = load_ref('ref_gridencoder')
+    if ref is None:
+        pytest.skip('oracle/_ref/ref_gridencoder not built')
+    for (D, C, L, base, log2T, desired, gridtype, B) in GE_CASES[:3]:
+        offsets, pls, emb, g = _ge_setup(D, C, L, base, log2T, desired, seed=3)
+        x = torch.rand(B, D, generator=g).to(DEV)
+        S = np.log2(pls)
+        ee, oe = emb.to(DEV), offsets.to(DEV)
+        out, rout = torch.empty(L, B, C, device=DEV), torch.empty(L, B, C, device=DEV)
+        dd, rdd = torch.empty(B, L * D * C, device=DEV), torch.empty(B, L * D * C, device=DEV)
+        ops.grid_encode_forward(x, ee, oe, out, B, D, C, L, S, base, True, dd, gridtype, False)
+        ref.grid_encode_forward(x, ee, oe, rout, B, D, C, L, S, base, True, rdd, gridtype, False)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(out.cpu().numpy(), rout.cpu().numpy(), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(dd.cpu().numpy(), rdd.cpu().numpy(), rtol=1e-5, atol=1e-5 * float(rdd.abs().max()))
+        grad = torch.randn(L, B, C, generator=g).to(DEV)
+        ge, rge = torch.zeros_like(ee), torch.zeros_like(ee)
+        gi, rgi = torch.zeros(B, D, device=DEV), torch.zeros(B, D, device=DEV)
+        ops.grid_encode_backward(grad, x, ee, oe, ge, B, D, C, L, S, base, True, dd, gi, gridtype, False)
+        ref.grid_encode_backward(grad, x, ee, oe, rge, B, D, C, L, S, base, True, rdd, rgi, gridtype, False)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(ge.cpu().numpy(), rge.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(gi.cpu().numpy(), rgi.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(rgi.abs().max()))
+
+
+def test_positional_encoding_vs_oracle_and_reference():
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(37, 50, 1, 3, generator=g) * 2 - 1)
+    y = ops.positional_encoding(x.to(DEV), 5, -1, True)
+    assert y.shape == (37, 50, 1, 33)
+    # the reference's own self-check tolerance (positional_encoding.py:63)
+    np.testing.assert_allclose(y.cpu().numpy(), oracle.positional_encoding_pt(x, 5, -1, True).numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(y.cpu().numpy(), oracle.positional_encoding(x, 5, -1, True).numpy(), rtol=1e-5, atol=1e-5)
+    x2 = torch.rand(6, 5, 7, generator=g) * 8
+    y2 = ops.positional_encoding(x2.to(DEV), 4, 1, False)
+    assert y2.shape == (6, 40, 7)
+    np.testing.assert_allclose(y2.cpu().numpy(), oracle.positional_encoding_pt(x2, 4, 1, False).numpy(), rtol=1e-4, atol=1e-4)
+    gy = torch.randn(y.shape, generator=g)
+    gx = ops.positional_encoding_backward(gy.to(DEV), y, 5, -1, True)
+    np.testing.assert_allclose(gx.cpu().numpy(), oracle.positional_encoding_backward(gy, y.cpu(), 5, -1, True).numpy(),
+                               rtol=1e-4, atol=1e-4)
+    ref = load_ref('ref_voxlib')
+    if ref is not None:
+        ry = ref.positional_encoding(x.to(DEV), 5, -1, True)
+        np.testing.assert_allclose(y.cpu().numpy(), ry.cpu().numpy(), rtol=1e-6, atol=1e-6)
+        rgx = ref.positional_encoding_backward(gy.to(DEV), ry, 5, -1, True)
+        np.testing.assert_allclose(gx.cpu().numpy(), rgx.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('N,K,bf16', [(256, 256, False), (256, 128, False), (64, 256, False), (256, 256, True), (32, 16, False)])
+def test_tcgen05_selftest(N, K, bf16):
+    g = torch.Generator().manual_seed(N + K)
+    a = torch.randn(128, K, generator=g).to(DEV)
+    b = torch.randn(N, K, generator=g).to(DEV)
+    c = ops.tc_selftest(a, b, bf16=bf16, variant=0)
+    torch.cuda.synchronize()
+    lo = torch.bfloat16 if bf16 else torch.float16
+    ref = a.to(lo).double() @ b.to(lo).double().t()
+    err = float((c.double() - ref).abs().max())
+    print('tcgen05 selftest N=%d K=%d bf16=%s max abs err %.3e (ref max %.2f)' % (N, K, bf16, err, float(ref.abs().max())))
+    assert err < 1e-3 * max(1.0, float(ref.abs().max()))
