@@ -97,65 +97,72 @@ int sdb_positional_encoding_backward(const float *d_out_grad, const float *d_out
  * See sdb_render_params below and DESIGN.md for layouts.
  * ------------------------------------------------------------------------------------------ */
 typedef struct sdb_render_params {
-    /* rays (outputs of a1), R = number of rays */
-    int64_t R;
-    int32_t M;                   /* slots per ray (num_blocks_early_stop)                     */
-    int32_t S;                   /* samples per ray (num_samples); S+1 stratification points  */
+    /* rays (outputs of a1): n_img images of H x W rays, R = n_img*H*W, row-major like the reference */
+    int32_t n_img, H, W;
+    int32_t M;                   /* slots per ray (num_blocks_early_stop), 1..8               */
+    int32_t S;                   /* samples per ray (num_samples), 1..64; S+1 strata points   */
     const int32_t *d_voxel_id;   /* [R, M]                                                    */
-    const float *d_depth2;       /* [2, R, M]                                                 */
+    const float *d_depth2;       /* [n_img][2][H*W][M] (reference layout [N,2,H,W,M,1])       */
     const float *d_raydirs;      /* [R, 3]                                                    */
-    float cam_ori[3];
+    const float *d_cam_ori;      /* [n_img, 3] device                                         */
     float voxel_dims[3];         /* normalisation of world coords (scenedreamer.py:298-299)   */
-    float global_enc[2];         /* scene code appended as dims 3,4 (scenedreamer.py:300-302) */
+    const float *d_global_enc;   /* [n_img, 2] device: scene code = encoder dims 3,4 (:300-302)*/
     float sample_depth;          /* mc_utils.py:107                                           */
     float dists_scale;           /* scenedreamer.py:373                                       */
-    /* sampling positions: S+1 fractions in (0,1) (deterministic linspace, mc_utils.py:118-120)
-       or NULL with d_uniforms [R, S+1] given (stratified branch, :122-125)                    */
+    /* sampling positions along the ray.  Deterministic branch (mc_utils.py:118-120):
+       d_fractions[S+1] = linspace(0,1,S+3)[1:-1], d_uniforms = NULL.  Stratified branch
+       (:122-125): d_uniforms [R, S+1] in [0,1) and d_fractions[S+1] = linspace(0,1,S+2)[:-1].  */
     const float *d_fractions;
     const float *d_uniforms;
-    /* label translation: reduced label per Minecraft id, ignore already mapped to dirt
-       (mc_utils.py:241-246), n_lut entries                                                    */
+    /* label translation: reduced label per Minecraft id with ignore already mapped to dirt
+       (mc_utils.py:241-246); labels must be < 16                                              */
     const int32_t *d_label_lut;
     int32_t n_lut;
-    /* hash grid (D=5, C=8, all levels hashed with T = 2^log2_T): either the raw 5-D table
-       [L*T, 8] (d_table, exact reference arithmetic, 32 corners) or the per-scene pre-blended
-       3-D table from sdb_preblend_table (d_table3, 8 corners).  Exactly one is non-NULL.      */
+    /* hash grid, D=5, C=8, every level hashed with T = 2^log2_T entries:
+       d_table  = raw 5-D table [L*T, 8] (exact reference arithmetic, 32 corners / level), or
+       d_table3 = per-scene pre-blended table from sdb_preblend_table (8 corners / level;
+                  needs n_img == 1 or identical global_enc).  Exactly one is non-NULL.         */
     const float *d_table;
     const float *d_table3;
-    int32_t L;
+    int32_t L;                   /* 16                                                        */
     int32_t log2_T;
     float level_S;               /* log2(per_level_scale)                                     */
     int32_t base_res;
-    /* MLP weights, packed by sdb_pack_mlp() for one style code                                */
+    /* MLP weights packed by sdb_pack_mlp(): one pack per image (style code), stride bytes     */
     const void *d_mlp_pack;
-    /* sky features per ray [R, 64] (SKYMLP output) and the frame-global mean [64]             */
+    int64_t mlp_pack_stride;     /* 0 = all images share one pack                             */
+    int32_t precision;           /* must match the pack: 0 = fp16 x1, 1 = bf16 x3 (fp32-grade) */
+    /* sky: SKYMLP output per ray [R, 64] and the per-image mean [n_img, 64]                   */
     const float *d_sky;
     const float *d_sky_avg;
     /* outputs */
     float *d_net_out;            /* [R, 64]                                                   */
     float *d_depth_out;          /* [R] sum w*t (scenedreamer.py:816) or NULL                 */
     float *d_total_weight;       /* [R] or NULL                                               */
-    int32_t precision;           /* 0: fp16 x1 tensor pass, 1: bf16 x3 split (fp32-grade)     */
+    /* scratch: sdb_render_workspace_bytes(n_img, H, W) bytes                                  */
+    void *d_workspace;
 } sdb_render_params;
 
+int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W);
 int sdb_render_rays_forward(const sdb_render_params *p, void *stream);
 
 /* Per-scene collapse of the two constant encoder dimensions (inference only):
  * table3[l][i] = sum_j w_j(l) * table[l][i ^ K_j(l)], j over the 4 (dim3,dim4) corners.
  * d_table [L*T, 8] -> d_table3 [L*T, 8].  ("parity-preserving work
- * reductions"; valid because every level is hashed and T is a power of two.)                  */
+ * reductions"; valid because every level is hashed and T is a power of two.)
+ * d_global_enc: 2 floats on the device.                                                       */
 int sdb_preblend_table(const float *d_table, float *d_table3, int32_t L, int32_t log2_T, float level_S,
-                       int32_t base_res, const float global_enc[2], void *stream);
+                       int32_t base_res, const float *d_global_enc, void *stream);
 
-/* Size in bytes of the packed MLP image, and the packer.  Inputs are DEVICE fp32 row-major
- * matrices of the style-modulated network for ONE style code:
- *   w1 [256,128] b1 [256]; emb [12,256] (= fc_m_a.weight^T rows per label);
- *   wh [5][256,256] (fc_2..fc_6 weight * alpha, per input column) bh [5][256] (beta);
+/* Size in bytes of the packed MLP image for a precision mode, and the packer.  Inputs are DEVICE
+ * fp32 row-major matrices of the style-modulated network for ONE style code:
+ *   w1 [256,128] b1 [256]; emb [n_labels<=16, 256] (row k = fc_m_a.weight[:, k]);
+ *   wh [5][256,256] (fc_2..fc_6: weight * alpha per input column) bh [5][256] (beta);
  *   wsig [256] bsig [1]; wout [64,256] bout [64].                                             */
-int64_t sdb_mlp_pack_bytes(void);
-int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, const float *d_wh,
-                 const float *d_bh, const float *d_wsig, const float *d_bsig, const float *d_wout,
-                 const float *d_bout, void *d_pack, void *stream);
+int64_t sdb_mlp_pack_bytes(int32_t precision);
+int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, int32_t n_labels,
+                 const float *d_wh, const float *d_bh, const float *d_wsig, const float *d_bsig,
+                 const float *d_wout, const float *d_bout, int32_t precision, void *d_pack, void *stream);
 
 /* tcgen05 / TMEM self test: C[128,N] = A[128,K] * B[N,K]^T with the exact smem descriptors the
  * fused kernel uses.  d_a, d_b fp32 inputs (rounded to fp16/bf16 inside), d_c fp32 output.

@@ -178,7 +178,7 @@ static inline uint32_t grid_index(uint32_t D, uint32_t C, uint32_t gridtype, int
 void sdo_grid_encode_forward(const float *inputs, const float *embeddings, const int32_t *offsets,
                              float *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
                              float S, uint32_t H, int calc_grad_inputs, float *dy_dx,
-                             uint32_t gridtype, int align_corners)
+                             uint32_t gridtype, int align_corners, const float *level_scales)
 {
 #pragma omp parallel for schedule(static)
     for (int64_t bl = 0; bl < (int64_t)B * L; bl++) {
@@ -198,7 +198,9 @@ void sdo_grid_encode_forward(const float *inputs, const float *embeddings, const
             continue;
         }
         const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-        const float scale = exp2f((float)level * S) * (float)H - 1.0f;
+        /* level_scales (optional) overrides exp2f(): CUDA's exp2f may differ from libm's by 1 ulp,
+           which moves samples by ~1e-4 cells at the finest level; tests pass device-computed values */
+        const float scale = level_scales ? level_scales[level] : exp2f((float)level * S) * (float)H - 1.0f;
         const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
 
         float pos[SDO_MAX_D];
@@ -249,7 +251,8 @@ void sdo_grid_encode_forward(const float *inputs, const float *embeddings, const
 void sdo_grid_encode_backward(const float *grad, const float *inputs, const float *embeddings,
                               const int32_t *offsets, float *grad_embeddings, uint32_t B, uint32_t D,
                               uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
-                              const float *dy_dx, float *grad_inputs, uint32_t gridtype, int align_corners)
+                              const float *dy_dx, float *grad_inputs, uint32_t gridtype, int align_corners,
+                              const float *level_scales)
 {
     (void)embeddings;
     /* levels write disjoint slices of grad_embeddings -> parallel over levels is race-free */
@@ -257,7 +260,7 @@ void sdo_grid_encode_backward(const float *grad, const float *inputs, const floa
     for (int level = 0; level < (int)L; level++) {
         float *gg = grad_embeddings + (size_t)(uint32_t)offsets[level] * C;
         const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-        const float scale = exp2f((float)level * S) * (float)H - 1.0f;
+        const float scale = level_scales ? level_scales[level] : exp2f((float)level * S) * (float)H - 1.0f;
         const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
         for (uint32_t b = 0; b < B; b++) {
             const float *x = inputs + (size_t)b * D;

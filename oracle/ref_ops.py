@@ -99,8 +99,21 @@ def grid_offsets(input_dim=5, num_levels=16, per_level_scale=None, base_resoluti
     return torch.from_numpy(np.array(offsets, dtype=np.int32)), float(per_level_scale)
 
 
+def level_scales_libm(L, per_level_scale, base_resolution):
+    S = np.float32(np.log2(per_level_scale))
+    return torch.tensor([np.exp2(np.float32(np.float32(l) * S), dtype=np.float32) * np.float32(base_resolution)
+                         - np.float32(1.0) for l in range(L)], dtype=torch.float32)
+
+
+def _scales_ptr(level_scales):
+    if level_scales is None:
+        return None, None
+    t = _f32(level_scales)
+    return t, _p(t, ctypes.c_float)
+
+
 def grid_encode_forward(inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False,
-                        gridtype=0, align_corners=False):
+                        gridtype=0, align_corners=False, level_scales=None):
     """inputs [B,D] in [0,1] -> (outputs [L,B,C], dy_dx [B,L*D*C] or None); the raw kernel contract."""
     inputs, embeddings = _f32(inputs), _f32(embeddings)
     offsets = offsets.to(torch.int32).cpu().contiguous()
@@ -109,17 +122,18 @@ def grid_encode_forward(inputs, embeddings, offsets, per_level_scale, base_resol
     S = np.log2(per_level_scale)
     out = torch.empty(L, B, C, dtype=torch.float32)
     dy_dx = torch.empty(B, L * D * C, dtype=torch.float32) if calc_grad_inputs else None
+    _keep, sp = _scales_ptr(level_scales)
     _lib().sdo_grid_encode_forward(
         _p(inputs, ctypes.c_float), _p(embeddings, ctypes.c_float), _p(offsets, ctypes.c_int32),
         _p(out, ctypes.c_float), ctypes.c_uint32(B), ctypes.c_uint32(D), ctypes.c_uint32(C), ctypes.c_uint32(L),
         ctypes.c_float(S), ctypes.c_uint32(base_resolution), ctypes.c_int(bool(calc_grad_inputs)),
         _p(dy_dx, ctypes.c_float) if calc_grad_inputs else None, ctypes.c_uint32(gridtype),
-        ctypes.c_int(bool(align_corners)))
+        ctypes.c_int(bool(align_corners)), sp)
     return out, dy_dx
 
 
 def grid_encode_backward(grad, inputs, embeddings, offsets, per_level_scale, base_resolution, dy_dx=None,
-                         gridtype=0, align_corners=False):
+                         gridtype=0, align_corners=False, level_scales=None):
     """grad [L,B,C] -> (grad_embeddings, grad_inputs or None)."""
     grad, inputs, embeddings = _f32(grad), _f32(inputs), _f32(embeddings)
     offsets = offsets.to(torch.int32).cpu().contiguous()
@@ -131,22 +145,23 @@ def grid_encode_backward(grad, inputs, embeddings, offsets, per_level_scale, bas
     gi = torch.zeros(B, D, dtype=torch.float32) if calc else None
     if calc:
         dy_dx = _f32(dy_dx)
+    _keep, sp = _scales_ptr(level_scales)
     _lib().sdo_grid_encode_backward(
         _p(grad, ctypes.c_float), _p(inputs, ctypes.c_float), _p(embeddings, ctypes.c_float),
         _p(offsets, ctypes.c_int32), _p(ge, ctypes.c_float), ctypes.c_uint32(B), ctypes.c_uint32(D),
         ctypes.c_uint32(C), ctypes.c_uint32(L), ctypes.c_float(S), ctypes.c_uint32(base_resolution),
         ctypes.c_int(calc), _p(dy_dx, ctypes.c_float) if calc else None,
-        _p(gi, ctypes.c_float) if calc else None, ctypes.c_uint32(gridtype), ctypes.c_int(bool(align_corners)))
+        _p(gi, ctypes.c_float) if calc else None, ctypes.c_uint32(gridtype), ctypes.c_int(bool(align_corners)), sp)
     return ge, gi
 
 
 def grid_encoder_module_forward(inputs, embeddings, offsets, per_level_scale, base_resolution=16, bound=1,
-                                gridtype=0, align_corners=False):
+                                gridtype=0, align_corners=False, level_scales=None):
     """GridEncoder.forward (gridencoder/grid.py:140-156): [-bound,bound] -> [0,1], encode, [.., L*C]."""
     x = (_f32(inputs) + bound) / (2 * bound)
     prefix = list(x.shape[:-1])
     out, _ = grid_encode_forward(x.reshape(-1, x.shape[-1]), embeddings, offsets, per_level_scale,
-                                 base_resolution, False, gridtype, align_corners)
+                                 base_resolution, False, gridtype, align_corners, level_scales)
     L, B, C = out.shape
     return out.permute(1, 0, 2).reshape(prefix + [L * C])
 
@@ -388,7 +403,7 @@ def make_params(seed=0, stress=False, style_dim=128, interm=256, hidden=256, fea
 def forward_perpix(P, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc, voxel_dims, mc2reduced_lut,
                    offsets, per_level_scale, num_samples=24, sample_depth=3.0, deterministic=True,
                    uniforms=None, dists_scale=0.25, sky_avg=None, ignore_id=0, dirt_id=3,
-                   pe_sky=(5, True), base_resolution=16, chunk_rays=16384):
+                   pe_sky=(5, True), base_resolution=16, chunk_rays=16384, level_scales=None):
     """Restates Generator._forward_perpix for the SceneDreamer inference/training configuration
     (clip_feat_map=True, keep_sky_out=True, keep_sky_out_avgpool=True, sky_global_avgpool=True,
     sample_use_box_boundaries=False, raw_noise_std=0, viewdir PE disabled).
@@ -426,7 +441,7 @@ def forward_perpix(P, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc, voxel
         for r0 in range(0, H * W, chunk_rays):
             r1 = min(H * W, r0 + chunk_rays)
             feat = grid_encoder_module_forward(nflat[n, r0:r1], P['hash_encoder.embeddings'], offsets,
-                                               per_level_scale, base_resolution)
+                                               per_level_scale, base_resolution, level_scales=level_scales)
             s_, c_ = render_mlp(feat.reshape(1, -1, feat.shape[-1]), z[n:n + 1],
                                 lflat[n, r0:r1].reshape(1, -1), P)
             sig[n, r0:r1] = s_.reshape(r1 - r0, S, 1)

@@ -25,15 +25,14 @@ SIGNATURES = {
                                          c_u32, c_f32, c_u32, c_int, c_void_p, c_void_p, c_u32, c_int, c_void_p]),
     'sdb_positional_encoding': (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_int, c_void_p]),
     'sdb_positional_encoding_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_int, c_void_p]),
+    'sdb_render_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
     'sdb_render_rays_forward': (c_int, [c_void_p, c_void_p]),
-    'sdb_preblend_table': (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_f32, c_i32, _F3, c_void_p]),
-    'sdb_mlp_pack_bytes': (c_i64, []),
-    'sdb_pack_mlp': (c_int, [c_void_p] * 10 + [c_void_p]),
+    'sdb_preblend_table': (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_f32, c_i32, c_void_p, c_void_p]),
+    'sdb_mlp_pack_bytes': (c_i64, [c_i32]),
+    'sdb_pack_mlp': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_i32, c_void_p, c_void_p]),
     'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
 }
-
-
-_PENDING = ('sdb_render_rays_forward', 'sdb_preblend_table', 'sdb_mlp_pack_bytes', 'sdb_pack_mlp')
 
 
 def lib():
@@ -48,8 +47,6 @@ def lib():
                                'this package has no CPU or PyTorch fallback' % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            if name in _PENDING and not hasattr(L, name):
-                continue
             fn = getattr(L, name)          # AttributeError here == header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args

@@ -1,0 +1,809 @@
+// Fused per-pixel render for sm_100a: depth sampling -> label lookup -> hash-grid features ->
+// style-modulated sigma/colour MLP on tcgen05 tensor cores -> front-to-back compositing + sky blend.
+//
+// Behavioural contract = Generator._forward_perpix of the reference and the tile loop around it
+// (imaginaire/generators/scenedreamer.py:285-428, :600-628) with its callees
+//   mc_utils.sample_depth_batched        mc_utils.py:82-151     (a2)
+//   NaN guard / world coords / labels    scenedreamer.py:350-363 (a3, a4)
+//   normalise + scene code + GridEncoder scenedreamer.py:298-303, gridencoder.cu:75-170 (a5, a6)
+//   LightningMLP / ModLinear             model_utils/layers.py:92-126, :241-271 (a8)
+//   volum_rendering_relu + blending      mc_utils.py:154-161, scenedreamer.py:373-413 (a10, a11)
+//
+// Design (DESIGN.md has the long version)
+//   * persistent CTAs (one per SM); a work item is a 16x8-pixel ray tile = 128 rays = the M of one
+//     tcgen05 MMA; row r of every GEMM is ray r, the tile is walked sample by sample (s = 0..S-1),
+//     so compositing is a per-thread running sum (no cross-thread reduction, any S);
+//   * warp roles: 4 epilogue warps (TMEM -> bias/LeakyReLU -> 16-bit operand in smem; sigma tap;
+//     compositing), 1 weight-loader warp (1-D bulk TMA into a 4-stage ring), 1 MMA-issuer warp,
+//     8 gather warps (hash-grid fetch for the NEXT sample step while the MLP of the current one
+//     runs; results wait in registers until the operand buffer is free);
+//   * activations stay on chip: TMEM accumulators (256 + 64 columns) and ONE in-place 128x256
+//     operand buffer in shared memory; the only per-sample HBM/L2 traffic is the table gather;
+//   * precision: 0 = one fp16 pass; 1 = bf16 "x3" split (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo,
+//     ~2^-16 relative, i.e. fp32-grade for the 1e-3 parity bar) -- accumulation is fp32 in TMEM;
+//   * sky-only tiles never reach this kernel: a pre-pass writes their outputs and compacts the
+//     list of live tiles (their compositing weights are exactly zero, scenedreamer.py:376).
+#include <math.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace rf {
+
+constexpr int kRows = 128, kTileW = 16, kTileH = 8;
+constexpr int kHidden = 256, kFeat = 128, kOutC = 64, kLevels = 16, kLayers = 7;
+constexpr int kMaxM = 8, kMaxS = 64, kMaxLabels = 16;
+constexpr int kEpiThreads = 128, kGatherThreads = 256;
+constexpr int kLoaderWarp = 4, kMmaWarp = 5, kGatherWarp0 = 6;
+constexpr int kThreads = kEpiThreads + 64 + kGatherThreads;   // 448
+constexpr int kStageBytes = 16384, kStages = 4;
+constexpr uint32_t kTmemCols = 512, kAccCol = 0, kOutCol = 256;
+constexpr uint32_t kLboA = kRows * 16, kSbo = 128;
+
+__host__ __device__ constexpr int layerK(int l) { return l == 0 ? kFeat : kHidden; }
+__host__ __device__ constexpr int layerN(int l) { return l == kLayers - 1 ? kOutC : kHidden; }
+__host__ __device__ constexpr int64_t layerOff(int l, int parts) {
+    int64_t o = 0;
+    for (int j = 0; j < l; j++) o += (int64_t)layerK(j) * layerN(j) * 2 * parts;
+    return o;
+}
+// fp32 tail of the pack (float offsets)
+constexpr int kFBias = 0;            // 6 x 256 (fc_1 bias, beta of fc_2..fc_6)
+constexpr int kFBout = 1536;         // 64
+constexpr int kFWsig = 1600;         // 256
+constexpr int kFBsig = 1856;         // 1
+constexpr int kFEmb = 1864;          // 16 x 256 (label embedding rows)
+constexpr int kFSmemFloats = 1860;   // part staged in shared memory
+constexpr int kFTotal = kFEmb + kMaxLabels * kHidden;
+__host__ __device__ constexpr int64_t packBytes(int parts) { return layerOff(kLayers, parts) + (int64_t)kFTotal * 4; }
+
+// ---- shared memory map ---------------------------------------------------------------------------
+struct Smem {
+    uint32_t h_hi, h_lo, ring, fsec, scales, frac, state, bars, tmem_slot, total;
+};
+__host__ __device__ constexpr Smem smem_map(bool x3) {
+    Smem m{};
+    uint32_t o = 0;
+    m.h_hi = o; o += kRows * kHidden * 2;
+    m.h_lo = o; if (x3) o += kRows * kHidden * 2;
+    m.ring = o; o += kStages * kStageBytes;
+    m.fsec = o; o += ((kFSmemFloats * 4 + 15) / 16) * 16;
+    m.scales = o; o += kLevels * 4;
+    m.frac = o; o += ((kMaxS + 1) * 4 + 15) / 16 * 16;
+    m.state = o; o += 2 * (2 * kMaxM + 6) * kRows * 4;
+    m.bars = o; o += 32 * 8;
+    m.tmem_slot = o; o += 16;
+    m.total = o;
+    return m;
+}
+// per-buffer ray state: float arrays of kRows each
+constexpr int kStAccu = 0;                   // [kMaxM]
+constexpr int kStHeads = kMaxM;              // [kMaxM]
+constexpr int kStTotal = 2 * kMaxM;          // 1
+constexpr int kStDir = 2 * kMaxM + 1;        // 3
+constexpr int kStLab = 2 * kMaxM + 4;        // 1 (uint32: 4 bits per slot)
+constexpr int kStFlags = 2 * kMaxM + 5;      // 1 (uint32: bit0 live, bit1 sky_mask, bit2 valid)
+constexpr int kStFloats = 2 * kMaxM + 6;
+
+// barrier indices
+enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_ACT, B_ACC, B_OUTRDY, B_OUTFREE, B_STRDY, B_STFREE = B_STRDY + 2,
+       B_COUNT = B_STFREE + 2 };
+
+struct Params {
+    int n_img, H, W, M, S;
+    const int32_t *voxel_id;
+    const float *depth2, *raydirs, *cam_ori, *genc;
+    float vdim[3];
+    float sample_depth, dists_scale;
+    const float *fractions, *uniforms;
+    const int32_t *lut;
+    int n_lut;
+    const float *table;
+    int raw5d;
+    int log2_T;
+    float level_S;
+    int base_res;
+    const uint8_t *pack;
+    long long pack_stride;
+    const float *sky, *sky_avg;
+    float *net_out, *depth_out, *total_weight;
+    const int32_t *tile_list;      // [n_live]
+    const int32_t *n_live;
+    int tiles_x, tiles_y;
+};
+
+__device__ __constant__ uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u, kPrime3 = 3674653429u, kPrime4 = 2097192037u;
+
+struct TileCoord { int img, y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    TileCoord t;
+    t.img = tile / per_img;
+    const int r = tile - t.img * per_img;
+    t.y0 = (r / p.tiles_x) * kTileH;
+    t.x0 = (r % p.tiles_x) * kTileW;
+    return t;
+}
+
+// ---- sampling (a2/a3) ------------------------------------------------------------------------------
+struct Sample { float depth, nd; int idx; };
+
+__device__ __forceinline__ Sample sample_at(const Params &p, const float *st, int row, int k, const float *frac,
+                                            long long ray) {
+    const float total = st[kStTotal * kRows + row];
+    float r0, r1;
+    if (p.uniforms == nullptr) {          // deterministic: linspace fractions * total (mc_utils.py:118-126)
+        r0 = __fmul_rn(frac[k], total);
+        r1 = __fmul_rn(frac[k + 1], total);
+    } else {                              // stratified: (u / nsamples + k / nsamples) * total (:122-126)
+        const float ns = (float)(p.S + 1);
+        const float u0 = __ldg(p.uniforms + ray * (p.S + 1) + k), u1 = __ldg(p.uniforms + ray * (p.S + 1) + k + 1);
+        r0 = __fmul_rn(__fadd_rn(__fdiv_rn(u0, ns), frac[k]), total);
+        r1 = __fmul_rn(__fadd_rn(__fdiv_rn(u1, ns), frac[k + 1]), total);
+    }
+    Sample s;
+    const float mid = __fmul_rn(__fadd_rn(r1, r0), 0.5f);     // (a + b) / 2 (:134)
+    s.nd = __fsub_rn(r1, r0);                                   // :135
+    int idx = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxM; j++)
+        if (j < p.M && mid > st[(kStAccu + j) * kRows + row]) idx++;   // :139 (strict >)
+    if (idx > p.M - 1) idx = p.M - 1;
+    s.idx = idx;
+    float d = __fadd_rn(st[(kStHeads + idx) * kRows + row], mid);      // :145-149
+    if (!(fabsf(d) <= 3.402823466e38f)) d = 0.0f;                      // NaN / inf -> 0 (scenedreamer.py:350-352)
+    s.depth = d;
+    return s;
+}
+
+// ---- gather (a5/a6) ----------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(const float *g, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(g) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <bool RAW5D>
+__device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint32_t mask, float scale, const float (&x)[5],
+                                             float (&res)[8]) {
+    // gridencoder.cu:133-170.  pos = x*scale + 0.5 is one FFMA in the reference's device code.
+    constexpr int D = RAW5D ? 5 : 3;
+    float f[D];
+    uint32_t g[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const float pos = fmaf(x[d], scale, 0.5f);
+        const float fl = floorf(pos);
+        g[d] = (uint32_t)fl;
+        f[d] = pos - (float)g[d];
+    }
+    const uint32_t h0[2] = {g[0], g[0] + 1u};
+    const uint32_t h1[2] = {g[1] * kPrime1, (g[1] + 1u) * kPrime1};
+    const uint32_t h2[2] = {g[2] * kPrime2, (g[2] + 1u) * kPrime2};
+#pragma unroll
+    for (int c = 0; c < 8; c++) res[c] = 0.0f;
+    if constexpr (RAW5D) {
+        const uint32_t h3[2] = {g[3] * kPrime3, (g[3] + 1u) * kPrime3};
+        const uint32_t h4[2] = {g[4] * kPrime4, (g[4] + 1u) * kPrime4};
+#pragma unroll
+        for (int idx = 0; idx < 32; idx++) {
+            const int b0 = idx & 1, b1 = (idx >> 1) & 1, b2 = (idx >> 2) & 1, b3 = (idx >> 3) & 1, b4 = (idx >> 4) & 1;
+            float w = b0 ? f[0] : 1.0f - f[0];
+            w *= b1 ? f[1] : 1.0f - f[1];
+            w *= b2 ? f[2] : 1.0f - f[2];
+            w *= b3 ? f[3] : 1.0f - f[3];
+            w *= b4 ? f[4] : 1.0f - f[4];
+            const uint32_t index = (h0[b0] ^ h1[b1] ^ h2[b2] ^ h3[b3] ^ h4[b4]) & mask;
+            float v[8];
+            ld8(tbl + (size_t)index * 8, v);
+#pragma unroll
+            for (int c = 0; c < 8; c++) res[c] = fmaf(w, v[c], res[c]);
+        }
+    } else {
+#pragma unroll
+        for (int idx = 0; idx < 8; idx++) {
+            const int b0 = idx & 1, b1 = (idx >> 1) & 1, b2 = (idx >> 2) & 1;
+            float w = b0 ? f[0] : 1.0f - f[0];
+            w *= b1 ? f[1] : 1.0f - f[1];
+            w *= b2 ? f[2] : 1.0f - f[2];
+            const uint32_t index = (h0[b0] ^ h1[b1] ^ h2[b2]) & mask;
+            float v[8];
+            ld8(tbl + (size_t)index * 8, v);
+#pragma unroll
+            for (int c = 0; c < 8; c++) res[c] = fmaf(w, v[c], res[c]);
+        }
+    }
+}
+
+// 8 fp32 values -> one 16-byte chunk of 16-bit operand (hi) and, for the x3 split, the residual (lo)
+template <bool X3>
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+    if constexpr (X3) {
+        // hi = v truncated to bf16 (exactly representable), lo = bf16(v - hi): |err| <= 2^-16 |v|
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t a = __float_as_uint(v[2 * q]), b = __float_as_uint(v[2 * q + 1]);
+            h[q] = __byte_perm(a, b, 0x7632);
+            const float la = v[2 * q] - __uint_as_float(a & 0xFFFF0000u);
+            const float lb = v[2 * q + 1] - __uint_as_float(b & 0xFFFF0000u);
+            l[q] = tc05::pack2<true>(la, lb);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) { h[q] = tc05::pack2<false>(v[2 * q], v[2 * q + 1]); l[q] = 0; }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+template <bool X3, bool RAW5D>
+__global__ void __launch_bounds__(kThreads, 1)
+render_kernel(const Params p)
+{
+    constexpr Smem SM = smem_map(X3);
+    constexpr int PARTS = X3 ? 2 : 1;
+    constexpr int KS = X3 ? 1 : 2;                 // k16 steps per ring stage
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sHhi = smem + SM.h_hi;
+    uint8_t *sHlo = smem + SM.h_lo;
+    uint8_t *sRing = smem + SM.ring;
+    float *sF = reinterpret_cast<float *>(smem + SM.fsec);
+    float *sScale = reinterpret_cast<float *>(smem + SM.scales);
+    float *sFrac = reinterpret_cast<float *>(smem + SM.frac);
+    float *sState = reinterpret_cast<float *>(smem + SM.state);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM.bars);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM.tmem_slot);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_live = *p.n_live;
+    const int n_iter = (n_live > (int)blockIdx.x) ? (n_live - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        for (int i = 0; i < kStages; i++) { tc05::mbar_init(&bars[B_WFULL + i], 1); tc05::mbar_init(&bars[B_WEMPTY + i], 1); }
+        tc05::mbar_init(&bars[B_FEAT], kGatherThreads);
+        tc05::mbar_init(&bars[B_HFREE], 1);
+        tc05::mbar_init(&bars[B_ACT], kEpiThreads);
+        tc05::mbar_init(&bars[B_ACC], 1);
+        tc05::mbar_init(&bars[B_OUTRDY], 1);
+        tc05::mbar_init(&bars[B_OUTFREE], kEpiThreads);
+        for (int i = 0; i < 2; i++) { tc05::mbar_init(&bars[B_STRDY + i], kRows); tc05::mbar_init(&bars[B_STFREE + i], kEpiThreads); }
+        tc05::fence_mbar_init();
+    }
+    if (warp == kLoaderWarp) tc05::tmem_alloc(tmem_slot, kTmemCols);
+    for (int i = tid; i < kLevels; i += kThreads) sScale[i] = exp2f(i * p.level_S) * p.base_res - 1.0f;   // gridencoder.cu:126
+    for (int i = tid; i <= p.S; i += kThreads) sFrac[i] = p.fractions[i];
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    tc05::fence_after_thread_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t mask = (1u << p.log2_T) - 1u;
+
+    if (warp < 4) {
+        // =========================== EPILOGUE / COMPOSITING WARPS ===========================
+        const int row = tid;
+        const uint32_t tm_row = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t n = 0;                 // global step counter
+        int loaded_img = -1;
+        for (int it = 0; it < n_iter; it++) {
+            const int tile = p.tile_list[blockIdx.x + it * gridDim.x];
+            const TileCoord tc = tile_coord(p, tile);
+            const int buf = it & 1;
+            const float *st = sState + buf * kStFloats * kRows;
+            const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
+            const float *packF = reinterpret_cast<const float *>(pack + layerOff(kLayers, PARTS));
+            if (loaded_img != tc.img) {
+                // the fp32 tail (biases, sigma weights) of this image's pack -> shared memory.  All 128
+                // epilogue threads are the only readers; a named barrier orders the refill.
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = tid; i < kFSmemFloats; i += kEpiThreads) sF[i] = __ldg(packF + i);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                loaded_img = tc.img;
+            }
+            tc05::mbar_wait(&bars[B_STRDY + buf], (it >> 1) & 1);
+            const uint32_t flags = __float_as_uint(st[kStFlags * kRows + row]);
+            const uint32_t labs = __float_as_uint(st[kStLab * kRows + row]);
+            const bool live = flags & 1u, valid = flags & 4u;
+            const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
+            const long long ray = ((long long)tc.img * p.H + y) * p.W + x;
+            const float dir0 = st[(kStDir + 0) * kRows + row];
+            const float ori0 = __ldg(p.cam_ori + tc.img * 3);
+            float outc[kOutC];
+#pragma unroll
+            for (int c = 0; c < kOutC; c++) outc[c] = 0.0f;
+            float Wsum = 0.0f, Dsum = 0.0f, Eexcl = 0.0f;
+            bool is_gnd = false;
+
+            for (int s = 0; s < p.S; s++, n++) {
+                const Sample sm = sample_at(p, st, row, s, sFrac, ray);
+                const int label = (labs >> (4 * sm.idx)) & 15u;
+                is_gnd = is_gnd || (__fadd_rn(__fmul_rn(dir0, sm.depth), ori0) <= 1.0f);   // scenedreamer.py:354,380
+                float sigma = 0.0f;
+#pragma unroll 1
+                for (int l = 0; l < 6; l++) {
+                    tc05::mbar_wait(&bars[B_ACC], (n * 6 + l) & 1);
+                    tc05::fence_after_thread_sync();
+                    const float *bias = sF + kFBias + l * kHidden;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < kHidden; c0 += 32) {
+                        float v[32];
+                        tc05::tmem_ld32(tm_row + kAccCol + c0, v);
+                        tc05::tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 b = *reinterpret_cast<const float4 *>(bias + c0 + 4 * q);
+                            v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                        }
+                        if (l == 0) {   // + fc_m_a(onehot) == embedding row of the sample's label (layers.py:103-105)
+                            const float4 *e4 = reinterpret_cast<const float4 *>(packF + kFEmb + label * kHidden + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const float4 e = __ldg(e4 + q);
+                                v[4 * q + 0] += e.x; v[4 * q + 1] += e.y; v[4 * q + 2] += e.z; v[4 * q + 3] += e.w;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.2f * v[j]);          // LeakyReLU(0.2)
+                        if (l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
+                            const float *ws = sF + kFWsig + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) sigma = fmaf(v[j], ws[j], sigma);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            uint4 hi, lo;
+                            const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
+                            split8<X3>(v8, hi, lo);
+                            const uint32_t off = tc05::chunk_off(kRows, row, (c0 >> 3) + q);
+                            *reinterpret_cast<uint4 *>(sHhi + off) = hi;
+                            if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
+                        }
+                    }
+                    tc05::fence_proxy_async_smem();
+                    tc05::fence_before_thread_sync();
+                    tc05::mbar_arrive(&bars[B_ACT]);
+                }
+                sigma += sF[kFBsig];
+                // ---- colour layer + compositing (a10/a11) ----
+                tc05::mbar_wait(&bars[B_OUTRDY], n & 1);
+                tc05::fence_after_thread_sync();
+                float c[kOutC];
+                {
+                    float v[32];
+                    tc05::tmem_ld32(tm_row + kOutCol, v);
+                    tc05::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) c[j] = v[j];
+                    tc05::tmem_ld32(tm_row + kOutCol + 32, v);
+                    tc05::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) c[32 + j] = v[j];
+                }
+                tc05::fence_before_thread_sync();
+                tc05::mbar_arrive(&bars[B_OUTFREE]);
+                const float e = __fmul_rn(fmaxf(sigma, 0.0f), __fmul_rn(sm.nd, p.dists_scale));   // mc_utils.py:155
+                const float a = 1.0f - expf(-e);
+                const float b = expf(-Eexcl);
+                float w = a * b;
+                Eexcl = __fadd_rn(Eexcl, e);
+                w = live ? w : 0.0f;                                                              // scenedreamer.py:376
+                Wsum += w;
+                Dsum = fmaf(w, sm.depth, Dsum);
+                const float *bo = sF + kFBout;
+#pragma unroll
+                for (int j = 0; j < kOutC; j++) {
+                    const float rgb = fminf(fmaxf(c[j] + bo[j], -1.0f), 1.0f) + 1.0f;              // :407-408
+                    outc[j] = fmaf(w, rgb, outc[j]);
+                }
+            }
+            // ---- finalize the tile (sky blend, scenedreamer.py:380-413) ----
+            if (valid) {
+                const bool sky_mask = flags & 2u;
+                const bool nosky = (!sky_mask) || is_gnd;
+                const float sky_w = 1.0f - Wsum;
+                const float4 *skp = reinterpret_cast<const float4 *>((nosky ? p.sky_avg + (long long)tc.img * kOutC
+                                                                             : p.sky + ray * kOutC));
+                float4 *dst = reinterpret_cast<float4 *>(p.net_out + ray * kOutC);
+#pragma unroll
+                for (int q = 0; q < kOutC / 4; q++) {
+                    const float4 sk = __ldg(skp + q);
+                    float4 o;
+                    o.x = (outc[4 * q + 0] + sky_w * (fminf(fmaxf(sk.x, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                    o.y = (outc[4 * q + 1] + sky_w * (fminf(fmaxf(sk.y, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                    o.z = (outc[4 * q + 2] + sky_w * (fminf(fmaxf(sk.z, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                    o.w = (outc[4 * q + 3] + sky_w * (fminf(fmaxf(sk.w, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                    dst[q] = o;
+                }
+                if (p.depth_out) p.depth_out[ray] = Dsum;
+                if (p.total_weight) p.total_weight[ray] = Wsum;
+            }
+            tc05::mbar_arrive(&bars[B_STFREE + buf]);
+        }
+    } else if (warp == kLoaderWarp) {
+        // =========================== WEIGHT LOADER (1-D bulk TMA) ===========================
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int it = 0; it < n_iter; it++) {
+                const int tile = p.tile_list[blockIdx.x + it * gridDim.x];
+                const TileCoord tc = tile_coord(p, tile);
+                const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
+                for (int s = 0; s < p.S; s++) {
+                    for (int l = 0; l < kLayers; l++) {
+                        const int nstage = layerK(l) / 16 / KS;
+                        const uint32_t bytes = (uint32_t)KS * layerN(l) * 32 * PARTS;
+                        const uint8_t *src = pack + layerOff(l, PARTS);
+                        for (int g = 0; g < nstage; g++, q++) {
+                            const uint32_t stg = q % kStages, par = (q / kStages) & 1;
+                            tc05::mbar_wait(&bars[B_WEMPTY + stg], par ^ 1);
+                            tc05::mbar_arrive_expect_tx(&bars[B_WFULL + stg], bytes);
+                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)g * bytes, bytes, &bars[B_WFULL + stg]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =========================== MMA ISSUER (one thread) ===========================
+        if (lane == 0) {
+            uint32_t q = 0, n = 0;
+            const uint32_t aHi = tc05::smem_u32(sHhi), aLo = tc05::smem_u32(sHlo), ring = tc05::smem_u32(sRing);
+            for (int it = 0; it < n_iter; it++) {
+                for (int s = 0; s < p.S; s++, n++) {
+                    for (int l = 0; l < kLayers; l++) {
+                        if (l == 0) tc05::mbar_wait(&bars[B_FEAT], n & 1);
+                        else tc05::mbar_wait(&bars[B_ACT], (n * 6 + (l - 1)) & 1);
+                        if (l == kLayers - 1 && n > 0) tc05::mbar_wait(&bars[B_OUTFREE], (n - 1) & 1);
+                        tc05::fence_after_thread_sync();
+                        const int N = layerN(l);
+                        const uint32_t idesc = tc05::make_idesc(kRows, N, X3);
+                        const uint32_t dcol = tmem + (l == kLayers - 1 ? kOutCol : kAccCol);
+                        const uint32_t slab = (uint32_t)N * 32, lboB = (uint32_t)N * 16;
+                        const int nk16 = layerK(l) / 16;
+                        for (int kk = 0; kk < nk16; kk++) {
+                            const uint32_t stg = q % kStages, par = (q / kStages) & 1;
+                            if (kk % KS == 0) {
+                                tc05::mbar_wait(&bars[B_WFULL + stg], par);
+                                tc05::fence_after_thread_sync();
+                            }
+                            const uint32_t bbase = ring + stg * kStageBytes + (kk % KS) * slab * PARTS;
+                            const uint64_t dAhi = tc05::make_smem_desc(aHi + kk * 2 * kLboA, kLboA, kSbo);
+                            const uint64_t dBhi = tc05::make_smem_desc(bbase, lboB, kSbo);
+                            tc05::mma_f16_ss(dcol, dAhi, dBhi, idesc, kk > 0 ? 1u : 0u);
+                            if constexpr (X3) {
+                                const uint64_t dAlo = tc05::make_smem_desc(aLo + kk * 2 * kLboA, kLboA, kSbo);
+                                const uint64_t dBlo = tc05::make_smem_desc(bbase + slab, lboB, kSbo);
+                                tc05::mma_f16_ss(dcol, dAlo, dBhi, idesc, 1u);
+                                tc05::mma_f16_ss(dcol, dAhi, dBlo, idesc, 1u);
+                            }
+                            if (kk % KS == KS - 1) {
+                                tc05::mma_commit(&bars[B_WEMPTY + stg]);
+                                q++;
+                            }
+                        }
+                        if (l == kLayers - 1) {
+                            tc05::mma_commit(&bars[B_OUTRDY]);
+                            tc05::mma_commit(&bars[B_HFREE]);
+                        } else {
+                            tc05::mma_commit(&bars[B_ACC]);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== GATHER WARPS (hash-grid fetch) ===========================
+        const int gt = tid - kGatherWarp0 * 32;
+        const int row = gt & (kRows - 1), half = gt >> 7;
+        uint32_t n = 0;
+        for (int it = 0; it < n_iter; it++) {
+            const int tile = p.tile_list[blockIdx.x + it * gridDim.x];
+            const TileCoord tc = tile_coord(p, tile);
+            const int buf = it & 1;
+            float *st = sState + buf * kStFloats * kRows;
+            const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
+            const bool valid = (y < p.H) && (x < p.W);
+            const long long pix = (long long)y * p.W + x, hw = (long long)p.H * p.W;
+            const long long ray = (long long)tc.img * hw + pix;
+            // ---- per-ray sampling state (first 128 gather threads) ----
+            if (it >= 2) tc05::mbar_wait(&bars[B_STFREE + buf], ((it >> 1) - 1) & 1);
+            if (half == 0) {
+                float accu = 0.0f, cum = 0.0f, entry0 = 0.0f, prev_exit = 0.0f;
+                uint32_t labs = 0, flags = 0;
+                int32_t id0 = 0, idl = 0;
+#pragma unroll
+                for (int j = 0; j < kMaxM; j++) {
+                    if (j < p.M) {
+                        float en = 0.0f, ex = 0.0f;
+                        int32_t id = 0;
+                        if (valid) {
+                            id = __ldg(p.voxel_id + ray * p.M + j);
+                            en = __ldg(p.depth2 + ((long long)tc.img * 2 + 0) * hw * p.M + pix * p.M + j);
+                            ex = __ldg(p.depth2 + ((long long)tc.img * 2 + 1) * hw * p.M + pix * p.M + j);
+                        }
+                        float d = __fsub_rn(ex, en);                       // mc_utils.py:102-104
+                        if (d != d) d = 0.0f;
+                        accu = (j == 0) ? d : __fadd_rn(accu, d);
+                        st[(kStAccu + j) * kRows + row] = accu;
+                        if (j == 0) {
+                            entry0 = en;
+                            st[(kStHeads + 0) * kRows + row] = en;
+                        } else {                                           // :141-143
+                            const float dd = __fsub_rn(en, prev_exit);
+                            cum = (j == 1) ? dd : __fadd_rn(cum, dd);
+                            st[(kStHeads + j) * kRows + row] = __fadd_rn(cum, entry0);
+                        }
+                        prev_exit = ex;
+                        int lid = (id >= 0 && id < p.n_lut) ? __ldg(p.lut + id) : 0;
+                        labs |= ((uint32_t)lid & 15u) << (4 * j);
+                        if (j == 0) id0 = id;
+                        idl = id;
+                    }
+                }
+                st[kStTotal * kRows + row] = fminf(accu, p.sample_depth);   // :107
+                flags = (valid && id0 != 0 ? 1u : 0u) | (idl == 0 ? 2u : 0u) | (valid ? 4u : 0u);
+                st[kStLab * kRows + row] = __uint_as_float(labs);
+                st[kStFlags * kRows + row] = __uint_as_float(flags);
+#pragma unroll
+                for (int k = 0; k < 3; k++) st[(kStDir + k) * kRows + row] = valid ? __ldg(p.raydirs + ray * 3 + k) : 0.0f;
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (half == 0) tc05::mbar_arrive(&bars[B_STRDY + buf]);
+            const bool live = __float_as_uint(st[kStFlags * kRows + row]) & 1u;
+            const float d0 = st[(kStDir + 0) * kRows + row], d1 = st[(kStDir + 1) * kRows + row], d2 = st[(kStDir + 2) * kRows + row];
+            const float o0 = __ldg(p.cam_ori + tc.img * 3 + 0), o1 = __ldg(p.cam_ori + tc.img * 3 + 1), o2 = __ldg(p.cam_ori + tc.img * 3 + 2);
+            float x5[5];
+            x5[3] = __fmul_rn(__fadd_rn(__ldg(p.genc + tc.img * 2 + 0), 1.0f), 0.5f);   // grid.py:144 on dims 3,4
+            x5[4] = __fmul_rn(__fadd_rn(__ldg(p.genc + tc.img * 2 + 1), 1.0f), 0.5f);
+
+            for (int s = 0; s < p.S; s++, n++) {
+                uint4 fh[8], fl[8];
+                const Sample sm = sample_at(p, st, row, s, sFrac, ray);
+                // world coordinate, normalisation and [0,1] mapping with the reference's operation order
+                // (scenedreamer.py:354, :299; grid.py:144): p = dir*t + ori; p / dim * 2 - 1; (x + 1) / 2
+                const float pw[3] = {__fadd_rn(__fmul_rn(d0, sm.depth), o0), __fadd_rn(__fmul_rn(d1, sm.depth), o1),
+                                     __fadd_rn(__fmul_rn(d2, sm.depth), o2)};
+                bool oob = !live;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(pw[k], p.vdim[k]), 2.0f), 1.0f);
+                    x5[k] = __fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f);
+                    if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int level = half + 2 * i;
+                    float res[8];
+                    if (oob) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) res[c] = 0.0f;
+                    } else {
+                        encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                    }
+                    split8<X3>(res, fh[i], fl[i]);
+                }
+                if (n > 0) tc05::mbar_wait(&bars[B_HFREE], (n - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t off = tc05::chunk_off(kRows, row, half + 2 * i);
+                    *reinterpret_cast<uint4 *>(sHhi + off) = fh[i];
+                    if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = fl[i];
+                }
+                tc05::fence_proxy_async_smem();
+                tc05::mbar_arrive(&bars[B_FEAT]);
+            }
+        }
+    }
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == kLoaderWarp) tc05::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- pre-pass: live-tile list + outputs of sky-only tiles -----------------------------------------
+__global__ void __launch_bounds__(kRows)
+prepass_kernel(const Params p, int32_t *tile_list, int32_t *n_live)
+{
+    const int tile = blockIdx.x, row = threadIdx.x;
+    const TileCoord tc = tile_coord(p, tile);
+    const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
+    const bool valid = (y < p.H) && (x < p.W);
+    const long long ray = ((long long)tc.img * p.H + y) * p.W + x;
+    const bool live = valid && (__ldg(p.voxel_id + ray * p.M) != 0);
+    const int any = __syncthreads_or(live ? 1 : 0);
+    if (any) {
+        if (row == 0) tile_list[atomicAdd(n_live, 1)] = tile;
+        return;
+    }
+    if (!valid) return;
+    // sky-only ray: weights are zero, all samples sit at the camera origin (scenedreamer.py:350-354,376)
+    const bool is_gnd = __ldg(p.cam_ori + tc.img * 3) <= 1.0f;
+    const float4 *skp = reinterpret_cast<const float4 *>(is_gnd ? p.sky_avg + (long long)tc.img * kOutC : p.sky + ray * kOutC);
+    float4 *dst = reinterpret_cast<float4 *>(p.net_out + ray * kOutC);
+#pragma unroll
+    for (int q = 0; q < kOutC / 4; q++) {
+        const float4 sk = __ldg(skp + q);
+        float4 o;
+        o.x = (0.0f + 1.0f * (fminf(fmaxf(sk.x, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        o.y = (0.0f + 1.0f * (fminf(fmaxf(sk.y, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        o.z = (0.0f + 1.0f * (fminf(fmaxf(sk.z, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        o.w = (0.0f + 1.0f * (fminf(fmaxf(sk.w, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        dst[q] = o;
+    }
+    if (p.depth_out) p.depth_out[ray] = 0.0f;
+    if (p.total_weight) p.total_weight[ray] = 0.0f;
+}
+
+// ---- per-scene pre-blend of the two constant encoder dims -------------------------------------------
+__global__ void __launch_bounds__(256)
+preblend_kernel(const float *__restrict__ table, float *__restrict__ table3, int L, int log2_T, float level_S, int base_res,
+                const float *__restrict__ genc)
+{
+    const uint32_t T = 1u << log2_T, mask = T - 1u;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)L * T) return;
+    const uint32_t level = (uint32_t)(i >> log2_T), e = (uint32_t)i & mask;
+    const float scale = exp2f(level * level_S) * base_res - 1.0f;
+    float f[2];
+    uint32_t g[2];
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const float x = __fmul_rn(__fadd_rn(genc[d], 1.0f), 0.5f);
+        const float pos = fmaf(x, scale, 0.5f);
+        g[d] = (uint32_t)floorf(pos);
+        f[d] = pos - (float)g[d];
+    }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float *tl = table + ((size_t)level << log2_T) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int b3 = j & 1, b4 = j >> 1;
+        const float w = (b3 ? f[0] : 1.0f - f[0]) * (b4 ? f[1] : 1.0f - f[1]);
+        const uint32_t K = ((g[0] + b3) * kPrime3) ^ ((g[1] + b4) * kPrime4);
+        float v[8];
+        ld8(tl + (size_t)((e ^ K) & mask) * 8, v);
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = fmaf(w, v[c], acc[c]);
+    }
+    float4 *o = reinterpret_cast<float4 *>(table3 + i * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// ---- weight packer ---------------------------------------------------------------------------------
+template <bool X3>
+__global__ void __launch_bounds__(256)
+pack_kernel(const float *w1, const float *b1, const float *emb, int n_labels, const float *wh, const float *bh,
+            const float *wsig, const float *bsig, const float *wout, const float *bout, uint8_t *pack)
+{
+    constexpr int PARTS = X3 ? 2 : 1;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long nW = 0;
+    for (int l = 0; l < kLayers; l++) nW += (long long)layerK(l) * layerN(l);
+    if (t < nW) {
+        long long r = t;
+        int l = 0;
+        while (r >= (long long)layerK(l) * layerN(l)) { r -= (long long)layerK(l) * layerN(l); l++; }
+        const int K = layerK(l), N = layerN(l);
+        const int nn = (int)(r / K), k = (int)(r % K);
+        const float *src = (l == 0) ? w1 : (l == kLayers - 1 ? wout : wh + (long long)(l - 1) * kHidden * kHidden);
+        const float v = src[(long long)nn * K + k];
+        const int kk = k >> 4, k16 = k & 15;
+        const long long slab_off = (long long)(k16 >> 3) * N * 16 + (nn >> 3) * 128 + (nn & 7) * 16 + (k16 & 7) * 2;
+        uint8_t *base = pack + layerOff(l, PARTS) + (long long)kk * N * 32 * PARTS;
+        if constexpr (X3) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            *reinterpret_cast<__nv_bfloat16 *>(base + slab_off) = hi;
+            *reinterpret_cast<__nv_bfloat16 *>(base + (long long)N * 32 + slab_off) = lo;
+        } else {
+            *reinterpret_cast<__half *>(base + slab_off) = __float2half_rn(v);
+        }
+        return;
+    }
+    const long long u = t - nW;
+    if (u >= kFTotal) return;
+    float *F = reinterpret_cast<float *>(pack + layerOff(kLayers, PARTS));
+    float v = 0.0f;
+    if (u < 256) v = b1[u];
+    else if (u < kFBout) v = bh[u - 256];
+    else if (u < kFBout + kOutC) v = bout[u - kFBout];
+    else if (u >= kFWsig && u < kFWsig + kHidden) v = wsig[u - kFWsig];
+    else if (u == kFBsig) v = bsig[0];
+    else if (u >= kFEmb) {
+        const int lab = (int)(u - kFEmb) / kHidden, c = (int)(u - kFEmb) % kHidden;
+        v = lab < n_labels ? emb[(long long)lab * kHidden + c] : 0.0f;
+    }
+    F[u] = v;
+}
+
+}  // namespace rf
+
+extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes(precision == 1 ? 2 : 1); }
+
+extern "C" int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, int32_t n_labels,
+                            const float *d_wh, const float *d_bh, const float *d_wsig, const float *d_bsig,
+                            const float *d_wout, const float *d_bout, int32_t precision, void *d_pack, void *stream)
+{
+    if (!d_w1 || !d_b1 || !d_emb || !d_wh || !d_bh || !d_wsig || !d_bsig || !d_wout || !d_bout || !d_pack) return SDB_EINVAL;
+    if (n_labels < 1 || n_labels > rf::kMaxLabels || precision < 0 || precision > 1) return SDB_EINVAL;
+    long long n = rf::kFTotal;
+    for (int l = 0; l < rf::kLayers; l++) n += (long long)rf::layerK(l) * rf::layerN(l);
+    const int blocks = (int)((n + 255) / 256);
+    if (precision == 1)
+        rf::pack_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
+                                                                          d_wout, d_bout, (uint8_t *)d_pack);
+    else
+        rf::pack_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
+                                                                           d_wout, d_bout, (uint8_t *)d_pack);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}
+
+extern "C" int sdb_preblend_table(const float *d_table, float *d_table3, int32_t L, int32_t log2_T, float level_S,
+                                  int32_t base_res, const float *d_global_enc, void *stream)
+{
+    if (!d_table || !d_table3 || !d_global_enc || L < 1 || L > 32 || log2_T < 4 || log2_T > 24) return SDB_EINVAL;
+    const size_t n = (size_t)L << log2_T;
+    rf::preblend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_table, d_table3, L, log2_T, level_S,
+                                                                                        base_res, d_global_enc);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}
+
+extern "C" int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
+    if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+    const int64_t tiles = (int64_t)n_img * sdb_div_up(H, rf::kTileH) * sdb_div_up(W, rf::kTileW);
+    return (tiles + 4) * 4;
+}
+
+extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream)
+{
+    using namespace rf;
+    if (!sp) return SDB_EINVAL;
+    if (!sp->d_voxel_id || !sp->d_depth2 || !sp->d_raydirs || !sp->d_cam_ori || !sp->d_global_enc || !sp->d_fractions ||
+        !sp->d_label_lut || !sp->d_mlp_pack || !sp->d_sky || !sp->d_sky_avg || !sp->d_net_out || !sp->d_workspace)
+        return SDB_EINVAL;
+    if ((sp->d_table == nullptr) == (sp->d_table3 == nullptr)) return SDB_EINVAL;
+    if (sp->n_img <= 0 || sp->H <= 0 || sp->W <= 0) return SDB_EINVAL;
+    if (sp->M < 1 || sp->M > kMaxM || sp->S < 1 || sp->S > kMaxS || sp->L != kLevels || sp->log2_T < 4 || sp->log2_T > 24 ||
+        sp->precision < 0 || sp->precision > 1 || sp->n_lut < 1)
+        return SDB_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    Params p;
+    p.n_img = sp->n_img; p.H = sp->H; p.W = sp->W; p.M = sp->M; p.S = sp->S;
+    p.voxel_id = sp->d_voxel_id; p.depth2 = sp->d_depth2; p.raydirs = sp->d_raydirs; p.cam_ori = sp->d_cam_ori;
+    p.genc = sp->d_global_enc;
+    for (int k = 0; k < 3; k++) p.vdim[k] = sp->voxel_dims[k];
+    p.sample_depth = sp->sample_depth; p.dists_scale = sp->dists_scale;
+    p.fractions = sp->d_fractions; p.uniforms = sp->d_uniforms;
+    p.lut = sp->d_label_lut; p.n_lut = sp->n_lut;
+    p.raw5d = sp->d_table != nullptr;
+    p.table = p.raw5d ? sp->d_table : sp->d_table3;
+    p.log2_T = sp->log2_T; p.level_S = sp->level_S; p.base_res = sp->base_res;
+    p.pack = (const uint8_t *)sp->d_mlp_pack; p.pack_stride = sp->mlp_pack_stride;
+    p.sky = sp->d_sky; p.sky_avg = sp->d_sky_avg;
+    p.net_out = sp->d_net_out; p.depth_out = sp->d_depth_out; p.total_weight = sp->d_total_weight;
+    p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
+    const int n_tiles = p.n_img * p.tiles_x * p.tiles_y;
+    int32_t *ws = (int32_t *)sp->d_workspace;
+    p.n_live = ws; p.tile_list = ws + 4;
+    SDB_CUDA(cudaMemsetAsync(ws, 0, 16, st));
+    prepass_kernel<<<n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
+    SDB_CHECK_LAUNCH();
+    const int grid = n_tiles < sdb_num_sms() ? n_tiles : sdb_num_sms();
+    const bool x3 = sp->precision == 1;
+    const size_t smem = smem_map(x3).total;
+#define SDB_LAUNCH_RENDER(X3_, RAW_)                                                                                   \
+    do {                                                                                                               \
+        SDB_CUDA(cudaFuncSetAttribute(render_kernel<X3_, RAW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        render_kernel<X3_, RAW_><<<grid, kThreads, smem, st>>>(p);                                                     \
+    } while (0)
+    if (x3 && p.raw5d) SDB_LAUNCH_RENDER(true, true);
+    else if (x3) SDB_LAUNCH_RENDER(true, false);
+    else if (p.raw5d) SDB_LAUNCH_RENDER(false, true);
+    else SDB_LAUNCH_RENDER(false, false);
+#undef SDB_LAUNCH_RENDER
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}

@@ -1,0 +1,229 @@
+"""Host side of the fused per-pixel renderer (libsdb200: sdb_render_rays_forward & friends).
+
+Mirrors the role of Generator._forward_perpix (imaginaire/generators/scenedreamer.py:313-428) and
+of the tile loop in inference_givenstyle (:600-628): given the ray/voxel intersection buffers, the
+style code and the scene code it returns the per-pixel feature map `net_out` (+ depth, opacity).
+All heavy work happens in the CUDA library; torch is used to allocate tensors, to fold the style
+modulation into the weights (tiny [256x256] elementwise products, once per style code) and --
+for now -- to run the per-RAY sky MLP (3% of the FLOPs) through cuBLAS.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+PRECISION_FP16 = 0      # one fp16 tensor-core pass per product (~1e-3 relative)
+PRECISION_BF16X3 = 1    # bf16 split, 3 passes, fp32-grade (~2e-5 relative): the parity default
+
+
+class _RenderParams(ctypes.Structure):
+    _fields_ = [
+        ('n_img', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('M', ctypes.c_int32),
+        ('S', ctypes.c_int32),
+        ('d_voxel_id', ctypes.c_void_p), ('d_depth2', ctypes.c_void_p), ('d_raydirs', ctypes.c_void_p),
+        ('d_cam_ori', ctypes.c_void_p),
+        ('voxel_dims', ctypes.c_float * 3),
+        ('d_global_enc', ctypes.c_void_p),
+        ('sample_depth', ctypes.c_float), ('dists_scale', ctypes.c_float),
+        ('d_fractions', ctypes.c_void_p), ('d_uniforms', ctypes.c_void_p),
+        ('d_label_lut', ctypes.c_void_p), ('n_lut', ctypes.c_int32),
+        ('d_table', ctypes.c_void_p), ('d_table3', ctypes.c_void_p),
+        ('L', ctypes.c_int32), ('log2_T', ctypes.c_int32), ('level_S', ctypes.c_float), ('base_res', ctypes.c_int32),
+        ('d_mlp_pack', ctypes.c_void_p), ('mlp_pack_stride', ctypes.c_int64), ('precision', ctypes.c_int32),
+        ('d_sky', ctypes.c_void_p), ('d_sky_avg', ctypes.c_void_p),
+        ('d_net_out', ctypes.c_void_p), ('d_depth_out', ctypes.c_void_p), ('d_total_weight', ctypes.c_void_p),
+        ('d_workspace', ctypes.c_void_p),
+    ]
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def modulated_weights(P, z, prefix='render_net'):
+    """Fold the style modulation of ModLinear into plain weights for ONE style code z [256]
+    (model_utils/layers.py:247-260): W' = W * alpha (per input column), bias = beta."""
+    p = prefix + '.'
+    wh, bh = [], []
+    for k in (2, 3, 4, 5, 6):
+        n = p + 'fc_%d' % k
+        alpha = torch.addmm(P[n + '.bias_alpha'].unsqueeze(0), z.unsqueeze(0), P[n + '.weight_alpha'].t())   # [1, I]
+        beta = torch.addmm(P[n + '.bias_beta'].unsqueeze(0), z.unsqueeze(0), P[n + '.weight_beta'].t())      # [1, O]
+        wh.append(P[n + '.weight'].unsqueeze(0) * alpha.unsqueeze(1))                                         # [1, O, I]
+        bh.append(beta)
+    return torch.cat(wh, 0).contiguous(), torch.cat(bh, 0).contiguous()
+
+
+def pack_mlp(P, z, precision=PRECISION_BF16X3, prefix='render_net'):
+    """z [N, 256] (style_net output) -> uint8 tensor [N, pack_bytes] on z's device."""
+    L = _lib.lib()
+    dev = z.device
+    nbytes = int(L.sdb_mlp_pack_bytes(int(precision)))
+    N = z.shape[0]
+    pack = torch.empty(N, nbytes, dtype=torch.uint8, device=dev)
+    p = prefix + '.'
+    w1 = P[p + 'fc_1.weight'].contiguous()
+    b1 = P[p + 'fc_1.bias'].contiguous()
+    emb = P[p + 'fc_m_a.weight'].t().contiguous()            # [labels, 256]
+    wsig = P[p + 'fc_sigma.weight'].reshape(-1).contiguous()
+    bsig = P[p + 'fc_sigma.bias'].reshape(-1).contiguous()
+    wout = P[p + 'fc_out_c.weight'].contiguous()
+    bout = P[p + 'fc_out_c.bias'].contiguous()
+    with torch.cuda.device(dev):
+        for i in range(N):
+            wh, bh = modulated_weights(P, z[i], prefix)
+            code = L.sdb_pack_mlp(_ptr(w1), _ptr(b1), _ptr(emb), int(emb.shape[0]), _ptr(wh), _ptr(bh), _ptr(wsig),
+                                  _ptr(bsig), _ptr(wout), _ptr(bout), int(precision), _ptr(pack[i]), _stream(dev))
+            _lib.check(code, 'sdb_pack_mlp')
+    return pack
+
+
+def preblend_table(embeddings, global_enc, log2_T=19, per_level_scale=None, base_res=16, L=16):
+    """[L*T, 8] raw 5-D hash table + scene code [2] -> pre-blended 3-D table of the same shape."""
+    dev = embeddings.device
+    out = torch.empty_like(embeddings)
+    genc = global_enc.reshape(-1)[:2].to(dev, torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        code = _lib.lib().sdb_preblend_table(_ptr(embeddings), _ptr(out), int(L), int(log2_T),
+                                             float(np.log2(per_level_scale)), int(base_res), _ptr(genc),
+                                             _stream(dev))
+    _lib.check(code, 'sdb_preblend_table')
+    return out
+
+
+def deterministic_fractions(S, device):
+    """torch.linspace(0, 1, S+3)[1:-1] built on the CPU like the reference (mc_utils.py:118-120)."""
+    return torch.linspace(0, 1, S + 3)[1:-1].contiguous().to(device)
+
+
+def stratified_offsets(S, device):
+    """torch.linspace(0, 1, S+2)[:-1] (mc_utils.py:125)."""
+    return torch.linspace(0, 1, S + 2, device=device)[:-1].contiguous()
+
+
+def sky_features(P, raydirs, z, prefix='sky_net', pe=(5, True)):
+    """a9: PE(raydir) -> SKYMLP (gancraft_base.py:150-169).  raydirs [N,H,W,1,3], z [N,256] -> [N,H,W,64]."""
+    N, H, W = raydirs.shape[:3]
+    enc = ops.positional_encoding(raydirs.contiguous(), pe[0], -1, pe[1]).reshape(N, H * W, -1)
+    p = prefix + '.'
+    zz = F.linear(z, P[p + 'fc_z_a.weight']).unsqueeze(1)
+    y = F.leaky_relu(F.linear(enc, P[p + 'fc1.weight'], P[p + 'fc1.bias']) + zz, 0.2)
+    for k in (2, 3, 4, 5):
+        y = F.leaky_relu(F.linear(y, P[p + 'fc%d.weight' % k], P[p + 'fc%d.bias' % k]), 0.2)
+    return F.linear(y, P[p + 'fc_out_c.weight'], P[p + 'fc_out_c.bias']).reshape(N, H, W, -1)
+
+
+def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_dims, label_lut, mlp_pack, sky, sky_avg,
+                        table=None, table3=None, num_samples=24, sample_depth=3.0, dists_scale=0.25, uniforms=None,
+                        precision=PRECISION_BF16X3, per_level_scale=None, base_res=16, log2_T=19, L=16,
+                        want_depth=True):
+    """Fused a2-a12.  Shapes follow the reference:
+    voxel_id [N,H,W,M,1] int32, depth2 [N,2,H,W,M,1], raydirs [N,H,W,1,3], cam_ori [N,3], global_enc [N,2],
+    sky [N,H,W,64], sky_avg [N,64]; label_lut int32 [n] (ignore already mapped to dirt).
+    Returns dict(net_out [N,H,W,64], depth [N,H,W], total_weight [N,H,W])."""
+    dev = voxel_id.device
+    N, H, W, M = voxel_id.shape[:4]
+    S = int(num_samples)
+    for t, n in ((voxel_id, 'voxel_id'), (depth2, 'depth2'), (raydirs, 'raydirs'), (sky, 'sky')):
+        if not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError('%s must be a contiguous CUDA tensor' % n)
+    if voxel_id.dtype != torch.int32:
+        raise RuntimeError('voxel_id must be int32')
+    net_out = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
+    depth = torch.empty(N, H, W, dtype=torch.float32, device=dev) if want_depth else None
+    tw = torch.empty(N, H, W, dtype=torch.float32, device=dev) if want_depth else None
+    Lb = _lib.lib()
+    ws = torch.empty(int(Lb.sdb_render_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+    cam_ori = cam_ori.to(dev, torch.float32).reshape(N, 3).contiguous()
+    genc = global_enc.to(dev, torch.float32).reshape(N, 2).contiguous()
+    if uniforms is None:
+        frac = deterministic_fractions(S, dev)
+    else:
+        frac = stratified_offsets(S, dev)
+        uniforms = uniforms.to(dev, torch.float32).reshape(N * H * W, S + 1).contiguous()
+    lut = label_lut.to(dev, torch.int32).contiguous()
+    prm = _RenderParams()
+    prm.n_img, prm.H, prm.W, prm.M, prm.S = N, H, W, M, S
+    prm.d_voxel_id, prm.d_depth2, prm.d_raydirs = _ptr(voxel_id), _ptr(depth2), _ptr(raydirs)
+    prm.d_cam_ori = _ptr(cam_ori)
+    prm.voxel_dims = (ctypes.c_float * 3)(*[float(v) for v in voxel_dims])
+    prm.d_global_enc = _ptr(genc)
+    prm.sample_depth, prm.dists_scale = float(sample_depth), float(dists_scale)
+    prm.d_fractions, prm.d_uniforms = _ptr(frac), _ptr(uniforms)
+    prm.d_label_lut, prm.n_lut = _ptr(lut), int(lut.numel())
+    prm.d_table, prm.d_table3 = _ptr(table), _ptr(table3)
+    prm.L, prm.log2_T, prm.level_S, prm.base_res = int(L), int(log2_T), float(np.log2(per_level_scale)), int(base_res)
+    prm.d_mlp_pack = _ptr(mlp_pack)
+    prm.mlp_pack_stride = int(mlp_pack.stride(0)) if (mlp_pack.dim() == 2 and mlp_pack.shape[0] > 1) else 0
+    prm.precision = int(precision)
+    sky = sky.reshape(N, H, W, 64)
+    sky_avg = sky_avg.to(dev, torch.float32).reshape(N, 64).contiguous()
+    prm.d_sky, prm.d_sky_avg = _ptr(sky), _ptr(sky_avg)
+    prm.d_net_out, prm.d_depth_out, prm.d_total_weight = _ptr(net_out), _ptr(depth), _ptr(tw)
+    prm.d_workspace = _ptr(ws)
+    with torch.cuda.device(dev):
+        code = Lb.sdb_render_rays_forward(ctypes.byref(prm), _stream(dev))
+    _lib.check(code, 'sdb_render_rays_forward')
+    return dict(net_out=net_out, depth=depth, total_weight=tw)
+
+
+def reduced_label_lut(mc2reduced, ignore_id=0, dirt_id=3):
+    """mc id -> reduced label with ignore -> dirt folded in (mc_utils.py:241-246, ign2dirt=True)."""
+    lut = torch.as_tensor(mc2reduced).to(torch.int32).clone()
+    lut[lut == ignore_id] = dirt_id
+    return lut
+
+
+class FusedPerPixelRenderer:
+    """Caches per-style weight packs, the per-scene pre-blended table and runs one frame.
+
+    P: dict of parameters with the reference's state-dict names (render_net.*, sky_net.*,
+    hash_encoder.embeddings) on the CUDA device."""
+
+    def __init__(self, P, voxel_dims, label_lut, per_level_scale, precision=PRECISION_BF16X3, preblend=True,
+                 base_res=16, log2_T=19, L=16):
+        self.P, self.voxel_dims, self.lut = P, [float(v) for v in voxel_dims], label_lut
+        self.pls, self.precision, self.preblend = per_level_scale, precision, preblend
+        self.base_res, self.log2_T, self.L = base_res, log2_T, L
+        self._pack_key = self._pack = self._t3_key = self._t3 = None
+
+    def pack_for(self, z):
+        key = (z.data_ptr(), z._version, self.precision)
+        if self._pack_key != key:
+            self._pack, self._pack_key = pack_mlp(self.P, z, self.precision), key
+        return self._pack
+
+    def table3_for(self, global_enc):
+        emb = self.P['hash_encoder.embeddings']
+        key = (emb.data_ptr(), emb._version, tuple(global_enc.reshape(-1).tolist()))
+        if self._t3_key != key:
+            self._t3 = preblend_table(emb, global_enc, self.log2_T, self.pls, self.base_res, self.L)
+            self._t3_key = key
+        return self._t3
+
+    def forward(self, voxel_id, depth2, raydirs, cam_ori, z, global_enc, num_samples=24, sample_depth=3.0,
+                dists_scale=0.25, uniforms=None, sky_avg=None, sky=None):
+        N = voxel_id.shape[0]
+        if sky is None:
+            sky = sky_features(self.P, raydirs, z)
+        if sky_avg is None:
+            sky_avg = sky.mean(dim=(1, 2))                       # scenedreamer.py:395 / :597
+        pack = self.pack_for(z)
+        kw = {}
+        if self.preblend and N == 1:
+            kw['table3'] = self.table3_for(global_enc)
+        else:
+            kw['table'] = self.P['hash_encoder.embeddings']
+        out = render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, self.voxel_dims, self.lut, pack, sky,
+                                  sky_avg, num_samples=num_samples, sample_depth=sample_depth, dists_scale=dists_scale,
+                                  uniforms=uniforms, precision=self.precision, per_level_scale=self.pls,
+                                  base_res=self.base_res, log2_T=self.log2_T, L=self.L, **kw)
+        out['sky'], out['sky_avg'] = sky, sky_avg
+        return out

@@ -1,0 +1,170 @@
+"""GPU parity tests for the fused per-pixel renderer (sdb_render_rays_forward) through the C ABI:
+CUDA path vs the CPU oracle on the same seeded inputs, vs the committed reference-generated golden
+frame, plus size-independent properties.  Tolerance: 1e-3 max-abs on net_out / depth (north star);
+sampling indices are covered bit-exactly by the oracle tests."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from scenedreamer_b200 import ops, render, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+DEV = 'cuda:0'
+TOL = 1e-3
+
+
+def to_dev(P):
+    return {k: v.to(DEV) for k, v in P.items()}
+
+
+def device_level_scales(L, pls, base):
+    S = torch.tensor(float(np.float32(np.log2(pls))), device=DEV)
+    lv = torch.arange(L, device=DEV, dtype=torch.float32)
+    return (torch.exp2(lv * S) * float(base) - 1.0).cpu()
+
+
+@pytest.fixture(scope='module')
+def lut(golden_ops):
+    return render.reduced_label_lut(golden_ops['mc2reduced_lut'], 0, 3)
+
+
+@pytest.fixture(scope='module')
+def scene():
+    world = synth.SyntheticVoxelWorld(size=128, seed=7)
+    pose = synth.eval_camera_poses(world, maxstep=8, pattern=0)[1]
+    o, d, u, f, c, res = synth.frame_camera(world, pose, resolution_hw=(44, 60), pad=4)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV), o, d, u, f, c, res, 6)
+    return dict(world=world, o=o, vid=vid.unsqueeze(0), dep=dep.unsqueeze(0), rd=rd.unsqueeze(0))
+
+
+def run_oracle(P, sc, z, genc, lut_raw, S=24, uniforms=None):
+    offsets, pls = oracle.grid_offsets()
+    return oracle.forward_perpix(P, sc['vid'].cpu(), sc['dep'].cpu(), sc['rd'].cpu(), sc['o'].unsqueeze(0), z, genc,
+                                 list(sc['world'].voxel_t.shape), lut_raw, offsets, pls, num_samples=S,
+                                 deterministic=uniforms is None, uniforms=uniforms,
+                                 level_scales=device_level_scales(16, pls, 16))
+
+
+def run_fused(P, sc, z, genc, lut, precision, preblend, S=24, uniforms=None):
+    _, pls = oracle.grid_offsets()
+    r = render.FusedPerPixelRenderer(to_dev(P), sc['world'].voxel_t.shape, lut, pls, precision=precision, preblend=preblend)
+    out = r.forward(sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), z.to(DEV), genc.to(DEV), num_samples=S,
+                    uniforms=uniforms)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize('stress', [False, True])
+@pytest.mark.parametrize('preblend', [False, True])
+def test_fused_vs_oracle_x3(scene, lut, golden_ops, stress, preblend):
+    P = oracle.make_params(seed=21, stress=stress)
+    g = torch.Generator().manual_seed(8888)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    ref = run_oracle(P, scene, z, genc, torch.from_numpy(golden_ops['mc2reduced_lut']))
+    out = run_fused(P, scene, z, genc, lut, render.PRECISION_BF16X3, preblend)
+    err = (out['net_out'].cpu() - ref['net_out']).abs()
+    derr = (out['depth'].cpu() - ref['depth_map'].squeeze(-1)).abs()
+    werr = (out['total_weight'].cpu() - ref['total_weights'].reshape(out['total_weight'].shape)).abs()
+    print('x3 stress=%s preblend=%s: net_out max err %.3e (|ref| max %.2f), depth err %.3e, weight err %.3e, live %.2f'
+          % (stress, preblend, float(err.max()), float(ref['net_out'].abs().max()), float(derr.max()), float(werr.max()),
+             float((scene['vid'][..., 0, 0] != 0).float().mean())))
+    assert float(err.max()) <= TOL
+    assert float(derr.max()) <= TOL * max(1.0, float(ref['depth_map'].abs().max()))
+    assert float(werr.max()) <= TOL
+    if stress:
+        assert float(ref['net_out'].abs().max()) > 0.5 and float(ref['total_weights'].max()) > 0.9
+
+
+def test_fused_vs_reference_golden_frame(lut, golden_fpp, golden_ops):
+    """The committed frame produced by the reference's own _forward_perpix (tests/golden)."""
+    g = golden_fpp
+    dims = [int(v) for v in g['fpp_voxel_dims']]
+    cam = g['fpp_cam']
+    _, pls = oracle.grid_offsets()
+    for tag, stress in (('spec', False), ('stress', True)):
+        P = oracle.make_params(seed=9, stress=stress)
+        r = render.FusedPerPixelRenderer(to_dev(P), dims, lut, pls, precision=render.PRECISION_BF16X3, preblend=False)
+        vid = torch.from_numpy(g['fpp_voxel_id']).to(DEV).unsqueeze(0).contiguous()
+        dep = torch.from_numpy(g['fpp_depth2']).to(DEV).unsqueeze(0).contiguous()
+        rd = torch.from_numpy(g['fpp_raydirs']).to(DEV).unsqueeze(0).contiguous()
+        out = r.forward(vid, dep, rd, torch.from_numpy(cam[0:3]).float().unsqueeze(0),
+                        torch.from_numpy(g['fpp_%s_z' % tag]).to(DEV), torch.from_numpy(g['fpp_%s_genc' % tag]).to(DEV))
+        torch.cuda.synchronize()
+        err = np.abs(out['net_out'].cpu().numpy() - g['fpp_%s_net_out' % tag])
+        werr = np.abs(out['total_weight'].cpu().numpy() - g['fpp_%s_total_weights_raw' % tag].reshape(out['total_weight'].shape))
+        print('golden frame %s: net_out max err %.3e, total weight err %.3e' % (tag, err.max(), werr.max()))
+        assert err.max() <= TOL and werr.max() <= TOL
+
+
+def test_fused_fp16_single_pass_error_budget(scene, lut, golden_ops):
+    """precision 0 (one fp16 pass) is the fast mode: documents its error; must stay within 1e-2."""
+    P = oracle.make_params(seed=21, stress=True)
+    g = torch.Generator().manual_seed(8888)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    ref = run_oracle(P, scene, z, genc, torch.from_numpy(golden_ops['mc2reduced_lut']))
+    out = run_fused(P, scene, z, genc, lut, render.PRECISION_FP16, True)
+    err = (out['net_out'].cpu() - ref['net_out']).abs()
+    print('fp16x1 stress: net_out max err %.3e mean %.3e' % (float(err.max()), float(err.mean())))
+    assert float(err.max()) <= 1e-2
+
+
+def test_fused_stratified_sampling_and_small_S(scene, lut, golden_ops):
+    P = oracle.make_params(seed=5, stress=True)
+    g = torch.Generator().manual_seed(1)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    N, H, W = scene['vid'].shape[:3]
+    for S in (24, 4):
+        u = torch.rand(N, H, W, S + 1, 1, generator=g)
+        ref = run_oracle(P, scene, z, genc, torch.from_numpy(golden_ops['mc2reduced_lut']), S=S, uniforms=u)
+        out = run_fused(P, scene, z, genc, lut, render.PRECISION_BF16X3, False, S=S, uniforms=u)
+        err = (out['net_out'].cpu() - ref['net_out']).abs()
+        print('stratified S=%d: net_out max err %.3e' % (S, float(err.max())))
+        assert float(err.max()) <= TOL
+
+
+def test_fused_batch_of_views_two_styles(scene, lut, golden_ops):
+    """N=2 images with different style codes / scene codes (the train.py shape): per-image packs."""
+    P = oracle.make_params(seed=33, stress=True)
+    g = torch.Generator().manual_seed(3)
+    z = oracle.style_mlp(torch.randn(2, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(2, 2, generator=g))
+    sc2 = dict(scene)
+    sc2['vid'] = torch.cat([scene['vid'], scene['vid'].flip(2)], 0).contiguous()
+    sc2['dep'] = torch.cat([scene['dep'], scene['dep'].flip(3)], 0).contiguous()
+    sc2['rd'] = torch.cat([scene['rd'], scene['rd'].flip(2)], 0).contiguous()
+    offsets, pls = oracle.grid_offsets()
+    ref = oracle.forward_perpix(P, sc2['vid'].cpu(), sc2['dep'].cpu(), sc2['rd'].cpu(), scene['o'].repeat(2, 1), z, genc,
+                                list(scene['world'].voxel_t.shape), torch.from_numpy(golden_ops['mc2reduced_lut']), offsets,
+                                pls, level_scales=device_level_scales(16, pls, 16))
+    r = render.FusedPerPixelRenderer(to_dev(P), scene['world'].voxel_t.shape, lut, pls, preblend=False)
+    out = r.forward(sc2['vid'], sc2['dep'], sc2['rd'], scene['o'].repeat(2, 1), z.to(DEV), genc.to(DEV))
+    torch.cuda.synchronize()
+    err = (out['net_out'].cpu() - ref['net_out']).abs()
+    print('batch of 2 views: net_out max err %.3e' % float(err.max()))
+    assert float(err.max()) <= TOL
+
+
+def test_fused_properties_all_sky_and_determinism(scene, lut):
+    """Sky-only frame -> output is exactly the clamped sky feature; two runs are bit-identical."""
+    P = oracle.make_params(seed=2, stress=True)
+    _, pls = oracle.grid_offsets()
+    r = render.FusedPerPixelRenderer(to_dev(P), scene['world'].voxel_t.shape, lut, pls)
+    g = torch.Generator().manual_seed(4)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P).to(DEV)
+    genc = torch.tanh(torch.randn(1, 2, generator=g)).to(DEV)
+    vid0 = torch.zeros_like(scene['vid'])
+    dep0 = torch.full_like(scene['dep'], float('nan'))
+    out = r.forward(vid0, dep0, scene['rd'], scene['o'].unsqueeze(0), z, genc)
+    sky = out['sky']
+    expect = (torch.clamp(sky, -1, 1) + 1) - 1
+    assert torch.equal(out['net_out'], expect)
+    assert float(out['total_weight'].abs().max()) == 0.0
+    a = r.forward(scene['vid'], scene['dep'], scene['rd'], scene['o'].unsqueeze(0), z, genc)['net_out'].clone()
+    b = r.forward(scene['vid'], scene['dep'], scene['rd'], scene['o'].unsqueeze(0), z, genc)['net_out']
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert bool(torch.isfinite(a).all())
