@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the SceneDreamer per-pixel render hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, libsdb200)
+    python bench.py --impl reference --steps K --warmup W    # reference arm: CPU path on host cores
+
+A "step" is ONE frame of the C2 workload: 540x960 output pixels, 24 samples/ray,
+scene_size 1024, cam_mode 0, pad 30 -> 570x990 rays raycast + shaded:
+    a1  ray/voxel DDA                        (sdb_ray_voxel_intersection_perspective)
+    a9  sky branch: PE kernel + SKYMLP       (PE: ours; the per-RAY 6-layer MLP runs on cuBLAS for now)
+    a2-a8, a10-a12 fused per-pixel kernel    (sdb_render_rays_forward: tcgen05 MLP, hash gather, compositing)
+Credit = OUTPUT samples: 518,400 px x 24 = 12,441,600 samples per frame (padding rays are overhead).
+Each step renders a different pose of the 40-frame cam_mode-0 trajectory and L2 is flushed between
+steps (256 MiB memset outside the per-step CUDA events).
+Multi-GPU (weak scaling): every rank renders its own frames (frame f -> rank f mod N); the finished
+per-pixel scalar maps (depth, opacity) are all-gathered once per step over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OUT_HW = (540, 960)
+PAD = 30
+SPP = 24
+SCENE = 1024
+BYTES_PER_SAMPLE = 16384 + 344.0 / SPP     # table gather + per-ray I/O
+SAMPLES_PER_FRAME = OUT_HW[0] * OUT_HW[1] * SPP
+PIX_PER_FRAME = OUT_HW[0] * OUT_HW[1]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1430.0))), 'measured'
+    return 6650.0, 1400.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self._stop_evt.is_set():
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def build_workload(device, seed=3407):
+    import oracle
+    from scenedreamer_b200 import synth
+    world = synth.SyntheticVoxelWorld(SCENE, seed)
+    poses = synth.eval_camera_poses(world, maxstep=40, pattern=0)
+    P = oracle.make_params(seed=0, stress=True)
+    g = torch.Generator().manual_seed(8888)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    lut = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_python_ops.npz'))['mc2reduced_lut']
+    return world, poses, P, z, genc, lut
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the reference's path restated for the CPU (oracle/), all host threads, bounded sample
+# ----------------------------------------------------------------------------------------------------
+def cpu_frame_sample(world, pose, P, z, genc, lut, crop=64):
+    """One bounded sample of the C2 frame on the CPU: a crop x crop ray window in the image centre.
+    Returns (seconds, samples credited)."""
+    import oracle
+    from scenedreamer_b200 import synth
+    o, d, u, f, c, res = synth.frame_camera(world, pose, OUT_HW, PAD)
+    # shift the principal point so that the crop window is the centre of the full frame
+    i0, j0 = (res[0] - crop) // 2, (res[1] - crop) // 2
+    cc = [c[0] - i0, c[1] - j0]
+    offsets, pls = oracle.grid_offsets()
+    t0 = time.perf_counter()
+    vid, dep, rd = oracle.ray_voxel_intersection_perspective(world.voxel_t, o, d, u, f, cc, [crop, crop], 6)
+    oracle.forward_perpix(P, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0), z, genc,
+                          list(world.voxel_t.shape), torch.from_numpy(lut), offsets, pls, num_samples=SPP)
+    return time.perf_counter() - t0, crop * crop * SPP
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import oracle
+    torch.set_num_threads(os.cpu_count())
+    world, poses, P, z, genc, lut = build_workload('cpu')
+    crop = 64
+    for w in range(args.warmup):
+        cpu_frame_sample(world, poses[w % 40], P, z, genc, lut, crop)
+    ts, ns = [], 0
+    for k in range(args.steps):
+        dt, n = cpu_frame_sample(world, poses[k % 40], P, z, genc, lut, crop)
+        ts.append(dt)
+        ns += n
+    total = sum(ts)
+    val = ns / total / 1e6
+    line = {
+        'impl': 'reference', 'metric': 'rendered Msamples/sec at 960x540x24spp', 'value': val, 'unit': 'Msamples/s',
+        'mpix_per_s': val / SPP, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0 (CPU: %dx%d-ray '
+                               'centre crop per step)' % (crop, crop)},
+        'cpu_baseline': {'value': val, 'unit': 'Msamples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': '%dx%d-ray centre crop of the C2 frame per step (oracle/: C DDA + hash encode with '
+                                   'OpenMP, torch fp32 MLP), %d steps' % (crop, crop, args.steps),
+                         'omp_threads': oracle.num_threads()},
+        'e2e': {'value': val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+class FrameRenderer:
+    """The public-API call a user makes per frame: pose (host) -> DDA -> sky -> fused render."""
+
+    def __init__(self, world, P, z, genc, lut, device, precision):
+        from scenedreamer_b200 import ops, render
+        import oracle
+        self.ops, self.render, self.dev = ops, render, device
+        self.P = {k: v.to(device) for k, v in P.items()}
+        self.voxel = world.voxel_t.to(device)
+        _, pls = oracle.grid_offsets()
+        self.r = render.FusedPerPixelRenderer(self.P, world.voxel_t.shape, render.reduced_label_lut(lut), pls,
+                                              precision=precision, preblend=True)
+        self.z, self.genc = z.to(device), genc.to(device)
+        self.launches_per_frame = None
+
+    def frame(self, cam, events=None, ori_dev=None):
+        """cam = (ori, dir, up, f, c, res) with HOST tensors (the reference API takes the pose from the CPU and
+        passes it by value to the DDA kernel); ori_dev: optional device-resident copy of ori for the fused kernel."""
+        o, d, u, f, c, res = cam
+        vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, res, 6)
+        vid, dep, rd = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0)
+        sky = self.render.sky_features(self.P, rd, self.z)
+        sky_avg = sky.mean(dim=(1, 2))
+        if events is not None:
+            events[0].record()
+        out = self.r.forward(vid, dep, rd, (o if ori_dev is None else ori_dev).unsqueeze(0), self.z, self.genc,
+                             num_samples=SPP, sky=sky, sky_avg=sky_avg)
+        if events is not None:
+            events[1].record()
+        return out
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from scenedreamer_b200 import synth, render
+    world_size = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world_size > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    precision = {'fp16': render.PRECISION_FP16, 'bf16x3': render.PRECISION_BF16X3, 'fp16x3': render.PRECISION_FP16X3}[args.precision]
+    world, poses, P, z, genc, lut = build_workload(dev)
+    fr = FrameRenderer(world, P, z, genc, lut, dev, precision)
+    cams = [synth.frame_camera(world, p, OUT_HW, PAD) for p in poses]
+    # pinned host copies of the per-frame inputs (camera pose) and of the per-frame result
+    pose_pinned = [torch.stack([c[0], c[1], c[2]]).pin_memory() for c in cams]
+    res = cams[0][5]
+    host_out = torch.empty(2, res[0], res[1], dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gather_buf = torch.empty(world_size, 2, res[0], res[1], dtype=torch.float32, device=dev) if world_size > 1 else None
+
+    def one_step(k, ev=None, kev=None):
+        idx = (k * world_size + rank) % len(cams)
+        cam = cams[idx]
+        if ev is not None:
+            ev[0].record()
+        pose = pose_pinned[idx]                                      # this step's inputs, pinned host memory:
+        out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev)   # by-value to the DDA, H2D for the rest
+        maps = torch.stack([out['depth'][0], out['total_weight'][0]])
+        if world_size > 1:
+            dist.all_gather_into_tensor(gather_buf, maps)            # the single collective of the path
+        host_out.copy_(maps, non_blocking=True)                      # D2H of the step's result
+        if ev is not None:
+            ev[1].record()
+        return out
+
+    for w in range(max(args.warmup, 3)):
+        one_step(w)
+        flush.zero_()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        one_step(k, evs[k], kevs[k])
+        flush.zero_()                                                # L2 flush between timed iterations
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
+    if world_size > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    kern_ms = [a.elapsed_time(b) for a, b in kevs]
+    tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms, tot_kern_ms = float(tot[0]), float(tot[1])
+
+    # device-only number: inputs resident, no host copies (pose tensors already on the device)
+    doris = [c[0].to(dev) for c in cams]
+    dev_ms = []
+    for k in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        idx = (k * world_size + rank) % len(cams)
+        flush.zero_()
+        a.record()
+        fr.frame(cams[idx], ori_dev=doris[idx])
+        b.record()
+        torch.cuda.synchronize()
+        dev_ms.append(a.elapsed_time(b))
+    dtot = torch.tensor([sum(dev_ms)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(dtot, op=dist.ReduceOp.MAX)
+    dev_tot_ms = float(dtot[0])
+
+    if rank == 0:
+        hbm, tf, which = measured_peaks()
+        frames = args.steps * world_size
+        value = frames * SAMPLES_PER_FRAME / (dev_tot_ms * 1e-3) / 1e6
+        e2e = frames * SAMPLES_PER_FRAME / (tot_ms * 1e-3) / 1e6
+        kern_s = tot_kern_ms * 1e-3 / args.steps
+        achieved = SAMPLES_PER_FRAME * BYTES_PER_SAMPLE / kern_s / 1e9
+        cpu = None
+        if world_size == 1 and not args.no_cpu:
+            import oracle
+            torch.set_num_threads(os.cpu_count())
+            cpu_frame_sample(world, poses[0], P, z, genc, lut, 32)
+            t, n = 0.0, 0
+            while t < 12.0:
+                dt, nn = cpu_frame_sample(world, poses[n % 7], P, z, genc, lut, 64)
+                t, n = t + dt, n + nn
+            cpu = {'value': n / t / 1e6, 'unit': 'Msamples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                   'sample': '64x64-ray centre crops of the C2 frame for %.0f s (oracle/: OpenMP C DDA + hash encode, '
+                             'torch fp32 MLP on all host threads)' % t}
+        line = {
+            'metric': 'rendered Msamples/sec at 960x540x24spp', 'value': value, 'unit': 'Msamples/s',
+            'mpix_per_s': value / SPP, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': dev_tot_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fp16': 'f16 (f32 accumulate)', 'bf16x3': 'bf16x3 split (f32-grade), f32 accumulate',
+                      'fp16x3': 'f16x3 split (f32-grade), f32 accumulate'}[args.precision] + '; table/compositing f32',
+            'data': 'synthetic',
+            'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0, pad 30 '
+                                   '(570x990 rays cast+shaded, 518400 px credited); one frame per GPU per step',
+                       'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
+                       'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'cuBLAS fp32 (per ray)'},
+            'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
+                    'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': tot_ms / args.steps,
+                    'note': 'pose from pinned host memory -> DDA -> sky -> fused render -> depth+opacity maps to pinned host'},
+            'gpu_launches': 4 * args.steps,
+            'gpu_launches_note': 'per step: dda_perspective, pe_forward, prepass, render_kernel (ours) + cuBLAS/ATen for the sky MLP',
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
+                         'traffic': None, 'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)',
+                         'kernel': 'rf::render_kernel (+prepass)', 'kernel_ms': tot_kern_ms / args.steps,
+                         'algorithmic_bytes_per_launch': SAMPLES_PER_FRAME * BYTES_PER_SAMPLE,
+                         'tensor_tflops': SAMPLES_PER_FRAME * 754176 / kern_s / 1e12, 'tensor_peak_tflops': tf},
+            'cpu_baseline': cpu, 'clocks': clocks, 'wall_s': t_wall,
+        }
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='fp16x3', choices=['fp16', 'bf16x3', 'fp16x3'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback '
+                         '(use --impl reference for the CPU baseline)')
+    run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

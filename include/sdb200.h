@@ -131,7 +131,7 @@ typedef struct sdb_render_params {
     /* MLP weights packed by sdb_pack_mlp(): one pack per image (style code), stride bytes     */
     const void *d_mlp_pack;
     int64_t mlp_pack_stride;     /* 0 = all images share one pack                             */
-    int32_t precision;           /* must match the pack: 0 = fp16 x1, 1 = bf16 x3 (fp32-grade) */
+    int32_t precision;           /* must match the pack: 0 = fp16 x1, 1 = bf16 x3, 2 = fp16 x3 */
     /* sky: SKYMLP output per ray [R, 64] and the per-image mean [n_img, 64]                   */
     const float *d_sky;
     const float *d_sky_avg;

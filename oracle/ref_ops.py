@@ -346,7 +346,7 @@ def make_params(seed=0, stress=False, style_dim=128, interm=256, hidden=256, fea
 
     stress=False: module default init followed by custom_init (kaiming_normal(a=0.2)*0.5, zero bias;
                   scenedreamer.py:66-78).  Every layer halves the activation RMS, so outputs are ~1e-3.
-    stress=True : gains chosen so hidden activations stay O(1), sigma spans roughly +-60 and colour
+    stress=True : gains chosen so hidden activations stay O(1), sigma spans roughly +-200 and colour
                   features exceed +-1 (exercises clamp, opacity saturation and the style modulation);
                   this is the weight set the 1e-3 parity bar is meaningful on.
     """
@@ -378,8 +378,8 @@ def make_params(seed=0, stress=False, style_dim=128, interm=256, hidden=256, fea
         P[n + '.bias_alpha'] = torch.ones(hidden)
         P[n + '.weight_beta'] = torch.randn(hidden, interm, generator=g) / np.sqrt(interm) * (0.5 if stress else 1.0)
         P[n + '.bias_beta'] = torch.zeros(hidden)
-    P[r + 'fc_sigma.weight'] = kaiming(1, hidden, wg * (40.0 if stress else 1.0))
-    P[r + 'fc_sigma.bias'] = torch.full((1,), 5.0 if stress else 0.0)
+    P[r + 'fc_sigma.weight'] = kaiming(1, hidden, wg * (120.0 if stress else 1.0))
+    P[r + 'fc_sigma.bias'] = torch.full((1,), 20.0 if stress else 0.0)
     P[r + 'fc_out_c.weight'] = kaiming(out_c, hidden, wg * (1.5 if stress else 1.0))
     P[r + 'fc_out_c.bias'] = torch.randn(out_c, generator=g) * bg
     # sky_net

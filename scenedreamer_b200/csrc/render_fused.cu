@@ -19,8 +19,8 @@
 //     runs; results wait in registers until the operand buffer is free);
 //   * activations stay on chip: TMEM accumulators (256 + 64 columns) and ONE in-place 128x256
 //     operand buffer in shared memory; the only per-sample HBM/L2 traffic is the table gather;
-//   * precision: 0 = one fp16 pass; 1 = bf16 "x3" split (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo,
-//     ~2^-16 relative, i.e. fp32-grade for the 1e-3 parity bar) -- accumulation is fp32 in TMEM;
+//   * precision: 0 = one fp16 pass; 1 / 2 = bf16 / fp16 "x3" split (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo:
+//     ~2^-16 resp. ~2^-21 relative, i.e. fp32-grade for the 1e-3 parity bar); accumulation is fp32 in TMEM;
 //   * sky-only tiles never reach this kernel: a pre-pass writes their outputs and compacts the
 //     list of live tiles (their compositing weights are exactly zero, scenedreamer.py:376).
 #include <math.h>
@@ -216,10 +216,19 @@ __device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint
 }
 
 // 8 fp32 values -> one 16-byte chunk of 16-bit operand (hi) and, for the x3 split, the residual (lo)
-template <bool X3>
+// PREC: 0 = fp16 single pass, 1 = bf16 hi/lo split, 2 = fp16 hi/lo split
+template <int PREC>
 __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
     uint32_t h[4], l[4];
-    if constexpr (X3) {
+    if constexpr (PREC == 2) {
+        // hi = fp16(v) (RN), lo = fp16(v - hi): 22 significant bits (|err| ~ 2^-22 |v|); needs |v| < 65504
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            h[q] = tc05::pack2<false>(v[2 * q], v[2 * q + 1]);
+            const float2 hf = tc05::unpack2<false>(h[q]);
+            l[q] = tc05::pack2<false>(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
+        }
+    } else if constexpr (PREC == 1) {
         // hi = v truncated to bf16 (exactly representable), lo = bf16(v - hi): |err| <= 2^-16 |v|
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -238,10 +247,12 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-template <bool X3, bool RAW5D>
+template <int PREC, bool RAW5D>
 __global__ void __launch_bounds__(kThreads, 1)
 render_kernel(const Params p)
 {
+    constexpr bool X3 = PREC != 0;
+    constexpr bool BF16 = PREC == 1;
     constexpr Smem SM = smem_map(X3);
     constexpr int PARTS = X3 ? 2 : 1;
     constexpr int KS = X3 ? 1 : 2;                 // k16 steps per ring stage
@@ -355,7 +366,7 @@ render_kernel(const Params p)
                         for (int q = 0; q < 4; q++) {
                             uint4 hi, lo;
                             const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
-                            split8<X3>(v8, hi, lo);
+                            split8<PREC>(v8, hi, lo);
                             const uint32_t off = tc05::chunk_off(kRows, row, (c0 >> 3) + q);
                             *reinterpret_cast<uint4 *>(sHhi + off) = hi;
                             if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
@@ -457,7 +468,7 @@ render_kernel(const Params p)
                         if (l == kLayers - 1 && n > 0) tc05::mbar_wait(&bars[B_OUTFREE], (n - 1) & 1);
                         tc05::fence_after_thread_sync();
                         const int N = layerN(l);
-                        const uint32_t idesc = tc05::make_idesc(kRows, N, X3);
+                        const uint32_t idesc = tc05::make_idesc(kRows, N, BF16);
                         const uint32_t dcol = tmem + (l == kLayers - 1 ? kOutCol : kAccCol);
                         const uint32_t slab = (uint32_t)N * 32, lboB = (uint32_t)N * 16;
                         const int nk16 = layerK(l) / 16;
@@ -581,7 +592,7 @@ render_kernel(const Params p)
                     } else {
                         encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
                     }
-                    split8<X3>(res, fh[i], fl[i]);
+                    split8<PREC>(res, fh[i], fl[i]);
                 }
                 if (n > 0) tc05::mbar_wait(&bars[B_HFREE], (n - 1) & 1);
 #pragma unroll
@@ -671,11 +682,12 @@ preblend_kernel(const float *__restrict__ table, float *__restrict__ table3, int
 }
 
 // ---- weight packer ---------------------------------------------------------------------------------
-template <bool X3>
+template <int PREC>
 __global__ void __launch_bounds__(256)
 pack_kernel(const float *w1, const float *b1, const float *emb, int n_labels, const float *wh, const float *bh,
             const float *wsig, const float *bsig, const float *wout, const float *bout, uint8_t *pack)
 {
+    constexpr bool X3 = PREC != 0;
     constexpr int PARTS = X3 ? 2 : 1;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long nW = 0;
@@ -691,11 +703,16 @@ pack_kernel(const float *w1, const float *b1, const float *emb, int n_labels, co
         const int kk = k >> 4, k16 = k & 15;
         const long long slab_off = (long long)(k16 >> 3) * N * 16 + (nn >> 3) * 128 + (nn & 7) * 16 + (k16 & 7) * 2;
         uint8_t *base = pack + layerOff(l, PARTS) + (long long)kk * N * 32 * PARTS;
-        if constexpr (X3) {
+        if constexpr (PREC == 1) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
             *reinterpret_cast<__nv_bfloat16 *>(base + slab_off) = hi;
             *reinterpret_cast<__nv_bfloat16 *>(base + (long long)N * 32 + slab_off) = lo;
+        } else if constexpr (PREC == 2) {
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            *reinterpret_cast<__half *>(base + slab_off) = hi;
+            *reinterpret_cast<__half *>(base + (long long)N * 32 + slab_off) = lo;
         } else {
             *reinterpret_cast<__half *>(base + slab_off) = __float2half_rn(v);
         }
@@ -719,23 +736,26 @@ pack_kernel(const float *w1, const float *b1, const float *emb, int n_labels, co
 
 }  // namespace rf
 
-extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes(precision == 1 ? 2 : 1); }
+extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes(precision != 0 ? 2 : 1); }
 
 extern "C" int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, int32_t n_labels,
                             const float *d_wh, const float *d_bh, const float *d_wsig, const float *d_bsig,
                             const float *d_wout, const float *d_bout, int32_t precision, void *d_pack, void *stream)
 {
     if (!d_w1 || !d_b1 || !d_emb || !d_wh || !d_bh || !d_wsig || !d_bsig || !d_wout || !d_bout || !d_pack) return SDB_EINVAL;
-    if (n_labels < 1 || n_labels > rf::kMaxLabels || precision < 0 || precision > 1) return SDB_EINVAL;
+    if (n_labels < 1 || n_labels > rf::kMaxLabels || precision < 0 || precision > 2) return SDB_EINVAL;
     long long n = rf::kFTotal;
     for (int l = 0; l < rf::kLayers; l++) n += (long long)rf::layerK(l) * rf::layerN(l);
     const int blocks = (int)((n + 255) / 256);
     if (precision == 1)
-        rf::pack_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
-                                                                          d_wout, d_bout, (uint8_t *)d_pack);
+        rf::pack_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
+                                                                       d_wout, d_bout, (uint8_t *)d_pack);
+    else if (precision == 2)
+        rf::pack_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
+                                                                       d_wout, d_bout, (uint8_t *)d_pack);
     else
-        rf::pack_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
-                                                                           d_wout, d_bout, (uint8_t *)d_pack);
+        rf::pack_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
+                                                                       d_wout, d_bout, (uint8_t *)d_pack);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
@@ -767,7 +787,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     if ((sp->d_table == nullptr) == (sp->d_table3 == nullptr)) return SDB_EINVAL;
     if (sp->n_img <= 0 || sp->H <= 0 || sp->W <= 0) return SDB_EINVAL;
     if (sp->M < 1 || sp->M > kMaxM || sp->S < 1 || sp->S > kMaxS || sp->L != kLevels || sp->log2_T < 4 || sp->log2_T > 24 ||
-        sp->precision < 0 || sp->precision > 1 || sp->n_lut < 1)
+        sp->precision < 0 || sp->precision > 2 || sp->n_lut < 1)
         return SDB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     Params p;
@@ -792,17 +812,20 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     prepass_kernel<<<n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
     SDB_CHECK_LAUNCH();
     const int grid = n_tiles < sdb_num_sms() ? n_tiles : sdb_num_sms();
-    const bool x3 = sp->precision == 1;
-    const size_t smem = smem_map(x3).total;
+    const size_t smem = smem_map(sp->precision != 0).total;
 #define SDB_LAUNCH_RENDER(X3_, RAW_)                                                                                   \
     do {                                                                                                               \
         SDB_CUDA(cudaFuncSetAttribute(render_kernel<X3_, RAW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         render_kernel<X3_, RAW_><<<grid, kThreads, smem, st>>>(p);                                                     \
     } while (0)
-    if (x3 && p.raw5d) SDB_LAUNCH_RENDER(true, true);
-    else if (x3) SDB_LAUNCH_RENDER(true, false);
-    else if (p.raw5d) SDB_LAUNCH_RENDER(false, true);
-    else SDB_LAUNCH_RENDER(false, false);
+    switch (sp->precision * 2 + (p.raw5d ? 1 : 0)) {
+        case 0: SDB_LAUNCH_RENDER(0, false); break;
+        case 1: SDB_LAUNCH_RENDER(0, true); break;
+        case 2: SDB_LAUNCH_RENDER(1, false); break;
+        case 3: SDB_LAUNCH_RENDER(1, true); break;
+        case 4: SDB_LAUNCH_RENDER(2, false); break;
+        default: SDB_LAUNCH_RENDER(2, true); break;
+    }
 #undef SDB_LAUNCH_RENDER
     SDB_CHECK_LAUNCH();
     return SDB_OK;

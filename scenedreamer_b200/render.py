@@ -16,7 +16,8 @@ import torch.nn.functional as F
 from . import _lib, ops
 
 PRECISION_FP16 = 0      # one fp16 tensor-core pass per product (~1e-3 relative)
-PRECISION_BF16X3 = 1    # bf16 split, 3 passes, fp32-grade (~2e-5 relative): the parity default
+PRECISION_BF16X3 = 1    # bf16 hi/lo split, 3 passes (~2e-5 relative), range-safe
+PRECISION_FP16X3 = 2    # fp16 hi/lo split, 3 passes (~1e-6 relative, |activations| < 65504): the parity default
 
 
 class _RenderParams(ctypes.Structure):
@@ -61,7 +62,7 @@ def modulated_weights(P, z, prefix='render_net'):
     return torch.cat(wh, 0).contiguous(), torch.cat(bh, 0).contiguous()
 
 
-def pack_mlp(P, z, precision=PRECISION_BF16X3, prefix='render_net'):
+def pack_mlp(P, z, precision=PRECISION_FP16X3, prefix='render_net'):
     """z [N, 256] (style_net output) -> uint8 tensor [N, pack_bytes] on z's device."""
     L = _lib.lib()
     dev = z.device
@@ -122,7 +123,7 @@ def sky_features(P, raydirs, z, prefix='sky_net', pe=(5, True)):
 
 def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_dims, label_lut, mlp_pack, sky, sky_avg,
                         table=None, table3=None, num_samples=24, sample_depth=3.0, dists_scale=0.25, uniforms=None,
-                        precision=PRECISION_BF16X3, per_level_scale=None, base_res=16, log2_T=19, L=16,
+                        precision=PRECISION_FP16X3, per_level_scale=None, base_res=16, log2_T=19, L=16,
                         want_depth=True):
     """Fused a2-a12.  Shapes follow the reference:
     voxel_id [N,H,W,M,1] int32, depth2 [N,2,H,W,M,1], raydirs [N,H,W,1,3], cam_ori [N,3], global_enc [N,2],
@@ -187,7 +188,7 @@ class FusedPerPixelRenderer:
     P: dict of parameters with the reference's state-dict names (render_net.*, sky_net.*,
     hash_encoder.embeddings) on the CUDA device."""
 
-    def __init__(self, P, voxel_dims, label_lut, per_level_scale, precision=PRECISION_BF16X3, preblend=True,
+    def __init__(self, P, voxel_dims, label_lut, per_level_scale, precision=PRECISION_FP16X3, preblend=True,
                  base_res=16, log2_T=19, L=16):
         self.P, self.voxel_dims, self.lut = P, [float(v) for v in voxel_dims], label_lut
         self.pls, self.precision, self.preblend = per_level_scale, precision, preblend
