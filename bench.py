@@ -7,7 +7,7 @@
 A "step" is ONE frame of the C2 workload: 540x960 output pixels, 24 samples/ray,
 scene_size 1024, cam_mode 0, pad 30 -> 570x990 rays raycast + shaded:
     a1  ray/voxel DDA                        (sdb_ray_voxel_intersection_perspective)
-    a9  sky branch: PE kernel + SKYMLP       (PE: ours; the per-RAY 6-layer MLP runs on cuBLAS for now)
+    a9  sky branch: PE + SKYMLP + frame mean  (sdb_sky_forward: same tcgen05 engine, per ray)
     a2-a8, a10-a12 fused per-pixel kernel    (sdb_render_rays_forward: tcgen05 MLP, hash gather, compositing)
 Credit = OUTPUT samples: 518,400 px x 24 = 12,441,600 samples per frame (padding rays are overhead).
 Each step renders a different pose of the 40-frame cam_mode-0 trajectory and L2 is flushed between
@@ -168,8 +168,7 @@ class FrameRenderer:
         o, d, u, f, c, res = cam
         vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, res, 6)
         vid, dep, rd = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0)
-        sky = self.render.sky_features(self.P, rd, self.z)
-        sky_avg = sky.mean(dim=(1, 2))
+        sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
         if events is not None:
             events[0].record()
         out = self.r.forward(vid, dep, rd, (o if ori_dev is None else ori_dev).unsqueeze(0), self.z, self.genc,
@@ -289,15 +288,15 @@ def run_gpu_arm(args):
             'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0, pad 30 '
                                    '(570x990 rays cast+shaded, 518400 px credited); one frame per GPU per step',
                        'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
-                       'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'cuBLAS fp32 (per ray)'},
+                       'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)'},
             'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
                     'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': tot_ms / args.steps,
                     'note': 'pose from pinned host memory -> DDA -> sky -> fused render -> depth+opacity maps to pinned host'},
-            'gpu_launches': 4 * args.steps,
-            'gpu_launches_note': 'per step: dda_perspective, pe_forward, prepass, render_kernel (ours) + cuBLAS/ATen for the sky MLP',
+            'gpu_launches': 5 * args.steps,
+            'gpu_launches_note': 'per step: dda_perspective, mlp_kernel<sky>, sky_mean, prepass, mlp_kernel<render> (all ours)',
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
                          'traffic': None, 'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)',
-                         'kernel': 'rf::render_kernel (+prepass)', 'kernel_ms': tot_kern_ms / args.steps,
+                         'kernel': 'rf::mlp_kernel<render> (+prepass)', 'kernel_ms': tot_kern_ms / args.steps,
                          'algorithmic_bytes_per_launch': SAMPLES_PER_FRAME * BYTES_PER_SAMPLE,
                          'tensor_tflops': SAMPLES_PER_FRAME * 754176 / kern_s / 1e12, 'tensor_peak_tflops': tf},
             'cpu_baseline': cpu, 'clocks': clocks, 'wall_s': t_wall,

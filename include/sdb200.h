@@ -115,7 +115,7 @@ typedef struct sdb_render_params {
     const float *d_fractions;
     const float *d_uniforms;
     /* label translation: reduced label per Minecraft id with ignore already mapped to dirt
-       (mc_utils.py:241-246); labels must be < 16                                              */
+       (mc_utils.py:241-246); labels must be < 15                                              */
     const int32_t *d_label_lut;
     int32_t n_lut;
     /* hash grid, D=5, C=8, every level hashed with T = 2^log2_T entries:
@@ -156,13 +156,30 @@ int sdb_preblend_table(const float *d_table, float *d_table3, int32_t L, int32_t
 
 /* Size in bytes of the packed MLP image for a precision mode, and the packer.  Inputs are DEVICE
  * fp32 row-major matrices of the style-modulated network for ONE style code:
- *   w1 [256,128] b1 [256]; emb [n_labels<=16, 256] (row k = fc_m_a.weight[:, k]);
+ *   w1 [256,128] b1 [256]; emb [n_labels<=15, 256] (row k = fc_m_a.weight[:, k]);
  *   wh [5][256,256] (fc_2..fc_6: weight * alpha per input column) bh [5][256] (beta);
  *   wsig [256] bsig [1]; wout [64,256] bout [64].                                             */
 int64_t sdb_mlp_pack_bytes(int32_t precision);
 int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, int32_t n_labels,
                  const float *d_wh, const float *d_bh, const float *d_wsig, const float *d_bsig,
                  const float *d_wout, const float *d_bout, int32_t precision, void *d_pack, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * a9. Sky branch on the tensor-core engine: PE(raydir, 5 degrees, incl. orig) -> SKYMLP -> sky
+ * features per ray + the per-image mean.  Replaces voxlib.positional_encoding + SKYMLP.forward +
+ * torch.mean on the hot path (scenedreamer.py:368-370, :592-598; gancraft_base.py:150-169).
+ *   pack: sdb_pack_sky_mlp() with w1 [256,33], b1 [256] (= fc1.bias + fc_z_a(z)), wh [4][256,256],
+ *         bh [4][256], wout [64,256], bout [64] (device fp32) for ONE style code;
+ *   d_raydirs [n_img*H*W, 3]; d_sky [n_img*H*W, 64]; d_sky_avg [n_img, 64];
+ *   d_workspace: sdb_sky_workspace_bytes(n_img, H, W) bytes.
+ * ------------------------------------------------------------------------------------------ */
+int64_t sdb_sky_pack_bytes(int32_t precision);
+int sdb_pack_sky_mlp(const float *d_w1, const float *d_b1, const float *d_wh, const float *d_bh,
+                     const float *d_wout, const float *d_bout, int32_t precision, void *d_pack, void *stream);
+int64_t sdb_sky_workspace_bytes(int32_t n_img, int32_t H, int32_t W);
+int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
+                    int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
+                    void *stream);
 
 /* tcgen05 / TMEM self test: C[128,N] = A[128,K] * B[N,K]^T with the exact smem descriptors the
  * fused kernel uses.  d_a, d_b fp32 inputs (rounded to fp16/bf16 inside), d_c fp32 output.

@@ -31,6 +31,11 @@ SIGNATURES = {
     'sdb_mlp_pack_bytes': (c_i64, [c_i32]),
     'sdb_pack_mlp': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_i32, c_void_p, c_void_p]),
+    'sdb_sky_pack_bytes': (c_i64, [c_i32]),
+    'sdb_pack_sky_mlp': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
+    'sdb_sky_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
+    'sdb_sky_forward': (c_int, [c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
     'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
 }
 

@@ -1,5 +1,6 @@
 // Fused per-pixel render for sm_100a: depth sampling -> label lookup -> hash-grid features ->
-// style-modulated sigma/colour MLP on tcgen05 tensor cores -> front-to-back compositing + sky blend.
+// style-modulated sigma/colour MLP on tcgen05 tensor cores -> front-to-back compositing + sky blend,
+// plus the per-ray sky MLP on the same tensor-core engine.
 //
 // Behavioural contract = Generator._forward_perpix of the reference and the tile loop around it
 // (imaginaire/generators/scenedreamer.py:285-428, :600-628) with its callees
@@ -7,21 +8,29 @@
 //   NaN guard / world coords / labels    scenedreamer.py:350-363 (a3, a4)
 //   normalise + scene code + GridEncoder scenedreamer.py:298-303, gridencoder.cu:75-170 (a5, a6)
 //   LightningMLP / ModLinear             model_utils/layers.py:92-126, :241-271 (a8)
+//   PE + SKYMLP                          voxlib/positional_encoding_kernel.cu:40-75, gancraft_base.py:150-169 (a9)
 //   volum_rendering_relu + blending      mc_utils.py:154-161, scenedreamer.py:373-413 (a10, a11)
 //
 // Design (DESIGN.md has the long version)
 //   * persistent CTAs (one per SM); a work item is a 16x8-pixel ray tile = 128 rays = the M of one
 //     tcgen05 MMA; row r of every GEMM is ray r, the tile is walked sample by sample (s = 0..S-1),
 //     so compositing is a per-thread running sum (no cross-thread reduction, any S);
-//   * warp roles: 4 epilogue warps (TMEM -> bias/LeakyReLU -> 16-bit operand in smem; sigma tap;
-//     compositing), 1 weight-loader warp (1-D bulk TMA into a 4-stage ring), 1 MMA-issuer warp,
-//     8 gather warps (hash-grid fetch for the NEXT sample step while the MLP of the current one
-//     runs; results wait in registers until the operand buffer is free);
-//   * activations stay on chip: TMEM accumulators (256 + 64 columns) and ONE in-place 128x256
-//     operand buffer in shared memory; the only per-sample HBM/L2 traffic is the table gather;
+//   * warp roles: 8 epilogue warps (TMEM -> LeakyReLU -> 16-bit operand in smem; sigma tap;
+//     compositing; warps 0-3 own columns 0..127, warps 4-7 columns 128..255 of the same 128 rows),
+//     1 weight-loader warp (1-D bulk TMA into a ring), 1 MMA-issuer warp, 8 gather warps (hash-grid
+//     fetch for the NEXT sample step while the MLP of the current one runs; results wait in
+//     registers until the operand buffer is free);
+//   * MMA / epilogue overlap: accumulators ping-pong between two 256-column TMEM buffers; layer l+1
+//     starts on a 64-column K chunk as soon as the epilogue of layer l has written it (per-chunk
+//     mbarriers), so the tensor pipe only idles while the first chunk of each layer is produced;
+//   * bias, style beta and the label embedding ride in the GEMM: the operand has 16 extra K columns
+//     (one-hot label + constant 1), the weight image carries bias / embedding rows there -- exactly
+//     the reference's fc_m_a(onehot) product -- so the epilogue is LeakyReLU + 16-bit split only;
+//   * activations stay on chip: TMEM accumulators and ONE in-place 128x272 operand buffer in shared
+//     memory; the only per-sample HBM/L2 traffic is the table gather;
 //   * precision: 0 = one fp16 pass; 1 / 2 = bf16 / fp16 "x3" split (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo:
 //     ~2^-16 resp. ~2^-21 relative, i.e. fp32-grade for the 1e-3 parity bar); accumulation is fp32 in TMEM;
-//   * sky-only tiles never reach this kernel: a pre-pass writes their outputs and compacts the
+//   * sky-only tiles never reach the render kernel: a pre-pass writes their outputs and compacts the
 //     list of live tiles (their compositing weights are exactly zero, scenedreamer.py:376).
 #include <math.h>
 
@@ -31,45 +40,63 @@
 namespace rf {
 
 constexpr int kRows = 128, kTileW = 16, kTileH = 8;
-constexpr int kHidden = 256, kFeat = 128, kOutC = 64, kLevels = 16, kLayers = 7;
-constexpr int kMaxM = 8, kMaxS = 64, kMaxLabels = 16;
-constexpr int kEpiThreads = 128, kGatherThreads = 256;
-constexpr int kLoaderWarp = 4, kMmaWarp = 5, kGatherWarp0 = 6;
-constexpr int kThreads = kEpiThreads + 64 + kGatherThreads;   // 448
-constexpr int kStageBytes = 16384, kStages = 4;
-constexpr uint32_t kTmemCols = 512, kAccCol = 0, kOutCol = 256;
+constexpr int kHidden = 256, kFeat = 128, kOutC = 64, kLevels = 16;
+constexpr int kKExt = 16;                       // extra K columns: labels / bias
+constexpr int kKH = kHidden + kKExt;            // 272: K of every layer fed by hidden activations
+constexpr int kMaxM = 8, kMaxS = 64, kMaxLabels = 15;
+constexpr int kEpiThreads = 256, kGatherThreads = 256;
+constexpr int kLoaderWarp = 8, kMmaWarp = 9, kGatherWarp0 = 10;
+constexpr int kThreads = kEpiThreads + 64 + kGatherThreads;   // 576
+constexpr int kRingBytes = 65536;
+constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kLboA = kRows * 16, kSbo = 128;
+constexpr int kHChunks = kKH / 8;               // 34 16-byte k-chunks per row
+constexpr int kHBytes = kHChunks * kRows * 16;  // 69,632 bytes per operand part
+constexpr int kSkyK0 = 48;                      // PE(raydir) 33 + zeros + bias column 47
+constexpr int kRenderK0 = kFeat + kKExt;        // 144
 
-__host__ __device__ constexpr int layerK(int l) { return l == 0 ? kFeat : kHidden; }
-__host__ __device__ constexpr int layerN(int l) { return l == kLayers - 1 ? kOutC : kHidden; }
-__host__ __device__ constexpr int64_t layerOff(int l, int parts) {
+// network shapes: SKY = false: LightningMLP (6 hidden + colour), true: SKYMLP (5 hidden + colour)
+template <bool SKY> struct Net {
+    static constexpr int NH = SKY ? 5 : 6;
+    static constexpr int NL = NH + 1;
+    static constexpr int K0 = SKY ? kSkyK0 : kRenderK0;
+};
+template <bool SKY> __host__ __device__ constexpr int layerK(int l) { return l == 0 ? Net<SKY>::K0 : kKH; }
+template <bool SKY> __host__ __device__ constexpr int layerN(int l) { return l == Net<SKY>::NL - 1 ? kOutC : kHidden; }
+template <bool SKY> __host__ __device__ constexpr int64_t layerOff(int l, int parts) {
     int64_t o = 0;
-    for (int j = 0; j < l; j++) o += (int64_t)layerK(j) * layerN(j) * 2 * parts;
+    for (int j = 0; j < l; j++) o += (int64_t)layerK<SKY>(j) * layerN<SKY>(j) * 2 * parts;
     return o;
 }
-// fp32 tail of the pack (float offsets)
-constexpr int kFBias = 0;            // 6 x 256 (fc_1 bias, beta of fc_2..fc_6)
-constexpr int kFBout = 1536;         // 64
-constexpr int kFWsig = 1600;         // 256
-constexpr int kFBsig = 1856;         // 1
-constexpr int kFEmb = 1864;          // 16 x 256 (label embedding rows)
-constexpr int kFSmemFloats = 1860;   // part staged in shared memory
-constexpr int kFTotal = kFEmb + kMaxLabels * kHidden;
-__host__ __device__ constexpr int64_t packBytes(int parts) { return layerOff(kLayers, parts) + (int64_t)kFTotal * 4; }
+// fp32 tail of the render pack: sigma head
+constexpr int kFWsig = 0, kFBsig = 256, kFTotal = 264;
+template <bool SKY> __host__ __device__ constexpr int64_t packBytes(int parts) {
+    return layerOff<SKY>(Net<SKY>::NL, parts) + (SKY ? 0 : (int64_t)kFTotal * 4);
+}
+// consumption order of the 17 k16 steps of a K=272 layer: extension first (no dependency), then the
+// 64-column chunks in the order the epilogue halves produce them (0 and 2 first, then 1 and 3)
+__device__ __forceinline__ int kk_at(int l, int i) {
+    if (l == 0) return i;
+    if (i == 0) return 16;
+    const int c = (i - 1) >> 2, r = (i - 1) & 3;
+    const int chunk = (c == 1) ? 2 : (c == 2 ? 1 : c);
+    return chunk * 4 + r;
+}
 
 // ---- shared memory map ---------------------------------------------------------------------------
 struct Smem {
-    uint32_t h_hi, h_lo, ring, fsec, scales, frac, state, bars, tmem_slot, total;
+    uint32_t h_hi, h_lo, ring, fsec, scales, frac, sig, state, bars, tmem_slot, total;
 };
 __host__ __device__ constexpr Smem smem_map(bool x3) {
     Smem m{};
     uint32_t o = 0;
-    m.h_hi = o; o += kRows * kHidden * 2;
-    m.h_lo = o; if (x3) o += kRows * kHidden * 2;
-    m.ring = o; o += kStages * kStageBytes;
-    m.fsec = o; o += ((kFSmemFloats * 4 + 15) / 16) * 16;
+    m.h_hi = o; o += kHBytes;
+    m.h_lo = o; if (x3) o += kHBytes;
+    m.ring = o; o += kRingBytes;
+    m.fsec = o; o += kFTotal * 4;
     m.scales = o; o += kLevels * 4;
     m.frac = o; o += ((kMaxS + 1) * 4 + 15) / 16 * 16;
+    m.sig = o; o += 2 * kRows * 4;
     m.state = o; o += 2 * (2 * kMaxM + 6) * kRows * 4;
     m.bars = o; o += 32 * 8;
     m.tmem_slot = o; o += 16;
@@ -86,8 +113,9 @@ constexpr int kStFlags = 2 * kMaxM + 5;      // 1 (uint32: bit0 live, bit1 sky_m
 constexpr int kStFloats = 2 * kMaxM + 6;
 
 // barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_ACT, B_ACC, B_OUTRDY, B_OUTFREE, B_STRDY, B_STFREE = B_STRDY + 2,
-       B_COUNT = B_STFREE + 2 };
+enum { B_WFULL = 0, B_WEMPTY = 8, B_FEAT = 16, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 4, B_OUTRDY, B_EPIDONE, B_STRDY,
+       B_STFREE = B_STRDY + 2, B_COUNT = B_STFREE + 2 };
+static_assert(B_COUNT <= 32, "barrier table");
 
 struct Params {
     int n_img, H, W, M, S;
@@ -107,9 +135,13 @@ struct Params {
     long long pack_stride;
     const float *sky, *sky_avg;
     float *net_out, *depth_out, *total_weight;
-    const int32_t *tile_list;      // [n_live]
+    const int32_t *tile_list;      // [n_live] (render) / nullptr (sky: all tiles)
     const int32_t *n_live;
+    int n_tiles;
     int tiles_x, tiles_y;
+    // sky mode
+    float *sky_out;                // [R, 64]
+    float *sky_partial;            // [n_tiles, 64] per-tile column sums (deterministic mean)
 };
 
 __device__ __constant__ uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u, kPrime3 = 3674653429u, kPrime4 = 2097192037u;
@@ -246,16 +278,20 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+template <int PREC> __device__ __forceinline__ uint32_t one16() { return PREC == 1 ? 0x3F80u : 0x3C00u; }   // 1.0
+
 // ---- the kernel ------------------------------------------------------------------------------------
-template <int PREC, bool RAW5D>
+template <int PREC, bool RAW5D, bool SKY>
 __global__ void __launch_bounds__(kThreads, 1)
-render_kernel(const Params p)
+mlp_kernel(const Params p)
 {
     constexpr bool X3 = PREC != 0;
     constexpr bool BF16 = PREC == 1;
     constexpr Smem SM = smem_map(X3);
     constexpr int PARTS = X3 ? 2 : 1;
-    constexpr int KS = X3 ? 1 : 2;                 // k16 steps per ring stage
+    constexpr int NH = Net<SKY>::NH, NL = Net<SKY>::NL;
+    constexpr int kStageBytes = kHidden * 32 * PARTS;        // one k16 slab (hi [+ lo]) of an N=256 layer
+    constexpr int kStages = kRingBytes / kStageBytes;        // 4 (x3) / 8 (x1)
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sHhi = smem + SM.h_hi;
     uint8_t *sHlo = smem + SM.h_lo;
@@ -263,193 +299,228 @@ render_kernel(const Params p)
     float *sF = reinterpret_cast<float *>(smem + SM.fsec);
     float *sScale = reinterpret_cast<float *>(smem + SM.scales);
     float *sFrac = reinterpret_cast<float *>(smem + SM.frac);
+    float *sSig = reinterpret_cast<float *>(smem + SM.sig);
     float *sState = reinterpret_cast<float *>(smem + SM.state);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM.bars);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM.tmem_slot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_live = *p.n_live;
-    const int n_iter = (n_live > (int)blockIdx.x) ? (n_live - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_work = SKY ? p.n_tiles : *p.n_live;
+    const int n_iter = (n_work > (int)blockIdx.x) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int S = SKY ? 1 : p.S;
 
     // ---- one-time setup ----
     if (tid == 0) {
-        for (int i = 0; i < kStages; i++) { tc05::mbar_init(&bars[B_WFULL + i], 1); tc05::mbar_init(&bars[B_WEMPTY + i], 1); }
+        for (int i = 0; i < 8; i++) { tc05::mbar_init(&bars[B_WFULL + i], 1); tc05::mbar_init(&bars[B_WEMPTY + i], 1); }
         tc05::mbar_init(&bars[B_FEAT], kGatherThreads);
         tc05::mbar_init(&bars[B_HFREE], 1);
-        tc05::mbar_init(&bars[B_ACT], kEpiThreads);
+        for (int i = 0; i < 4; i++) tc05::mbar_init(&bars[B_CHUNK + i], kEpiThreads / 2);
         tc05::mbar_init(&bars[B_ACC], 1);
         tc05::mbar_init(&bars[B_OUTRDY], 1);
-        tc05::mbar_init(&bars[B_OUTFREE], kEpiThreads);
+        tc05::mbar_init(&bars[B_EPIDONE], kEpiThreads);
         for (int i = 0; i < 2; i++) { tc05::mbar_init(&bars[B_STRDY + i], kRows); tc05::mbar_init(&bars[B_STFREE + i], kEpiThreads); }
         tc05::fence_mbar_init();
     }
     if (warp == kLoaderWarp) tc05::tmem_alloc(tmem_slot, kTmemCols);
-    for (int i = tid; i < kLevels; i += kThreads) sScale[i] = exp2f(i * p.level_S) * p.base_res - 1.0f;   // gridencoder.cu:126
-    for (int i = tid; i <= p.S; i += kThreads) sFrac[i] = p.fractions[i];
+    if (!SKY) {
+        for (int i = tid; i < kLevels; i += kThreads) sScale[i] = exp2f(i * p.level_S) * p.base_res - 1.0f;   // gridencoder.cu:126
+        for (int i = tid; i <= p.S; i += kThreads) sFrac[i] = p.fractions[i];
+    }
+    // constant K-extension columns of the hidden operand: column 256 = 1.0 (bias), 257..271 = 0
+    for (int i = tid; i < 2 * kRows; i += kThreads) {
+        const int r = i & (kRows - 1), kc = kHidden / 8 + (i >> 7);
+        const uint4 one = make_uint4((i >> 7) == 0 ? one16<PREC>() : 0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sHhi + tc05::chunk_off(kRows, r, kc)) = one;
+        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + tc05::chunk_off(kRows, r, kc)) = make_uint4(0, 0, 0, 0);
+    }
+    tc05::fence_proxy_async_smem();
     tc05::fence_before_thread_sync();
     __syncthreads();
     tc05::fence_after_thread_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t mask = (1u << p.log2_T) - 1u;
+    const uint32_t mask = SKY ? 0u : ((1u << p.log2_T) - 1u);
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =========================== EPILOGUE / COMPOSITING WARPS ===========================
-        const int row = tid;
-        const uint32_t tm_row = tmem + ((uint32_t)(warp * 32) << 16);
+        const int row = tid & (kRows - 1), half = tid >> 7;          // column half: 128*half .. +127
+        const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t n = 0;                 // global step counter
         int loaded_img = -1;
         for (int it = 0; it < n_iter; it++) {
-            const int tile = p.tile_list[blockIdx.x + it * gridDim.x];
+            const int work = blockIdx.x + it * gridDim.x;
+            const int tile = SKY ? work : p.tile_list[work];
             const TileCoord tc = tile_coord(p, tile);
             const int buf = it & 1;
             const float *st = sState + buf * kStFloats * kRows;
-            const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
-            const float *packF = reinterpret_cast<const float *>(pack + layerOff(kLayers, PARTS));
-            if (loaded_img != tc.img) {
-                // the fp32 tail (biases, sigma weights) of this image's pack -> shared memory.  All 128
-                // epilogue threads are the only readers; a named barrier orders the refill.
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = tid; i < kFSmemFloats; i += kEpiThreads) sF[i] = __ldg(packF + i);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!SKY && loaded_img != tc.img) {
+                // sigma head of this image's pack -> shared memory (epilogue threads are the only readers)
+                const float *packF = reinterpret_cast<const float *>(p.pack + (long long)tc.img * p.pack_stride +
+                                                                     layerOff<SKY>(NL, PARTS));
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int i = tid; i < kFTotal; i += kEpiThreads) sF[i] = __ldg(packF + i);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 loaded_img = tc.img;
             }
-            tc05::mbar_wait(&bars[B_STRDY + buf], (it >> 1) & 1);
-            const uint32_t flags = __float_as_uint(st[kStFlags * kRows + row]);
-            const uint32_t labs = __float_as_uint(st[kStLab * kRows + row]);
-            const bool live = flags & 1u, valid = flags & 4u;
             const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
+            const bool in_img = (y < p.H) && (x < p.W);
             const long long ray = ((long long)tc.img * p.H + y) * p.W + x;
-            const float dir0 = st[(kStDir + 0) * kRows + row];
-            const float ori0 = __ldg(p.cam_ori + tc.img * 3);
-            float outc[kOutC];
+            uint32_t flags = in_img ? 4u : 0u, labs = 0;
+            float dir0 = 0.0f, ori0 = 0.0f;
+            if (!SKY) {
+                tc05::mbar_wait(&bars[B_STRDY + buf], (it >> 1) & 1);
+                flags = __float_as_uint(st[kStFlags * kRows + row]);
+                labs = __float_as_uint(st[kStLab * kRows + row]);
+                dir0 = st[(kStDir + 0) * kRows + row];
+                ori0 = __ldg(p.cam_ori + tc.img * 3);
+            }
+            (void)labs;
+            const bool live = flags & 1u, valid = flags & 4u;
+            float outc[32];
 #pragma unroll
-            for (int c = 0; c < kOutC; c++) outc[c] = 0.0f;
+            for (int c = 0; c < 32; c++) outc[c] = 0.0f;
             float Wsum = 0.0f, Dsum = 0.0f, Eexcl = 0.0f;
             bool is_gnd = false;
 
-            for (int s = 0; s < p.S; s++, n++) {
-                const Sample sm = sample_at(p, st, row, s, sFrac, ray);
-                const int label = (labs >> (4 * sm.idx)) & 15u;
-                is_gnd = is_gnd || (__fadd_rn(__fmul_rn(dir0, sm.depth), ori0) <= 1.0f);   // scenedreamer.py:354,380
-                float sigma = 0.0f;
+            for (int s = 0; s < S; s++, n++) {
+                Sample sm{0.0f, 0.0f, 0};
+                if (!SKY) {
+                    sm = sample_at(p, st, row, s, sFrac, ray);
+                    is_gnd = is_gnd || (__fadd_rn(__fmul_rn(dir0, sm.depth), ori0) <= 1.0f);   // scenedreamer.py:354,380
+                }
+                float sig_part = 0.0f;
 #pragma unroll 1
-                for (int l = 0; l < 6; l++) {
-                    tc05::mbar_wait(&bars[B_ACC], (n * 6 + l) & 1);
+                for (int l = 0; l < NH; l++) {
+                    const uint32_t g = n * NL + l;                   // global layer counter -> accumulator buffer
+                    const uint32_t acc = tm_row + (g & 1u) * 256u + half * 128u;
+                    tc05::mbar_wait(&bars[B_ACC], (n * NH + l) & 1);
                     tc05::fence_after_thread_sync();
-                    const float *bias = sF + kFBias + l * kHidden;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < kHidden; c0 += 32) {
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
                         float v[32];
-                        tc05::tmem_ld32(tm_row + kAccCol + c0, v);
+                        tc05::tmem_ld32(acc + c0, v);
                         tc05::tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float4 b = *reinterpret_cast<const float4 *>(bias + c0 + 4 * q);
-                            v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-                        }
-                        if (l == 0) {   // + fc_m_a(onehot) == embedding row of the sample's label (layers.py:103-105)
-                            const float4 *e4 = reinterpret_cast<const float4 *>(packF + kFEmb + label * kHidden + c0);
-#pragma unroll
-                            for (int q = 0; q < 8; q++) {
-                                const float4 e = __ldg(e4 + q);
-                                v[4 * q + 0] += e.x; v[4 * q + 1] += e.y; v[4 * q + 2] += e.z; v[4 * q + 3] += e.w;
-                            }
-                        }
-#pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.2f * v[j]);          // LeakyReLU(0.2)
-                        if (l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
-                            const float *ws = sF + kFWsig + c0;
+                        if (!SKY && l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
+                            const float *ws = sF + kFWsig + half * 128 + c0;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) sigma = fmaf(v[j], ws[j], sigma);
+                            for (int j = 0; j < 32; j++) sig_part = fmaf(v[j], ws[j], sig_part);
                         }
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             uint4 hi, lo;
                             const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
                             split8<PREC>(v8, hi, lo);
-                            const uint32_t off = tc05::chunk_off(kRows, row, (c0 >> 3) + q);
+                            const uint32_t off = tc05::chunk_off(kRows, row, half * 16 + (c0 >> 3) + q);
                             *reinterpret_cast<uint4 *>(sHhi + off) = hi;
                             if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
                         }
+                        if (c0 & 32) {      // a 64-column K chunk of the next layer's operand is complete
+                            tc05::fence_proxy_async_smem();
+                            tc05::mbar_arrive(&bars[B_CHUNK + half * 2 + (c0 >> 6)]);
+                        }
                     }
-                    tc05::fence_proxy_async_smem();
                     tc05::fence_before_thread_sync();
-                    tc05::mbar_arrive(&bars[B_ACT]);
+                    tc05::mbar_arrive(&bars[B_EPIDONE]);
+                    if (!SKY && l == 3) sSig[half * kRows + row] = sig_part;
                 }
-                sigma += sF[kFBsig];
-                // ---- colour layer + compositing (a10/a11) ----
+                // ---- colour layer ----
+                const uint32_t go = n * NL + NH;
                 tc05::mbar_wait(&bars[B_OUTRDY], n & 1);
                 tc05::fence_after_thread_sync();
-                float c[kOutC];
-                {
-                    float v[32];
-                    tc05::tmem_ld32(tm_row + kOutCol, v);
-                    tc05::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++) c[j] = v[j];
-                    tc05::tmem_ld32(tm_row + kOutCol + 32, v);
-                    tc05::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++) c[32 + j] = v[j];
-                }
+                float c[32];
+                tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * 32u, c);
+                tc05::tmem_ld_wait();
                 tc05::fence_before_thread_sync();
-                tc05::mbar_arrive(&bars[B_OUTFREE]);
-                const float e = __fmul_rn(fmaxf(sigma, 0.0f), __fmul_rn(sm.nd, p.dists_scale));   // mc_utils.py:155
-                const float a = 1.0f - expf(-e);
-                const float b = expf(-Eexcl);
-                float w = a * b;
-                Eexcl = __fadd_rn(Eexcl, e);
-                w = live ? w : 0.0f;                                                              // scenedreamer.py:376
-                Wsum += w;
-                Dsum = fmaf(w, sm.depth, Dsum);
-                const float *bo = sF + kFBout;
+                tc05::mbar_arrive(&bars[B_EPIDONE]);
+                if constexpr (SKY) {
 #pragma unroll
-                for (int j = 0; j < kOutC; j++) {
-                    const float rgb = fminf(fmaxf(c[j] + bo[j], -1.0f), 1.0f) + 1.0f;              // :407-408
-                    outc[j] = fmaf(w, rgb, outc[j]);
+                    for (int j = 0; j < 32; j++) outc[j] = c[j];
+                } else {
+                    // ---- compositing (a10/a11) ----
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const float sigma = (sSig[row] + sSig[kRows + row]) + sF[kFBsig];
+                    const float e = __fmul_rn(fmaxf(sigma, 0.0f), __fmul_rn(sm.nd, p.dists_scale));   // mc_utils.py:155
+                    const float a = 1.0f - expf(-e);
+                    const float b = expf(-Eexcl);
+                    float w = a * b;
+                    Eexcl = __fadd_rn(Eexcl, e);
+                    w = live ? w : 0.0f;                                                              // scenedreamer.py:376
+                    Wsum += w;
+                    Dsum = fmaf(w, sm.depth, Dsum);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float rgb = fminf(fmaxf(c[j], -1.0f), 1.0f) + 1.0f;                     // :407-408
+                        outc[j] = fmaf(w, rgb, outc[j]);
+                    }
                 }
             }
-            // ---- finalize the tile (sky blend, scenedreamer.py:380-413) ----
-            if (valid) {
-                const bool sky_mask = flags & 2u;
-                const bool nosky = (!sky_mask) || is_gnd;
-                const float sky_w = 1.0f - Wsum;
-                const float4 *skp = reinterpret_cast<const float4 *>((nosky ? p.sky_avg + (long long)tc.img * kOutC
-                                                                             : p.sky + ray * kOutC));
-                float4 *dst = reinterpret_cast<float4 *>(p.net_out + ray * kOutC);
+            if constexpr (SKY) {
+                // ---- sky features out + per-tile column sums for the frame-global mean (scenedreamer.py:597) ----
+                if (valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.sky_out + ray * kOutC + half * 32);
 #pragma unroll
-                for (int q = 0; q < kOutC / 4; q++) {
-                    const float4 sk = __ldg(skp + q);
-                    float4 o;
-                    o.x = (outc[4 * q + 0] + sky_w * (fminf(fmaxf(sk.x, -1.0f), 1.0f) + 1.0f)) - 1.0f;
-                    o.y = (outc[4 * q + 1] + sky_w * (fminf(fmaxf(sk.y, -1.0f), 1.0f) + 1.0f)) - 1.0f;
-                    o.z = (outc[4 * q + 2] + sky_w * (fminf(fmaxf(sk.z, -1.0f), 1.0f) + 1.0f)) - 1.0f;
-                    o.w = (outc[4 * q + 3] + sky_w * (fminf(fmaxf(sk.w, -1.0f), 1.0f) + 1.0f)) - 1.0f;
-                    dst[q] = o;
+                    for (int q = 0; q < 8; q++) dst[q] = make_float4(outc[4 * q], outc[4 * q + 1], outc[4 * q + 2], outc[4 * q + 3]);
                 }
-                if (p.depth_out) p.depth_out[ray] = Dsum;
-                if (p.total_weight) p.total_weight[ray] = Wsum;
+                float *red = sSig;      // [4 quadrant warps][64] partial sums, then 64 threads finish
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    float v = valid ? outc[j] : 0.0f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) red[(warp & 3) * kOutC + half * 32 + j] = v;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid < kOutC)
+                    p.sky_partial[(long long)tile * kOutC + tid] =
+                        (red[tid] + red[kOutC + tid]) + (red[2 * kOutC + tid] + red[3 * kOutC + tid]);
+            } else {
+                // ---- finalize the tile (sky blend, scenedreamer.py:380-413) ----
+                if (valid) {
+                    const bool sky_mask = flags & 2u;
+                    const bool nosky = (!sky_mask) || is_gnd;
+                    const float sky_w = 1.0f - Wsum;
+                    const float4 *skp = reinterpret_cast<const float4 *>((nosky ? p.sky_avg + (long long)tc.img * kOutC
+                                                                                 : p.sky + ray * kOutC) + half * 32);
+                    float4 *dst = reinterpret_cast<float4 *>(p.net_out + ray * kOutC + half * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 sk = __ldg(skp + q);
+                        float4 o;
+                        o.x = (outc[4 * q + 0] + sky_w * (fminf(fmaxf(sk.x, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                        o.y = (outc[4 * q + 1] + sky_w * (fminf(fmaxf(sk.y, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                        o.z = (outc[4 * q + 2] + sky_w * (fminf(fmaxf(sk.z, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                        o.w = (outc[4 * q + 3] + sky_w * (fminf(fmaxf(sk.w, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                        dst[q] = o;
+                    }
+                    if (half == 0) {
+                        if (p.depth_out) p.depth_out[ray] = Dsum;
+                        if (p.total_weight) p.total_weight[ray] = Wsum;
+                    }
+                }
+                tc05::mbar_arrive(&bars[B_STFREE + buf]);
             }
-            tc05::mbar_arrive(&bars[B_STFREE + buf]);
         }
     } else if (warp == kLoaderWarp) {
         // =========================== WEIGHT LOADER (1-D bulk TMA) ===========================
         if (lane == 0) {
             uint32_t q = 0;
             for (int it = 0; it < n_iter; it++) {
-                const int tile = p.tile_list[blockIdx.x + it * gridDim.x];
+                const int work = blockIdx.x + it * gridDim.x;
+                const int tile = SKY ? work : p.tile_list[work];
                 const TileCoord tc = tile_coord(p, tile);
                 const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
-                for (int s = 0; s < p.S; s++) {
-                    for (int l = 0; l < kLayers; l++) {
-                        const int nstage = layerK(l) / 16 / KS;
-                        const uint32_t bytes = (uint32_t)KS * layerN(l) * 32 * PARTS;
-                        const uint8_t *src = pack + layerOff(l, PARTS);
-                        for (int g = 0; g < nstage; g++, q++) {
+                for (int s = 0; s < S; s++) {
+                    for (int l = 0; l < NL; l++) {
+                        const int nk16 = layerK<SKY>(l) / 16;
+                        const uint32_t bytes = (uint32_t)layerN<SKY>(l) * 32 * PARTS;
+                        const uint8_t *src = pack + layerOff<SKY>(l, PARTS);
+                        for (int i = 0; i < nk16; i++, q++) {
                             const uint32_t stg = q % kStages, par = (q / kStages) & 1;
-                            tc05::mbar_wait(&bars[B_WEMPTY + stg], par ^ 1);
+                            tc05::mbar_wait_backoff(&bars[B_WEMPTY + stg], par ^ 1, 64);
                             tc05::mbar_arrive_expect_tx(&bars[B_WFULL + stg], bytes);
-                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)g * bytes, bytes, &bars[B_WFULL + stg]);
+                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)kk_at(l, i) * bytes, bytes, &bars[B_WFULL + stg]);
                         }
                     }
                 }
@@ -461,39 +532,44 @@ render_kernel(const Params p)
             uint32_t q = 0, n = 0;
             const uint32_t aHi = tc05::smem_u32(sHhi), aLo = tc05::smem_u32(sHlo), ring = tc05::smem_u32(sRing);
             for (int it = 0; it < n_iter; it++) {
-                for (int s = 0; s < p.S; s++, n++) {
-                    for (int l = 0; l < kLayers; l++) {
+                for (int s = 0; s < S; s++, n++) {
+                    for (int l = 0; l < NL; l++) {
+                        const uint32_t g = n * NL + l;
+                        // accumulator buffer (g & 1) was last read by the epilogue of global layer g-2
+                        if (g >= 2) tc05::mbar_wait(&bars[B_EPIDONE], (g - 2) & 1);
                         if (l == 0) tc05::mbar_wait(&bars[B_FEAT], n & 1);
-                        else tc05::mbar_wait(&bars[B_ACT], (n * 6 + (l - 1)) & 1);
-                        if (l == kLayers - 1 && n > 0) tc05::mbar_wait(&bars[B_OUTFREE], (n - 1) & 1);
                         tc05::fence_after_thread_sync();
-                        const int N = layerN(l);
+                        const int N = layerN<SKY>(l);
                         const uint32_t idesc = tc05::make_idesc(kRows, N, BF16);
-                        const uint32_t dcol = tmem + (l == kLayers - 1 ? kOutCol : kAccCol);
+                        const uint32_t dcol = tmem + (g & 1u) * 256u;
                         const uint32_t slab = (uint32_t)N * 32, lboB = (uint32_t)N * 16;
-                        const int nk16 = layerK(l) / 16;
-                        for (int kk = 0; kk < nk16; kk++) {
-                            const uint32_t stg = q % kStages, par = (q / kStages) & 1;
-                            if (kk % KS == 0) {
-                                tc05::mbar_wait(&bars[B_WFULL + stg], par);
+                        const int nk16 = layerK<SKY>(l) / 16;
+                        for (int i = 0; i < nk16; i++, q++) {
+                            const int kk = kk_at(l, i);
+                            if (l > 0 && i > 0 && ((i - 1) & 3) == 0) {
+                                // 64-column K chunk (kk / 4) of this layer's operand, written by the previous epilogue
+                                tc05::mbar_wait(&bars[B_CHUNK + (kk >> 2)], (n * NH + (l - 1)) & 1);
                                 tc05::fence_after_thread_sync();
                             }
-                            const uint32_t bbase = ring + stg * kStageBytes + (kk % KS) * slab * PARTS;
+                            const uint32_t stg = q % kStages, par = (q / kStages) & 1;
+                            tc05::mbar_wait(&bars[B_WFULL + stg], par);
+                            tc05::fence_after_thread_sync();
+                            const uint32_t bbase = ring + stg * kStageBytes;
                             const uint64_t dAhi = tc05::make_smem_desc(aHi + kk * 2 * kLboA, kLboA, kSbo);
                             const uint64_t dBhi = tc05::make_smem_desc(bbase, lboB, kSbo);
-                            tc05::mma_f16_ss(dcol, dAhi, dBhi, idesc, kk > 0 ? 1u : 0u);
+                            tc05::mma_f16_ss(dcol, dAhi, dBhi, idesc, i > 0 ? 1u : 0u);
                             if constexpr (X3) {
-                                const uint64_t dAlo = tc05::make_smem_desc(aLo + kk * 2 * kLboA, kLboA, kSbo);
                                 const uint64_t dBlo = tc05::make_smem_desc(bbase + slab, lboB, kSbo);
-                                tc05::mma_f16_ss(dcol, dAlo, dBhi, idesc, 1u);
+                                const bool ext = (l > 0 && i == 0);      // A_lo of the constant extension columns is 0
+                                if (!ext) {
+                                    const uint64_t dAlo = tc05::make_smem_desc(aLo + kk * 2 * kLboA, kLboA, kSbo);
+                                    tc05::mma_f16_ss(dcol, dAlo, dBhi, idesc, 1u);
+                                }
                                 tc05::mma_f16_ss(dcol, dAhi, dBlo, idesc, 1u);
                             }
-                            if (kk % KS == KS - 1) {
-                                tc05::mma_commit(&bars[B_WEMPTY + stg]);
-                                q++;
-                            }
+                            tc05::mma_commit(&bars[B_WEMPTY + stg]);
                         }
-                        if (l == kLayers - 1) {
+                        if (l == NL - 1) {
                             tc05::mma_commit(&bars[B_OUTRDY]);
                             tc05::mma_commit(&bars[B_HFREE]);
                         } else {
@@ -504,105 +580,164 @@ render_kernel(const Params p)
             }
         }
     } else {
-        // =========================== GATHER WARPS (hash-grid fetch) ===========================
+        // =========================== GATHER WARPS (layer-0 operand producers) ===========================
         const int gt = tid - kGatherWarp0 * 32;
         const int row = gt & (kRows - 1), half = gt >> 7;
         uint32_t n = 0;
         for (int it = 0; it < n_iter; it++) {
-            const int tile = p.tile_list[blockIdx.x + it * gridDim.x];
+            const int work = blockIdx.x + it * gridDim.x;
+            const int tile = SKY ? work : p.tile_list[work];
             const TileCoord tc = tile_coord(p, tile);
-            const int buf = it & 1;
-            float *st = sState + buf * kStFloats * kRows;
             const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
             const bool valid = (y < p.H) && (x < p.W);
             const long long pix = (long long)y * p.W + x, hw = (long long)p.H * p.W;
             const long long ray = (long long)tc.img * hw + pix;
-            // ---- per-ray sampling state (first 128 gather threads) ----
-            if (it >= 2) tc05::mbar_wait(&bars[B_STFREE + buf], ((it >> 1) - 1) & 1);
-            if (half == 0) {
-                float accu = 0.0f, cum = 0.0f, entry0 = 0.0f, prev_exit = 0.0f;
-                uint32_t labs = 0, flags = 0;
-                int32_t id0 = 0, idl = 0;
+            if constexpr (SKY) {
+                // ---- positional encoding of the ray direction (positional_encoding_kernel.cu:58-72): 5 degrees + orig ----
+                uint4 ch[6], cl[6];
+                if (half == 0) {
+                    float pe[kSkyK0];
 #pragma unroll
-                for (int j = 0; j < kMaxM; j++) {
-                    if (j < p.M) {
-                        float en = 0.0f, ex = 0.0f;
-                        int32_t id = 0;
-                        if (valid) {
-                            id = __ldg(p.voxel_id + ray * p.M + j);
-                            en = __ldg(p.depth2 + ((long long)tc.img * 2 + 0) * hw * p.M + pix * p.M + j);
-                            ex = __ldg(p.depth2 + ((long long)tc.img * 2 + 1) * hw * p.M + pix * p.M + j);
+                    for (int k = 0; k < kSkyK0; k++) pe[k] = 0.0f;
+                    if (valid) {
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const float v = __ldg(p.raydirs + ray * 3 + d);
+#pragma unroll
+                            for (int i = 0; i < 5; i++) {
+                                const float rad = v * 3.14159265358979323846f * exp2f((float)i);
+                                float sn, cs;
+                                sincosf(rad, &sn, &cs);
+                                pe[(2 * i) * 3 + d] = sn;
+                                pe[(2 * i + 1) * 3 + d] = cs;
+                            }
+                            pe[30 + d] = v;
                         }
-                        float d = __fsub_rn(ex, en);                       // mc_utils.py:102-104
-                        if (d != d) d = 0.0f;
-                        accu = (j == 0) ? d : __fadd_rn(accu, d);
-                        st[(kStAccu + j) * kRows + row] = accu;
-                        if (j == 0) {
-                            entry0 = en;
-                            st[(kStHeads + 0) * kRows + row] = en;
-                        } else {                                           // :141-143
-                            const float dd = __fsub_rn(en, prev_exit);
-                            cum = (j == 1) ? dd : __fadd_rn(cum, dd);
-                            st[(kStHeads + j) * kRows + row] = __fadd_rn(cum, entry0);
-                        }
-                        prev_exit = ex;
-                        int lid = (id >= 0 && id < p.n_lut) ? __ldg(p.lut + id) : 0;
-                        labs |= ((uint32_t)lid & 15u) << (4 * j);
-                        if (j == 0) id0 = id;
-                        idl = id;
+                    }
+                    pe[kSkyK0 - 1] = 1.0f;      // bias column
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&pe[8 * c]);
+                        split8<PREC>(v8, ch[c], cl[c]);
                     }
                 }
-                st[kStTotal * kRows + row] = fminf(accu, p.sample_depth);   // :107
-                flags = (valid && id0 != 0 ? 1u : 0u) | (idl == 0 ? 2u : 0u) | (valid ? 4u : 0u);
-                st[kStLab * kRows + row] = __uint_as_float(labs);
-                st[kStFlags * kRows + row] = __uint_as_float(flags);
+                if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
+                if (half == 0) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) st[(kStDir + k) * kRows + row] = valid ? __ldg(p.raydirs + ray * 3 + k) : 0.0f;
-            }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (half == 0) tc05::mbar_arrive(&bars[B_STRDY + buf]);
-            const bool live = __float_as_uint(st[kStFlags * kRows + row]) & 1u;
-            const float d0 = st[(kStDir + 0) * kRows + row], d1 = st[(kStDir + 1) * kRows + row], d2 = st[(kStDir + 2) * kRows + row];
-            const float o0 = __ldg(p.cam_ori + tc.img * 3 + 0), o1 = __ldg(p.cam_ori + tc.img * 3 + 1), o2 = __ldg(p.cam_ori + tc.img * 3 + 2);
-            float x5[5];
-            x5[3] = __fmul_rn(__fadd_rn(__ldg(p.genc + tc.img * 2 + 0), 1.0f), 0.5f);   // grid.py:144 on dims 3,4
-            x5[4] = __fmul_rn(__fadd_rn(__ldg(p.genc + tc.img * 2 + 1), 1.0f), 0.5f);
-
-            for (int s = 0; s < p.S; s++, n++) {
-                uint4 fh[8], fl[8];
-                const Sample sm = sample_at(p, st, row, s, sFrac, ray);
-                // world coordinate, normalisation and [0,1] mapping with the reference's operation order
-                // (scenedreamer.py:354, :299; grid.py:144): p = dir*t + ori; p / dim * 2 - 1; (x + 1) / 2
-                const float pw[3] = {__fadd_rn(__fmul_rn(d0, sm.depth), o0), __fadd_rn(__fmul_rn(d1, sm.depth), o1),
-                                     __fadd_rn(__fmul_rn(d2, sm.depth), o2)};
-                bool oob = !live;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(pw[k], p.vdim[k]), 2.0f), 1.0f);
-                    x5[k] = __fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f);
-                    if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
-                }
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int level = half + 2 * i;
-                    float res[8];
-                    if (oob) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) res[c] = 0.0f;
-                    } else {
-                        encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                    for (int c = 0; c < 6; c++) {
+                        const uint32_t off = tc05::chunk_off(kRows, row, c);
+                        *reinterpret_cast<uint4 *>(sHhi + off) = ch[c];
+                        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = cl[c];
                     }
-                    split8<PREC>(res, fh[i], fl[i]);
-                }
-                if (n > 0) tc05::mbar_wait(&bars[B_HFREE], (n - 1) & 1);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint32_t off = tc05::chunk_off(kRows, row, half + 2 * i);
-                    *reinterpret_cast<uint4 *>(sHhi + off) = fh[i];
-                    if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = fl[i];
                 }
                 tc05::fence_proxy_async_smem();
                 tc05::mbar_arrive(&bars[B_FEAT]);
+                n++;
+            } else {
+                const int buf = it & 1;
+                float *st = sState + buf * kStFloats * kRows;
+                // ---- per-ray sampling state (first 128 gather threads) ----
+                if (it >= 2) tc05::mbar_wait_backoff(&bars[B_STFREE + buf], ((it >> 1) - 1) & 1);
+                if (half == 0) {
+                    float accu = 0.0f, cum = 0.0f, entry0 = 0.0f, prev_exit = 0.0f;
+                    uint32_t labs = 0, flags = 0;
+                    int32_t id0 = 0, idl = 0;
+#pragma unroll
+                    for (int j = 0; j < kMaxM; j++) {
+                        if (j < p.M) {
+                            float en = 0.0f, ex = 0.0f;
+                            int32_t id = 0;
+                            if (valid) {
+                                id = __ldg(p.voxel_id + ray * p.M + j);
+                                en = __ldg(p.depth2 + ((long long)tc.img * 2 + 0) * hw * p.M + pix * p.M + j);
+                                ex = __ldg(p.depth2 + ((long long)tc.img * 2 + 1) * hw * p.M + pix * p.M + j);
+                            }
+                            float d = __fsub_rn(ex, en);                       // mc_utils.py:102-104
+                            if (d != d) d = 0.0f;
+                            accu = (j == 0) ? d : __fadd_rn(accu, d);
+                            st[(kStAccu + j) * kRows + row] = accu;
+                            if (j == 0) {
+                                entry0 = en;
+                                st[(kStHeads + 0) * kRows + row] = en;
+                            } else {                                           // :141-143
+                                const float dd = __fsub_rn(en, prev_exit);
+                                cum = (j == 1) ? dd : __fadd_rn(cum, dd);
+                                st[(kStHeads + j) * kRows + row] = __fadd_rn(cum, entry0);
+                            }
+                            prev_exit = ex;
+                            int lid = (id >= 0 && id < p.n_lut) ? __ldg(p.lut + id) : 0;
+                            labs |= ((uint32_t)lid & 15u) << (4 * j);
+                            if (j == 0) id0 = id;
+                            idl = id;
+                        }
+                    }
+                    st[kStTotal * kRows + row] = fminf(accu, p.sample_depth);   // :107
+                    flags = (valid && id0 != 0 ? 1u : 0u) | (idl == 0 ? 2u : 0u) | (valid ? 4u : 0u);
+                    st[kStLab * kRows + row] = __uint_as_float(labs);
+                    st[kStFlags * kRows + row] = __uint_as_float(flags);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) st[(kStDir + k) * kRows + row] = valid ? __ldg(p.raydirs + ray * 3 + k) : 0.0f;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0) tc05::mbar_arrive(&bars[B_STRDY + buf]);
+                const bool live = __float_as_uint(st[kStFlags * kRows + row]) & 1u;
+                const uint32_t labs = __float_as_uint(st[kStLab * kRows + row]);
+                const float d0 = st[(kStDir + 0) * kRows + row], d1 = st[(kStDir + 1) * kRows + row], d2 = st[(kStDir + 2) * kRows + row];
+                const float o0 = __ldg(p.cam_ori + tc.img * 3 + 0), o1 = __ldg(p.cam_ori + tc.img * 3 + 1), o2 = __ldg(p.cam_ori + tc.img * 3 + 2);
+                float x5[5];
+                x5[3] = __fmul_rn(__fadd_rn(__ldg(p.genc + tc.img * 2 + 0), 1.0f), 0.5f);   // grid.py:144 on dims 3,4
+                x5[4] = __fmul_rn(__fadd_rn(__ldg(p.genc + tc.img * 2 + 1), 1.0f), 0.5f);
+
+                for (int s = 0; s < S; s++, n++) {
+                    uint4 fh[8], fl[8];
+                    const Sample sm = sample_at(p, st, row, s, sFrac, ray);
+                    // world coordinate, normalisation and [0,1] mapping with the reference's operation order
+                    // (scenedreamer.py:354, :299; grid.py:144): p = dir*t + ori; p / dim * 2 - 1; (x + 1) / 2
+                    const float pw[3] = {__fadd_rn(__fmul_rn(d0, sm.depth), o0), __fadd_rn(__fmul_rn(d1, sm.depth), o1),
+                                         __fadd_rn(__fmul_rn(d2, sm.depth), o2)};
+                    bool oob = !live;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(pw[k], p.vdim[k]), 2.0f), 1.0f);
+                        x5[k] = __fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f);
+                        if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int level = half + 2 * i;
+                        float res[8];
+                        if (oob) {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) res[c] = 0.0f;
+                        } else {
+                            encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                        }
+                        split8<PREC>(res, fh[i], fl[i]);
+                    }
+                    // K-extension of layer 0: one-hot label (columns 128..142) and the constant-1 bias column 143
+                    // == the reference's fc_m_a(onehot) product and fc_1's bias (layers.py:102-105)
+                    const uint32_t label = (labs >> (4 * sm.idx)) & 15u;
+                    uint32_t oh[4] = {0u, 0u, 0u, 0u};
+                    {
+                        const int k = (int)label - 8 * half;                     // position inside this thread's 8-wide chunk
+                        if (k >= 0 && k < 8) oh[k >> 1] = one16<PREC>() << (16 * (k & 1));
+                        if (half == 1) oh[3] |= one16<PREC>() << 16;             // column 143
+                    }
+                    if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t off = tc05::chunk_off(kRows, row, half + 2 * i);
+                        *reinterpret_cast<uint4 *>(sHhi + off) = fh[i];
+                        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = fl[i];
+                    }
+                    {
+                        const uint32_t off = tc05::chunk_off(kRows, row, kFeat / 8 + half);
+                        *reinterpret_cast<uint4 *>(sHhi + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = make_uint4(0, 0, 0, 0);
+                    }
+                    tc05::fence_proxy_async_smem();
+                    tc05::mbar_arrive(&bars[B_FEAT]);
+                }
             }
         }
     }
@@ -645,6 +780,17 @@ prepass_kernel(const Params p, int32_t *tile_list, int32_t *n_live)
     if (p.total_weight) p.total_weight[ray] = 0.0f;
 }
 
+// frame-global sky mean from the per-tile partial sums, fixed summation order (deterministic)
+__global__ void __launch_bounds__(kOutC)
+sky_mean_kernel(const float *__restrict__ partial, float *__restrict__ sky_avg, int tiles_per_img, float inv_count)
+{
+    const int img = blockIdx.x, c = threadIdx.x;
+    const float *pp = partial + (long long)img * tiles_per_img * kOutC + c;
+    float acc = 0.0f;
+    for (int t = 0; t < tiles_per_img; t++) acc += pp[(long long)t * kOutC];
+    sky_avg[img * kOutC + c] = acc * inv_count;
+}
+
 // ---- per-scene pre-blend of the two constant encoder dims -------------------------------------------
 __global__ void __launch_bounds__(256)
 preblend_kernel(const float *__restrict__ table, float *__restrict__ table3, int L, int log2_T, float level_S, int base_res,
@@ -682,27 +828,47 @@ preblend_kernel(const float *__restrict__ table, float *__restrict__ table3, int
 }
 
 // ---- weight packer ---------------------------------------------------------------------------------
-template <int PREC>
+// One thread per (layer, n, k) element of the K-extended weight matrices.
+//   render: layer 0 [256 x 144]: cols 0..127 fc_1.weight, 128+lab emb[lab][n], 143 fc_1.bias;
+//           layers 1..5 [256 x 272]: cols 0..255 W*alpha, 256 beta; colour [64 x 272]: W, 256 bias
+//   sky:    layer 0 [256 x 48]: cols 0..32 fc1.weight, 47 bias (fc1.bias + fc_z_a(z)); layers 1..4, colour as above
+template <int PREC, bool SKY>
 __global__ void __launch_bounds__(256)
-pack_kernel(const float *w1, const float *b1, const float *emb, int n_labels, const float *wh, const float *bh,
+pack_kernel(const float *w0, const float *b0, const float *emb, int n_labels, const float *wh, const float *bh,
             const float *wsig, const float *bsig, const float *wout, const float *bout, uint8_t *pack)
 {
     constexpr bool X3 = PREC != 0;
     constexpr int PARTS = X3 ? 2 : 1;
+    constexpr int NL = Net<SKY>::NL;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long nW = 0;
-    for (int l = 0; l < kLayers; l++) nW += (long long)layerK(l) * layerN(l);
+    for (int l = 0; l < NL; l++) nW += (long long)layerK<SKY>(l) * layerN<SKY>(l);
     if (t < nW) {
         long long r = t;
         int l = 0;
-        while (r >= (long long)layerK(l) * layerN(l)) { r -= (long long)layerK(l) * layerN(l); l++; }
-        const int K = layerK(l), N = layerN(l);
+        while (r >= (long long)layerK<SKY>(l) * layerN<SKY>(l)) { r -= (long long)layerK<SKY>(l) * layerN<SKY>(l); l++; }
+        const int K = layerK<SKY>(l), N = layerN<SKY>(l);
         const int nn = (int)(r / K), k = (int)(r % K);
-        const float *src = (l == 0) ? w1 : (l == kLayers - 1 ? wout : wh + (long long)(l - 1) * kHidden * kHidden);
-        const float v = src[(long long)nn * K + k];
+        float v = 0.0f;
+        if (l == 0) {
+            if (SKY) {
+                if (k < 33) v = w0[(long long)nn * 33 + k];
+                else if (k == kSkyK0 - 1) v = b0[nn];
+            } else {
+                if (k < kFeat) v = w0[(long long)nn * kFeat + k];
+                else if (k == kRenderK0 - 1) v = b0[nn];
+                else if (k - kFeat < n_labels) v = emb[(long long)(k - kFeat) * kHidden + nn];
+            }
+        } else if (l == NL - 1) {
+            if (k < kHidden) v = wout[(long long)nn * kHidden + k];
+            else if (k == kHidden) v = bout[nn];
+        } else {
+            if (k < kHidden) v = wh[((long long)(l - 1) * kHidden + nn) * kHidden + k];
+            else if (k == kHidden) v = bh[(long long)(l - 1) * kHidden + nn];
+        }
         const int kk = k >> 4, k16 = k & 15;
         const long long slab_off = (long long)(k16 >> 3) * N * 16 + (nn >> 3) * 128 + (nn & 7) * 16 + (k16 & 7) * 2;
-        uint8_t *base = pack + layerOff(l, PARTS) + (long long)kk * N * 32 * PARTS;
+        uint8_t *base = pack + layerOff<SKY>(l, PARTS) + (long long)kk * N * 32 * PARTS;
         if constexpr (PREC == 1) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -718,25 +884,46 @@ pack_kernel(const float *w1, const float *b1, const float *emb, int n_labels, co
         }
         return;
     }
+    if (SKY) return;
     const long long u = t - nW;
     if (u >= kFTotal) return;
-    float *F = reinterpret_cast<float *>(pack + layerOff(kLayers, PARTS));
+    float *F = reinterpret_cast<float *>(pack + layerOff<SKY>(NL, PARTS));
     float v = 0.0f;
-    if (u < 256) v = b1[u];
-    else if (u < kFBout) v = bh[u - 256];
-    else if (u < kFBout + kOutC) v = bout[u - kFBout];
-    else if (u >= kFWsig && u < kFWsig + kHidden) v = wsig[u - kFWsig];
+    if (u < kHidden) v = wsig[u];
     else if (u == kFBsig) v = bsig[0];
-    else if (u >= kFEmb) {
-        const int lab = (int)(u - kFEmb) / kHidden, c = (int)(u - kFEmb) % kHidden;
-        v = lab < n_labels ? emb[(long long)lab * kHidden + c] : 0.0f;
-    }
     F[u] = v;
+}
+
+template <bool SKY>
+int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels, const float *wh, const float *bh,
+                const float *wsig, const float *bsig, const float *wout, const float *bout, int precision, void *pack,
+                cudaStream_t st) {
+    long long n = SKY ? 0 : kFTotal;
+    for (int l = 0; l < Net<SKY>::NL; l++) n += (long long)layerK<SKY>(l) * layerN<SKY>(l);
+    const int blocks = (int)((n + 255) / 256);
+    if (precision == 1)
+        pack_kernel<1, SKY><<<blocks, 256, 0, st>>>(w0, b0, emb, n_labels, wh, bh, wsig, bsig, wout, bout, (uint8_t *)pack);
+    else if (precision == 2)
+        pack_kernel<2, SKY><<<blocks, 256, 0, st>>>(w0, b0, emb, n_labels, wh, bh, wsig, bsig, wout, bout, (uint8_t *)pack);
+    else
+        pack_kernel<0, SKY><<<blocks, 256, 0, st>>>(w0, b0, emb, n_labels, wh, bh, wsig, bsig, wout, bout, (uint8_t *)pack);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}
+
+template <int PREC, bool RAW5D, bool SKY>
+int launch_mlp(const Params &p, int grid, cudaStream_t st) {
+    const size_t smem = smem_map(PREC != 0).total;
+    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, SKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_kernel<PREC, RAW5D, SKY><<<grid, kThreads, smem, st>>>(p);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
 }
 
 }  // namespace rf
 
-extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes(precision != 0 ? 2 : 1); }
+extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes<false>(precision != 0 ? 2 : 1); }
+extern "C" int64_t sdb_sky_pack_bytes(int32_t precision) { return rf::packBytes<true>(precision != 0 ? 2 : 1); }
 
 extern "C" int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, int32_t n_labels,
                             const float *d_wh, const float *d_bh, const float *d_wsig, const float *d_bsig,
@@ -744,20 +931,17 @@ extern "C" int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d
 {
     if (!d_w1 || !d_b1 || !d_emb || !d_wh || !d_bh || !d_wsig || !d_bsig || !d_wout || !d_bout || !d_pack) return SDB_EINVAL;
     if (n_labels < 1 || n_labels > rf::kMaxLabels || precision < 0 || precision > 2) return SDB_EINVAL;
-    long long n = rf::kFTotal;
-    for (int l = 0; l < rf::kLayers; l++) n += (long long)rf::layerK(l) * rf::layerN(l);
-    const int blocks = (int)((n + 255) / 256);
-    if (precision == 1)
-        rf::pack_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
-                                                                       d_wout, d_bout, (uint8_t *)d_pack);
-    else if (precision == 2)
-        rf::pack_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
-                                                                       d_wout, d_bout, (uint8_t *)d_pack);
-    else
-        rf::pack_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig,
-                                                                       d_wout, d_bout, (uint8_t *)d_pack);
-    SDB_CHECK_LAUNCH();
-    return SDB_OK;
+    return rf::launch_pack<false>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig, d_wout, d_bout, precision, d_pack,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" int sdb_pack_sky_mlp(const float *d_w1, const float *d_b1, const float *d_wh, const float *d_bh,
+                                const float *d_wout, const float *d_bout, int32_t precision, void *d_pack, void *stream)
+{
+    if (!d_w1 || !d_b1 || !d_wh || !d_bh || !d_wout || !d_bout || !d_pack) return SDB_EINVAL;
+    if (precision < 0 || precision > 2) return SDB_EINVAL;
+    return rf::launch_pack<true>(d_w1, d_b1, nullptr, 0, d_wh, d_bh, nullptr, nullptr, d_wout, d_bout, precision, d_pack,
+                                 (cudaStream_t)stream);
 }
 
 extern "C" int sdb_preblend_table(const float *d_table, float *d_table3, int32_t L, int32_t log2_T, float level_S,
@@ -771,10 +955,45 @@ extern "C" int sdb_preblend_table(const float *d_table, float *d_table3, int32_t
     return SDB_OK;
 }
 
+static int64_t sdb_num_tiles(int32_t n_img, int32_t H, int32_t W) {
+    return (int64_t)n_img * sdb_div_up(H, rf::kTileH) * sdb_div_up(W, rf::kTileW);
+}
+
 extern "C" int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
     if (n_img <= 0 || H <= 0 || W <= 0) return 0;
-    const int64_t tiles = (int64_t)n_img * sdb_div_up(H, rf::kTileH) * sdb_div_up(W, rf::kTileW);
-    return (tiles + 4) * 4;
+    return (sdb_num_tiles(n_img, H, W) + 4) * 4;
+}
+
+extern "C" int64_t sdb_sky_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
+    if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+    return sdb_num_tiles(n_img, H, W) * rf::kOutC * 4;
+}
+
+extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
+                               int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
+                               void *stream)
+{
+    using namespace rf;
+    if (!d_raydirs || !d_sky_pack || !d_sky || !d_sky_avg || !d_workspace) return SDB_EINVAL;
+    if (n_img <= 0 || H <= 0 || W <= 0) return SDB_EINVAL;
+    if (precision < 0 || precision > 2) return SDB_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    Params p{};
+    p.n_img = n_img; p.H = H; p.W = W; p.M = 1; p.S = 1;
+    p.raydirs = d_raydirs;
+    p.pack = (const uint8_t *)d_sky_pack; p.pack_stride = pack_stride;
+    p.sky_out = d_sky; p.sky_partial = (float *)d_workspace;
+    p.tiles_x = sdb_div_up(W, kTileW); p.tiles_y = sdb_div_up(H, kTileH);
+    p.n_tiles = n_img * p.tiles_x * p.tiles_y;
+    const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
+    int rc;
+    if (precision == 1) rc = launch_mlp<1, false, true>(p, grid, st);
+    else if (precision == 2) rc = launch_mlp<2, false, true>(p, grid, st);
+    else rc = launch_mlp<0, false, true>(p, grid, st);
+    if (rc != SDB_OK) return rc;
+    sky_mean_kernel<<<n_img, kOutC, 0, st>>>(p.sky_partial, d_sky_avg, p.tiles_x * p.tiles_y, 1.0f / ((float)H * (float)W));
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
 }
 
 extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream)
@@ -790,7 +1009,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         sp->precision < 0 || sp->precision > 2 || sp->n_lut < 1)
         return SDB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    Params p;
+    Params p{};
     p.n_img = sp->n_img; p.H = sp->H; p.W = sp->W; p.M = sp->M; p.S = sp->S;
     p.voxel_id = sp->d_voxel_id; p.depth2 = sp->d_depth2; p.raydirs = sp->d_raydirs; p.cam_ori = sp->d_cam_ori;
     p.genc = sp->d_global_enc;
@@ -805,28 +1024,19 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     p.sky = sp->d_sky; p.sky_avg = sp->d_sky_avg;
     p.net_out = sp->d_net_out; p.depth_out = sp->d_depth_out; p.total_weight = sp->d_total_weight;
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
-    const int n_tiles = p.n_img * p.tiles_x * p.tiles_y;
+    p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
     int32_t *ws = (int32_t *)sp->d_workspace;
     p.n_live = ws; p.tile_list = ws + 4;
     SDB_CUDA(cudaMemsetAsync(ws, 0, 16, st));
-    prepass_kernel<<<n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
+    prepass_kernel<<<p.n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
     SDB_CHECK_LAUNCH();
-    const int grid = n_tiles < sdb_num_sms() ? n_tiles : sdb_num_sms();
-    const size_t smem = smem_map(sp->precision != 0).total;
-#define SDB_LAUNCH_RENDER(X3_, RAW_)                                                                                   \
-    do {                                                                                                               \
-        SDB_CUDA(cudaFuncSetAttribute(render_kernel<X3_, RAW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        render_kernel<X3_, RAW_><<<grid, kThreads, smem, st>>>(p);                                                     \
-    } while (0)
+    const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
     switch (sp->precision * 2 + (p.raw5d ? 1 : 0)) {
-        case 0: SDB_LAUNCH_RENDER(0, false); break;
-        case 1: SDB_LAUNCH_RENDER(0, true); break;
-        case 2: SDB_LAUNCH_RENDER(1, false); break;
-        case 3: SDB_LAUNCH_RENDER(1, true); break;
-        case 4: SDB_LAUNCH_RENDER(2, false); break;
-        default: SDB_LAUNCH_RENDER(2, true); break;
+        case 0: return launch_mlp<0, false, false>(p, grid, st);
+        case 1: return launch_mlp<0, true, false>(p, grid, st);
+        case 2: return launch_mlp<1, false, false>(p, grid, st);
+        case 3: return launch_mlp<1, true, false>(p, grid, st);
+        case 4: return launch_mlp<2, false, false>(p, grid, st);
+        default: return launch_mlp<2, true, false>(p, grid, st);
     }
-#undef SDB_LAUNCH_RENDER
-    SDB_CHECK_LAUNCH();
-    return SDB_OK;
 }

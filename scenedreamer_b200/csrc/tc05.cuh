@@ -121,6 +121,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// For waits that are NOT on the critical path (producers running ahead): back off with nanosleep so
+// the spinning warps do not steal issue slots from the warps doing the epilogue math on the same SMSP.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns = 256) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- 1-D bulk async copy global -> shared (TMA engine), completion on an mbarrier -------------
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

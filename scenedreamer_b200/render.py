@@ -109,8 +109,50 @@ def stratified_offsets(S, device):
     return torch.linspace(0, 1, S + 2, device=device)[:-1].contiguous()
 
 
+def pack_sky_mlp(P, z, precision=PRECISION_FP16X3, prefix='sky_net'):
+    """z [N, 256] -> uint8 [N, sky_pack_bytes]: SKYMLP weights with fc_z_a(z) folded into the first bias."""
+    L = _lib.lib()
+    dev = z.device
+    nbytes = int(L.sdb_sky_pack_bytes(int(precision)))
+    N = z.shape[0]
+    pack = torch.empty(N, nbytes, dtype=torch.uint8, device=dev)
+    p = prefix + '.'
+    w1 = P[p + 'fc1.weight'].contiguous()
+    wh = torch.stack([P[p + 'fc%d.weight' % k] for k in (2, 3, 4, 5)]).contiguous()
+    bh = torch.stack([P[p + 'fc%d.bias' % k] for k in (2, 3, 4, 5)]).contiguous()
+    wout = P[p + 'fc_out_c.weight'].contiguous()
+    bout = P[p + 'fc_out_c.bias'].contiguous()
+    zz = F.linear(z, P[p + 'fc_z_a.weight'])                      # [N, 256]  (gancraft_base.py:159)
+    with torch.cuda.device(dev):
+        for i in range(N):
+            b1 = (P[p + 'fc1.bias'] + zz[i]).contiguous()
+            code = L.sdb_pack_sky_mlp(_ptr(w1), _ptr(b1), _ptr(wh), _ptr(bh), _ptr(wout), _ptr(bout), int(precision),
+                                      _ptr(pack[i]), _stream(dev))
+            _lib.check(code, 'sdb_pack_sky_mlp')
+    return pack
+
+
+def sky_forward(raydirs, sky_pack, precision=PRECISION_FP16X3):
+    """a9 on the tensor-core engine: raydirs [N,H,W,1,3] -> (sky [N,H,W,64], sky_avg [N,64])."""
+    dev = raydirs.device
+    N, H, W = raydirs.shape[:3]
+    if not raydirs.is_cuda or not raydirs.is_contiguous() or raydirs.dtype != torch.float32:
+        raise RuntimeError('raydirs must be a contiguous float32 CUDA tensor')
+    L = _lib.lib()
+    sky = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
+    avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(L.sdb_sky_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+    stride = int(sky_pack.stride(0)) if (sky_pack.dim() == 2 and sky_pack.shape[0] > 1) else 0
+    with torch.cuda.device(dev):
+        code = L.sdb_sky_forward(_ptr(raydirs), N, H, W, _ptr(sky_pack), stride, int(precision), _ptr(sky), _ptr(avg),
+                                 _ptr(ws), _stream(dev))
+    _lib.check(code, 'sdb_sky_forward')
+    return sky, avg
+
+
 def sky_features(P, raydirs, z, prefix='sky_net', pe=(5, True)):
-    """a9: PE(raydir) -> SKYMLP (gancraft_base.py:150-169).  raydirs [N,H,W,1,3], z [N,256] -> [N,H,W,64]."""
+    """a9 through cuBLAS (kept as an independent cross-check of sky_forward): PE(raydir) -> SKYMLP
+    (gancraft_base.py:150-169).  raydirs [N,H,W,1,3], z [N,256] -> [N,H,W,64]."""
     N, H, W = raydirs.shape[:3]
     enc = ops.positional_encoding(raydirs.contiguous(), pe[0], -1, pe[1]).reshape(N, H * W, -1)
     p = prefix + '.'
@@ -193,13 +235,20 @@ class FusedPerPixelRenderer:
         self.P, self.voxel_dims, self.lut = P, [float(v) for v in voxel_dims], label_lut
         self.pls, self.precision, self.preblend = per_level_scale, precision, preblend
         self.base_res, self.log2_T, self.L = base_res, log2_T, L
-        self._pack_key = self._pack = self._t3_key = self._t3 = None
+        self._pack_key = self._pack = self._t3_key = self._t3 = self._sky_key = self._sky_pack = None
+        self.sky_impl = 'native'     # 'native' = sdb_sky_forward (tcgen05), 'torch' = cuBLAS cross-check
 
     def pack_for(self, z):
         key = (z.data_ptr(), z._version, self.precision)
         if self._pack_key != key:
             self._pack, self._pack_key = pack_mlp(self.P, z, self.precision), key
         return self._pack
+
+    def sky_pack_for(self, z):
+        key = (z.data_ptr(), z._version, self.precision)
+        if self._sky_key != key:
+            self._sky_pack, self._sky_key = pack_sky_mlp(self.P, z, self.precision), key
+        return self._sky_pack
 
     def table3_for(self, global_enc):
         emb = self.P['hash_encoder.embeddings']
@@ -213,7 +262,11 @@ class FusedPerPixelRenderer:
                 dists_scale=0.25, uniforms=None, sky_avg=None, sky=None):
         N = voxel_id.shape[0]
         if sky is None:
-            sky = sky_features(self.P, raydirs, z)
+            if self.sky_impl == 'native':
+                sky, avg = sky_forward(raydirs, self.sky_pack_for(z), self.precision)
+                sky_avg = avg if sky_avg is None else sky_avg
+            else:
+                sky = sky_features(self.P, raydirs, z)
         if sky_avg is None:
             sky_avg = sky.mean(dim=(1, 2))                       # scenedreamer.py:395 / :597
         pack = self.pack_for(z)

@@ -174,3 +174,24 @@ def test_fused_properties_all_sky_and_determinism(scene, lut):
     torch.cuda.synchronize()
     assert torch.equal(a, b)
     assert bool(torch.isfinite(a).all())
+
+
+def test_sky_forward_vs_oracle(scene):
+    """a9 on the tensor-core engine: PE + SKYMLP + frame mean vs the oracle (and vs the cuBLAS path)."""
+    P = oracle.make_params(seed=12, stress=True)
+    Pd = to_dev(P)
+    g = torch.Generator().manual_seed(6)
+    z = oracle.style_mlp(torch.randn(2, 128, generator=g), P)
+    rd = torch.cat([scene['rd'], scene['rd'].flip(1)], 0).contiguous()
+    N, H, W = rd.shape[:3]
+    pe = oracle.positional_encoding_pt(rd.cpu(), 5, -1, True)
+    ref = oracle.sky_mlp(pe.reshape(N, H * W, -1), z, P).reshape(N, H, W, 64)
+    for prec, tol in ((render.PRECISION_FP16X3, 2e-4), (render.PRECISION_BF16X3, 1e-3), (render.PRECISION_FP16, 2e-2)):
+        sky, avg = render.sky_forward(rd, render.pack_sky_mlp(Pd, z.to(DEV), prec), prec)
+        torch.cuda.synchronize()
+        err = float((sky.cpu() - ref).abs().max())
+        aerr = float((avg.cpu() - ref.mean(dim=(1, 2))).abs().max())
+        print('sky precision %d: max err %.3e (|ref| max %.2f), mean err %.3e' % (prec, err, float(ref.abs().max()), aerr))
+        assert err <= tol and aerr <= tol
+    t = render.sky_features(Pd, rd, z.to(DEV))
+    assert float((t.cpu() - ref).abs().max()) <= 1e-4
