@@ -181,6 +181,10 @@ int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W,
                     int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
                     void *stream);
 
+/* Diagnostics only: host-mapped (pinned) int32[64] progress buffer written by CTA 0 of the fused
+ * kernels (role, step, layer markers); pass NULL to disable (default).                          */
+void sdb_debug_set_progress_buffer(void *mapped);
+
 /* tcgen05 / TMEM self test: C[128,N] = A[128,K] * B[N,K]^T with the exact smem descriptors the
  * fused kernel uses.  d_a, d_b fp32 inputs (rounded to fp16/bf16 inside), d_c fp32 output.
  * variant 0 = the layout the library uses; 1 = LBO/SBO swapped (diagnostic only).              */

@@ -36,6 +36,7 @@ SIGNATURES = {
     'sdb_sky_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
     'sdb_sky_forward': (c_int, [c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    'sdb_debug_set_progress_buffer': (None, [c_void_p]),
     'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
 }
 

@@ -45,8 +45,16 @@ constexpr int kKExt = 16;                       // extra K columns: labels / bia
 constexpr int kKH = kHidden + kKExt;            // 272: K of every layer fed by hidden activations
 constexpr int kMaxM = 8, kMaxS = 64, kMaxLabels = 15;
 constexpr int kEpiThreads = 256, kGatherThreads = 256;
-constexpr int kLoaderWarp = 8, kMmaWarp = 9, kGatherWarp0 = 10;
-constexpr int kThreads = kEpiThreads + 64 + kGatherThreads;   // 576
+// warpgroup-aligned roles so that setmaxnreg can move registers from the control group to the gather group:
+//   WG0-1 epilogue (warps 0-7), WG2 control (8: weight loader, 9: MMA issuer, 10-11 idle), WG3-4 gather (12-19)
+constexpr int kLoaderWarp = 8, kMmaWarp = 9, kGatherWarp0 = 12;
+constexpr int kThreads = kEpiThreads + 128 + kGatherThreads;   // 640
+// setmaxnreg can only redistribute the registers the CTA was LAUNCHED with (640 threads x 96 = 61,440; the
+// allocator is a per-CTA pool -- USETMAXREG.TRY_ALLOC.CTAPOOL spins forever otherwise):
+//   8 epilogue warps x 96 + 4 control warps x 48 + 8 gather warps x 120 = 61,440
+constexpr int kRegsLaunch = 96, kRegsCtl = 48, kRegsGather = 120;
+static_assert(8 * 32 * kRegsLaunch + 4 * 32 * kRegsCtl + 8 * 32 * kRegsGather <= kThreads * kRegsLaunch,
+              "setmaxnreg budget exceeds the CTA's launch-time register allocation");
 constexpr int kRingBytes = 65536;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kLboA = kRows * 16, kSbo = 128;
@@ -73,14 +81,49 @@ constexpr int kFWsig = 0, kFBsig = 256, kFTotal = 264;
 template <bool SKY> __host__ __device__ constexpr int64_t packBytes(int parts) {
     return layerOff<SKY>(Net<SKY>::NL, parts) + (SKY ? 0 : (int64_t)kFTotal * 4);
 }
-// consumption order of the 17 k16 steps of a K=272 layer: extension first (no dependency), then the
-// 64-column chunks in the order the epilogue halves produce them (0 and 2 first, then 1 and 3)
-__device__ __forceinline__ int kk_at(int l, int i) {
-    if (l == 0) return i;
-    if (i == 0) return 16;
-    const int c = (i - 1) >> 2, r = (i - 1) & 3;
-    const int chunk = (c == 1) ? 2 : (c == 2 ? 1 : c);
-    return chunk * 4 + r;
+// Weight-ring schedule.  A ring stage holds KS consecutive k16 slabs (KS = 1 for the x3 modes, 2 for the
+// single-pass mode so that a stage is 16 KB either way).  Layers fed by hidden activations (K = 272) consume
+// the K extension first (no dependency), then the 64-column chunks in the order the two epilogue halves
+// produce them (0 and 2 first, then 1 and 3).  Loader and MMA issuer walk the same list.
+template <int KS, bool SKY> __host__ __device__ constexpr int num_stages(int l) {
+    return l == 0 ? (Net<SKY>::K0 / 16 + KS - 1) / KS : 1 + 16 / KS;   // extension + 8 chunks x (2 / KS)
+}
+// 32-column operand chunks (2 k16 steps each): chunk ids 0..3 are written by the epilogue half that owns
+// columns 0..127, ids 4..7 by the other half; both halves advance together -> consumption order 0,4,1,5,2,6,3,7
+__host__ __device__ constexpr int chunk_order(int c) { return (c >> 1) + (c & 1) * 4; }
+template <int KS, bool SKY> __host__ __device__ constexpr int stage_kk(int l, int j) {
+    if (l == 0) return j * KS;
+    if (j == 0) return 16;
+    const int i = j - 1, per = 2 / KS, c = i / per, r = i % per;
+    return chunk_order(c) * 2 + r * KS;
+}
+template <int KS, bool SKY> __host__ __device__ constexpr int stage_cnt(int l, int j) {
+    if (l == 0) { const int nk = Net<SKY>::K0 / 16; return (j * KS + KS <= nk) ? KS : nk - j * KS; }
+    return j == 0 ? 1 : KS;
+}
+// chunk barrier to wait on before stage j of a K=272 layer (-1: none)
+template <int KS> __host__ __device__ constexpr int stage_chunk_wait(int l, int j) {
+    if (l == 0 || j == 0) return -1;
+    const int i = j - 1, per = 2 / KS;
+    if (i % per != 0) return -1;
+    return chunk_order(i / per);
+}
+
+// Static schedule: the number of ring stages per sample step is padded to a multiple of the ring depth (4),
+// so the ring slot of every stage is a compile-time constant and its mbarrier parity depends only on the
+// step parity -- the issue loops become straight-line code with immediate addresses.
+template <int KS, bool SKY> __host__ __device__ constexpr int stage_index(int l, int j) {
+    int i = j;
+    for (int k = 0; k < l; k++) i += num_stages<KS, SKY>(k);
+    return i;
+}
+template <int KS, bool SKY> __host__ __device__ constexpr int stages_per_step() { return stage_index<KS, SKY>(Net<SKY>::NL, 0); }
+template <int KS, bool SKY> __host__ __device__ constexpr int stages_per_step_padded() { return (stages_per_step<KS, SKY>() + 3) / 4 * 4; }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- shared memory map ---------------------------------------------------------------------------
@@ -113,8 +156,8 @@ constexpr int kStFlags = 2 * kMaxM + 5;      // 1 (uint32: bit0 live, bit1 sky_m
 constexpr int kStFloats = 2 * kMaxM + 6;
 
 // barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 8, B_FEAT = 16, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 4, B_OUTRDY, B_EPIDONE, B_STRDY,
-       B_STFREE = B_STRDY + 2, B_COUNT = B_STFREE + 2 };
+enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 8, B_OUTRDY, B_EPIDONE,
+       B_STRDY = B_EPIDONE + 2, B_STFREE = B_STRDY + 2, B_COUNT = B_STFREE + 2 };
 static_assert(B_COUNT <= 32, "barrier table");
 
 struct Params {
@@ -142,7 +185,19 @@ struct Params {
     // sky mode
     float *sky_out;                // [R, 64]
     float *sky_partial;            // [n_tiles, 64] per-tile column sums (deterministic mean)
+    int32_t *debug;                // optional host-mapped progress buffer (diagnostics), else nullptr
 };
+
+// progress markers (CTA 0 only): debug[role*4 + {0,1,2}] = {marker, step, layer/stage}
+#define SDB_MARK(role, marker, a, b)                                              \
+    do {                                                                          \
+        if (p.debug != nullptr && blockIdx.x == 0) {                              \
+            volatile int32_t *d__ = p.debug + (role) * 4;                         \
+            d__[0] = (marker); d__[1] = (int32_t)(a); d__[2] = (int32_t)(b);      \
+        }                                                                         \
+    } while (0)
+
+static int32_t *g_debug_buffer = nullptr;
 
 __device__ __constant__ uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u, kPrime3 = 3674653429u, kPrime4 = 2097192037u;
 
@@ -290,8 +345,9 @@ mlp_kernel(const Params p)
     constexpr Smem SM = smem_map(X3);
     constexpr int PARTS = X3 ? 2 : 1;
     constexpr int NH = Net<SKY>::NH, NL = Net<SKY>::NL;
-    constexpr int kStageBytes = kHidden * 32 * PARTS;        // one k16 slab (hi [+ lo]) of an N=256 layer
-    constexpr int kStages = kRingBytes / kStageBytes;        // 4 (x3) / 8 (x1)
+    constexpr int KS = X3 ? 1 : 2;                           // k16 slabs per ring stage
+    constexpr int kStageBytes = KS * kHidden * 32 * PARTS;   // 16 KB either way
+    constexpr int kStages = kRingBytes / kStageBytes;        // 4
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sHhi = smem + SM.h_hi;
     uint8_t *sHlo = smem + SM.h_lo;
@@ -311,13 +367,15 @@ mlp_kernel(const Params p)
 
     // ---- one-time setup ----
     if (tid == 0) {
-        for (int i = 0; i < 8; i++) { tc05::mbar_init(&bars[B_WFULL + i], 1); tc05::mbar_init(&bars[B_WEMPTY + i], 1); }
+        static_assert(kStages <= 4, "barrier table holds 4 ring stages");
+        for (int i = 0; i < 4; i++) { tc05::mbar_init(&bars[B_WFULL + i], 1); tc05::mbar_init(&bars[B_WEMPTY + i], 1); }
         tc05::mbar_init(&bars[B_FEAT], kGatherThreads);
         tc05::mbar_init(&bars[B_HFREE], 1);
-        for (int i = 0; i < 4; i++) tc05::mbar_init(&bars[B_CHUNK + i], kEpiThreads / 2);
+        for (int i = 0; i < 8; i++) tc05::mbar_init(&bars[B_CHUNK + i], kEpiThreads / 2);
         tc05::mbar_init(&bars[B_ACC], 1);
         tc05::mbar_init(&bars[B_OUTRDY], 1);
         tc05::mbar_init(&bars[B_EPIDONE], kEpiThreads);
+        tc05::mbar_init(&bars[B_EPIDONE + 1], kEpiThreads);
         for (int i = 0; i < 2; i++) { tc05::mbar_init(&bars[B_STRDY + i], kRows); tc05::mbar_init(&bars[B_STFREE + i], kEpiThreads); }
         tc05::fence_mbar_init();
     }
@@ -392,8 +450,10 @@ mlp_kernel(const Params p)
                 for (int l = 0; l < NH; l++) {
                     const uint32_t g = n * NL + l;                   // global layer counter -> accumulator buffer
                     const uint32_t acc = tm_row + (g & 1u) * 256u + half * 128u;
+                    if ((tid & 127) == 0) SDB_MARK(half, 1, n, l);
                     tc05::mbar_wait(&bars[B_ACC], (n * NH + l) & 1);
                     tc05::fence_after_thread_sync();
+                    if ((tid & 127) == 0) SDB_MARK(half, 2, n, l);
 #pragma unroll 1
                     for (int c0 = 0; c0 < 128; c0 += 32) {
                         float v[32];
@@ -415,24 +475,26 @@ mlp_kernel(const Params p)
                             *reinterpret_cast<uint4 *>(sHhi + off) = hi;
                             if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
                         }
-                        if (c0 & 32) {      // a 64-column K chunk of the next layer's operand is complete
-                            tc05::fence_proxy_async_smem();
-                            tc05::mbar_arrive(&bars[B_CHUNK + half * 2 + (c0 >> 6)]);
-                        }
+                        // a 32-column K chunk of the next layer's operand is complete (all 128 rows once the four
+                        // quadrant warps of this half have arrived): the MMA issuer may start on it
+                        tc05::fence_proxy_async_smem();
+                        tc05::mbar_arrive(&bars[B_CHUNK + half * 4 + (c0 >> 5)]);
                     }
                     tc05::fence_before_thread_sync();
-                    tc05::mbar_arrive(&bars[B_EPIDONE]);
+                    tc05::mbar_arrive(&bars[B_EPIDONE + (g & 1u)]);        // accumulator buffer (g & 1) is free again
                     if (!SKY && l == 3) sSig[half * kRows + row] = sig_part;
                 }
                 // ---- colour layer ----
                 const uint32_t go = n * NL + NH;
+                if ((tid & 127) == 0) SDB_MARK(half, 3, n, NH);
                 tc05::mbar_wait(&bars[B_OUTRDY], n & 1);
+                if ((tid & 127) == 0) SDB_MARK(half, 4, n, NH);
                 tc05::fence_after_thread_sync();
                 float c[32];
                 tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * 32u, c);
                 tc05::tmem_ld_wait();
                 tc05::fence_before_thread_sync();
-                tc05::mbar_arrive(&bars[B_EPIDONE]);
+                tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
                 if constexpr (SKY) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) outc[j] = c[j];
@@ -502,85 +564,144 @@ mlp_kernel(const Params p)
                 tc05::mbar_arrive(&bars[B_STFREE + buf]);
             }
         }
-    } else if (warp == kLoaderWarp) {
+    } else if (warp < kGatherWarp0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+      constexpr int NSP = stages_per_step_padded<KS, SKY>();      // ring stages per sample step (multiple of 4)
+      constexpr int NS = stages_per_step<KS, SKY>();
+      constexpr uint32_t kStepFlip = (NSP / 4) & 1;                 // does the stage parity pattern flip every step?
+      static_assert(kStages == 4, "static schedule assumes a 4-deep ring");
+      if (warp == kLoaderWarp) {
         // =========================== WEIGHT LOADER (1-D bulk TMA) ===========================
         if (lane == 0) {
-            uint32_t q = 0;
+            uint32_t n = 0;
             for (int it = 0; it < n_iter; it++) {
                 const int work = blockIdx.x + it * gridDim.x;
                 const int tile = SKY ? work : p.tile_list[work];
                 const TileCoord tc = tile_coord(p, tile);
                 const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
-                for (int s = 0; s < S; s++) {
-                    for (int l = 0; l < NL; l++) {
-                        const int nk16 = layerK<SKY>(l) / 16;
-                        const uint32_t bytes = (uint32_t)layerN<SKY>(l) * 32 * PARTS;
-                        const uint8_t *src = pack + layerOff<SKY>(l, PARTS);
-                        for (int i = 0; i < nk16; i++, q++) {
-                            const uint32_t stg = q % kStages, par = (q / kStages) & 1;
-                            tc05::mbar_wait_backoff(&bars[B_WEMPTY + stg], par ^ 1, 64);
-                            tc05::mbar_arrive_expect_tx(&bars[B_WFULL + stg], bytes);
-                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)kk_at(l, i) * bytes, bytes, &bars[B_WFULL + stg]);
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == kMmaWarp) {
-        // =========================== MMA ISSUER (one thread) ===========================
-        if (lane == 0) {
-            uint32_t q = 0, n = 0;
-            const uint32_t aHi = tc05::smem_u32(sHhi), aLo = tc05::smem_u32(sHlo), ring = tc05::smem_u32(sRing);
-            for (int it = 0; it < n_iter; it++) {
                 for (int s = 0; s < S; s++, n++) {
+                    const uint32_t flip = kStepFlip & n;
+#pragma unroll
                     for (int l = 0; l < NL; l++) {
-                        const uint32_t g = n * NL + l;
-                        // accumulator buffer (g & 1) was last read by the epilogue of global layer g-2
-                        if (g >= 2) tc05::mbar_wait(&bars[B_EPIDONE], (g - 2) & 1);
-                        if (l == 0) tc05::mbar_wait(&bars[B_FEAT], n & 1);
-                        tc05::fence_after_thread_sync();
-                        const int N = layerN<SKY>(l);
-                        const uint32_t idesc = tc05::make_idesc(kRows, N, BF16);
-                        const uint32_t dcol = tmem + (g & 1u) * 256u;
-                        const uint32_t slab = (uint32_t)N * 32, lboB = (uint32_t)N * 16;
-                        const int nk16 = layerK<SKY>(l) / 16;
-                        for (int i = 0; i < nk16; i++, q++) {
-                            const int kk = kk_at(l, i);
-                            if (l > 0 && i > 0 && ((i - 1) & 3) == 0) {
-                                // 64-column K chunk (kk / 4) of this layer's operand, written by the previous epilogue
-                                tc05::mbar_wait(&bars[B_CHUNK + (kk >> 2)], (n * NH + (l - 1)) & 1);
-                                tc05::fence_after_thread_sync();
-                            }
-                            const uint32_t stg = q % kStages, par = (q / kStages) & 1;
-                            tc05::mbar_wait(&bars[B_WFULL + stg], par);
-                            tc05::fence_after_thread_sync();
-                            const uint32_t bbase = ring + stg * kStageBytes;
-                            const uint64_t dAhi = tc05::make_smem_desc(aHi + kk * 2 * kLboA, kLboA, kSbo);
-                            const uint64_t dBhi = tc05::make_smem_desc(bbase, lboB, kSbo);
-                            tc05::mma_f16_ss(dcol, dAhi, dBhi, idesc, i > 0 ? 1u : 0u);
-                            if constexpr (X3) {
-                                const uint64_t dBlo = tc05::make_smem_desc(bbase + slab, lboB, kSbo);
-                                const bool ext = (l > 0 && i == 0);      // A_lo of the constant extension columns is 0
-                                if (!ext) {
-                                    const uint64_t dAlo = tc05::make_smem_desc(aLo + kk * 2 * kLboA, kLboA, kSbo);
-                                    tc05::mma_f16_ss(dcol, dAlo, dBhi, idesc, 1u);
-                                }
-                                tc05::mma_f16_ss(dcol, dAhi, dBlo, idesc, 1u);
-                            }
-                            tc05::mma_commit(&bars[B_WEMPTY + stg]);
+                        const uint32_t slabB = (uint32_t)layerN<SKY>(l) * 32 * PARTS;      // one k16 slab (hi [+ lo])
+                        const uint8_t *src = pack + layerOff<SKY>(l, PARTS);
+#pragma unroll
+                        for (int j = 0; j < num_stages<KS, SKY>(l); j++) {
+                            const int i = stage_index<KS, SKY>(l, j);
+                            const uint32_t stg = i & 3, par = ((i >> 2) & 1) ^ flip;
+                            const uint32_t bytes = slabB * stage_cnt<KS, SKY>(l, j);
+                            tc05::mbar_wait_backoff(&bars[B_WEMPTY + stg], par ^ 1, 32);
+                            tc05::mbar_arrive_expect_tx(&bars[B_WFULL + stg], bytes);
+                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)stage_kk<KS, SKY>(l, j) * slabB, bytes,
+                                           &bars[B_WFULL + stg]);
                         }
-                        if (l == NL - 1) {
-                            tc05::mma_commit(&bars[B_OUTRDY]);
-                            tc05::mma_commit(&bars[B_HFREE]);
-                        } else {
-                            tc05::mma_commit(&bars[B_ACC]);
-                        }
+                    }
+#pragma unroll
+                    for (int i = NS; i < NSP; i++) {       // padding stages: a 16-byte dummy transaction keeps the phases regular
+                        const uint32_t stg = i & 3, par = ((i >> 2) & 1) ^ flip;
+                        tc05::mbar_wait_backoff(&bars[B_WEMPTY + stg], par ^ 1, 32);
+                        tc05::mbar_arrive_expect_tx(&bars[B_WFULL + stg], 16);
+                        tc05::bulk_g2s(sRing + stg * kStageBytes, pack, 16, &bars[B_WFULL + stg]);
                     }
                 }
             }
         }
+      } else if (warp == kMmaWarp) {
+        // =========================== MMA ISSUER ===========================
+        // The warp stays converged (uniform control flow, every lane polls the barriers), one elected lane
+        // issues tcgen05.mma / commit.  Ring slot, barrier addresses, parities and descriptor offsets of every
+        // stage are immediates (static schedule above) and two ring stages are issued per iteration, so the
+        // fixed cost of an iteration (~40 instructions of a single warp) is amortised over up to 6 MMAs.
+        // (Earlier versions spent ~600 cycles per k16 step in this loop and capped the tensor pipe at ~50 %,
+        // profiles/r01_v2b_*.)
+        uint32_t n = 0;
+        const uint64_t dA0h = tc05::make_smem_desc(tc05::smem_u32(sHhi), kLboA, kSbo);
+        const uint64_t dA0l = tc05::make_smem_desc(tc05::smem_u32(sHlo), kLboA, kSbo);
+        const uint64_t dB0_256 = tc05::make_smem_desc(tc05::smem_u32(sRing), 256 * 16, kSbo);
+        const uint64_t dB0_64 = tc05::make_smem_desc(tc05::smem_u32(sRing), kOutC * 16, kSbo);
+        for (int it = 0; it < n_iter; it++) {
+            for (int s = 0; s < S; s++, n++) {
+                const uint32_t flip = kStepFlip & n;
+                const uint32_t nodd = n & 1u;
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    const uint32_t g = n * NL + l;
+                    const uint32_t buf = ((nodd * (NL & 1)) ^ (l & 1)) & 1u;      // == g & 1
+                    // accumulator buffer `buf` was last read by the epilogue of global layer g-2.  One
+                    // barrier PER BUFFER: its next completion needs this layer's own MMAs, so the parity
+                    // wait can never fall two phases behind (a single shared barrier can: the 64-column
+                    // colour layer finishes within a few hundred cycles).
+                    if (lane == 0) SDB_MARK(2, 1, n, l);
+                    if (g >= 2) tc05::mbar_wait(&bars[B_EPIDONE + buf], ((g >> 1) - 1) & 1);
+                    if (l == 0) tc05::mbar_wait(&bars[B_FEAT], nodd);
+                    const int N = layerN<SKY>(l);                                  // compile-time after unrolling
+                    const uint32_t idesc = tc05::make_idesc(kRows, N, BF16);
+                    const uint32_t slab16 = (uint32_t)(N * 32) >> 4;              // one part of one k16 slab, in 16-byte units
+                    const uint32_t dcol = tmem + buf * 256u;
+                    const uint64_t dB0 = (N == kOutC) ? dB0_64 : dB0_256;
+                    const uint32_t cpar = (NH & 1) ? (((l - 1) & 1) ^ nodd) : ((l - 1) & 1);   // (n*NH + l-1) & 1
+                    constexpr int kPair = 2;
+#pragma unroll
+                    for (int j0 = 0; j0 < num_stages<KS, SKY>(l); j0 += kPair) {
+#pragma unroll
+                        for (int u = 0; u < kPair; u++) {
+                            const int j = j0 + u;
+                            if (j < num_stages<KS, SKY>(l)) {
+                                const int i = stage_index<KS, SKY>(l, j);
+                                const int chunk = stage_chunk_wait<KS>(l, j);
+                                if (chunk >= 0) tc05::mbar_wait(&bars[B_CHUNK + chunk], cpar);   // operand chunk from the previous epilogue
+                                tc05::mbar_wait(&bars[B_WFULL + (i & 3)], ((i >> 2) & 1) ^ flip);
+                            }
+                        }
+                        tc05::fence_after_thread_sync();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int u = 0; u < kPair; u++) {
+                                const int j = j0 + u;
+                                if (j < num_stages<KS, SKY>(l)) {
+                                    const int i = stage_index<KS, SKY>(l, j);
+                                    const uint32_t stg = i & 3;
+                                    const uint64_t dBs = dB0 + (uint64_t)(stg * (kStageBytes >> 4));
+#pragma unroll
+                                    for (int t = 0; t < stage_cnt<KS, SKY>(l, j); t++) {
+                                        const int kk = stage_kk<KS, SKY>(l, j) + t;
+                                        const uint64_t dAh = dA0h + (uint64_t)(kk * (2 * kLboA >> 4));
+                                        const uint64_t dBh = dBs + (uint64_t)(t * slab16 * PARTS);
+                                        const bool first = (j == 0 && t == 0);
+                                        tc05::mma_f16_ss(dcol, dAh, dBh, idesc, first ? 0u : 1u);
+                                        if constexpr (X3) {
+                                            const bool ext = (l > 0 && j == 0);      // A_lo of the constant extension columns is 0
+                                            if (!ext) tc05::mma_f16_ss(dcol, dA0l + (uint64_t)(kk * (2 * kLboA >> 4)), dBh, idesc, 1u);
+                                            tc05::mma_f16_ss(dcol, dAh, dBh + slab16, idesc, 1u);
+                                        }
+                                    }
+                                    tc05::mma_commit(&bars[B_WEMPTY + stg]);
+                                    if (j == num_stages<KS, SKY>(l) - 1) {
+                                        if (l == NL - 1) {
+                                            tc05::mma_commit(&bars[B_OUTRDY]);
+                                            tc05::mma_commit(&bars[B_HFREE]);
+                                        } else {
+                                            tc05::mma_commit(&bars[B_ACC]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+#pragma unroll
+                for (int i = NS; i < NSP; i++) {       // padding stages (see loader)
+                    tc05::mbar_wait(&bars[B_WFULL + (i & 3)], ((i >> 2) & 1) ^ flip);
+                    if (elect_one()) tc05::mma_commit(&bars[B_WEMPTY + (i & 3)]);
+                    __syncwarp();
+                }
+            }
+        }
+      }
     } else {
         // =========================== GATHER WARPS (layer-0 operand producers) ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsGather));
         const int gt = tid - kGatherWarp0 * 32;
         const int row = gt & (kRows - 1), half = gt >> 7;
         uint32_t n = 0;
@@ -621,6 +742,7 @@ mlp_kernel(const Params p)
                         split8<PREC>(v8, ch[c], cl[c]);
                     }
                 }
+                if (gt == 0) SDB_MARK(4, 3, n, it);
                 if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
                 if (half == 0) {
 #pragma unroll
@@ -637,6 +759,7 @@ mlp_kernel(const Params p)
                 const int buf = it & 1;
                 float *st = sState + buf * kStFloats * kRows;
                 // ---- per-ray sampling state (first 128 gather threads) ----
+                if (gt == 0) SDB_MARK(4, 1, n, it);
                 if (it >= 2) tc05::mbar_wait_backoff(&bars[B_STFREE + buf], ((it >> 1) - 1) & 1);
                 if (half == 0) {
                     float accu = 0.0f, cum = 0.0f, entry0 = 0.0f, prev_exit = 0.0f;
@@ -723,7 +846,9 @@ mlp_kernel(const Params p)
                         if (k >= 0 && k < 8) oh[k >> 1] = one16<PREC>() << (16 * (k & 1));
                         if (half == 1) oh[3] |= one16<PREC>() << 16;             // column 143
                     }
+                    if (gt == 0) SDB_MARK(4, 3, n, it);
                     if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
+                    if (gt == 0) SDB_MARK(4, 4, n, it);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const uint32_t off = tc05::chunk_off(kRows, row, half + 2 * i);
@@ -914,6 +1039,9 @@ int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels
 template <int PREC, bool RAW5D, bool SKY>
 int launch_mlp(const Params &p, int grid, cudaStream_t st) {
     const size_t smem = smem_map(PREC != 0).total;
+    cudaFuncAttributes fa;
+    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, SKY>));
+    if (fa.numRegs < kRegsLaunch) return SDB_EUNSUPPORTED;   // setmaxnreg pool would be too small: refuse rather than hang
     SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, SKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mlp_kernel<PREC, RAW5D, SKY><<<grid, kThreads, smem, st>>>(p);
     SDB_CHECK_LAUNCH();
@@ -921,6 +1049,9 @@ int launch_mlp(const Params &p, int grid, cudaStream_t st) {
 }
 
 }  // namespace rf
+
+// Diagnostics: a host-mapped (pinned) int32[64] buffer that CTA 0 fills with progress markers.
+extern "C" void sdb_debug_set_progress_buffer(void *mapped) { rf::g_debug_buffer = (int32_t *)mapped; }
 
 extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes<false>(precision != 0 ? 2 : 1); }
 extern "C" int64_t sdb_sky_pack_bytes(int32_t precision) { return rf::packBytes<true>(precision != 0 ? 2 : 1); }
@@ -983,6 +1114,7 @@ extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H,
     p.raydirs = d_raydirs;
     p.pack = (const uint8_t *)d_sky_pack; p.pack_stride = pack_stride;
     p.sky_out = d_sky; p.sky_partial = (float *)d_workspace;
+    p.debug = g_debug_buffer;
     p.tiles_x = sdb_div_up(W, kTileW); p.tiles_y = sdb_div_up(H, kTileH);
     p.n_tiles = n_img * p.tiles_x * p.tiles_y;
     const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
@@ -1023,6 +1155,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     p.pack = (const uint8_t *)sp->d_mlp_pack; p.pack_stride = sp->mlp_pack_stride;
     p.sky = sp->d_sky; p.sky_avg = sp->d_sky_avg;
     p.net_out = sp->d_net_out; p.depth_out = sp->d_depth_out; p.total_weight = sp->d_total_weight;
+    p.debug = g_debug_buffer;
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
     p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
     int32_t *ws = (int32_t *)sp->d_workspace;
