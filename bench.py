@@ -23,6 +23,14 @@ import sys
 import threading
 import time
 
+# The CPU arm runs two OpenMP pools (torch's and the oracle's libgomp); with active spinning and 100+
+# threads they fight each other, so: passive waiting and a bounded thread count (set before torch loads).
+CPU_THREADS = min(os.cpu_count() or 1, int(os.environ.get('SDB_CPU_THREADS', '32')))
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    os.environ.setdefault('OMP_NUM_THREADS', str(CPU_THREADS))
+    os.environ.setdefault('OMP_WAIT_POLICY', 'PASSIVE')
+    os.environ.setdefault('GOMP_SPINCOUNT', '0')
+
 import numpy as np
 import torch
 
@@ -115,7 +123,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import oracle
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(CPU_THREADS)
     world, poses, P, z, genc, lut = build_workload('cpu')
     crop = 64
     for w in range(args.warmup):
@@ -134,7 +142,7 @@ def run_reference_arm(args):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0 (CPU: %dx%d-ray '
                                'centre crop per step)' % (crop, crop)},
-        'cpu_baseline': {'value': val, 'unit': 'Msamples/s', 'cores': os.cpu_count(), 'kind': 'port',
+        'cpu_baseline': {'value': val, 'unit': 'Msamples/s', 'cores': CPU_THREADS, 'host_cpus': os.cpu_count(), 'kind': 'port',
                          'sample': '%dx%d-ray centre crop of the C2 frame per step (oracle/: C DDA + hash encode with '
                                    'OpenMP, torch fp32 MLP), %d steps' % (crop, crop, args.steps),
                          'omp_threads': oracle.num_threads()},
@@ -180,7 +188,7 @@ class FrameRenderer:
 
 def run_gpu_arm(args):
     import torch.distributed as dist
-    from scenedreamer_b200 import synth, render
+    from scenedreamer_b200 import synth, render, sharding
     world_size = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -197,7 +205,6 @@ def run_gpu_arm(args):
     res = cams[0][5]
     host_out = torch.empty(2, res[0], res[1], dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_buf = torch.empty(world_size, 2, res[0], res[1], dtype=torch.float32, device=dev) if world_size > 1 else None
 
     def one_step(k, ev=None, kev=None):
         idx = (k * world_size + rank) % len(cams)
@@ -208,7 +215,7 @@ def run_gpu_arm(args):
         out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev)   # by-value to the DDA, H2D for the rest
         maps = torch.stack([out['depth'][0], out['total_weight'][0]])
         if world_size > 1:
-            dist.all_gather_into_tensor(gather_buf, maps)            # the single collective of the path
+            sharding.gather_frames(maps.unsqueeze(0))                # the single collective of the path
         host_out.copy_(maps, non_blocking=True)                      # D2H of the step's result
         if ev is not None:
             ev[1].record()
@@ -268,16 +275,13 @@ def run_gpu_arm(args):
         achieved = SAMPLES_PER_FRAME * BYTES_PER_SAMPLE / kern_s / 1e9
         cpu = None
         if world_size == 1 and not args.no_cpu:
-            import oracle
-            torch.set_num_threads(os.cpu_count())
-            cpu_frame_sample(world, poses[0], P, z, genc, lut, 32)
-            t, n = 0.0, 0
-            while t < 12.0:
-                dt, nn = cpu_frame_sample(world, poses[n % 7], P, z, genc, lut, 64)
-                t, n = t + dt, n + nn
-            cpu = {'value': n / t / 1e6, 'unit': 'Msamples/s', 'cores': os.cpu_count(), 'kind': 'port',
-                   'sample': '64x64-ray centre crops of the C2 frame for %.0f s (oracle/: OpenMP C DDA + hash encode, '
-                             'torch fp32 MLP on all host threads)' % t}
+            # the CPU leg runs in a clean subprocess (its own OpenMP settings, no CUDA context)
+            try:
+                o = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '12',
+                                    '--warmup', '1'], capture_output=True, text=True, timeout=600)
+                cpu = json.loads(o.stdout.strip().splitlines()[-1])['cpu_baseline']
+            except Exception as e:          # noqa: BLE001
+                cpu = {'error': repr(e)[:200]}
         line = {
             'metric': 'rendered Msamples/sec at 960x540x24spp', 'value': value, 'unit': 'Msamples/s',
             'mpix_per_s': value / SPP, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),

@@ -139,6 +139,8 @@ typedef struct sdb_render_params {
     float *d_net_out;            /* [R, 64]                                                   */
     float *d_depth_out;          /* [R] sum w*t (scenedreamer.py:816) or NULL                 */
     float *d_total_weight;       /* [R] or NULL                                               */
+    float *d_weights_out;        /* [R, S] compositing weights (scenedreamer.py:373-376) or NULL */
+    float *d_rand_depth_out;     /* [R, S] sample depths after the NaN guard (:346-352) or NULL */
     /* scratch: sdb_render_workspace_bytes(n_img, H, W) bytes                                  */
     void *d_workspace;
 } sdb_render_params;

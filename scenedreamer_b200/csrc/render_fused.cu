@@ -177,7 +177,7 @@ struct Params {
     const uint8_t *pack;
     long long pack_stride;
     const float *sky, *sky_avg;
-    float *net_out, *depth_out, *total_weight;
+    float *net_out, *depth_out, *total_weight, *weights_out, *rdepth_out;
     const int32_t *tile_list;      // [n_live] (render) / nullptr (sky: all tiles)
     const int32_t *n_live;
     int n_tiles;
@@ -510,6 +510,10 @@ mlp_kernel(const Params p)
                     w = live ? w : 0.0f;                                                              // scenedreamer.py:376
                     Wsum += w;
                     Dsum = fmaf(w, sm.depth, Dsum);
+                    if (half == 0 && valid) {
+                        if (p.weights_out) p.weights_out[ray * S + s] = w;
+                        if (p.rdepth_out) p.rdepth_out[ray * S + s] = sm.depth;
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float rgb = fminf(fmaxf(c[j], -1.0f), 1.0f) + 1.0f;                     // :407-408
@@ -903,6 +907,10 @@ prepass_kernel(const Params p, int32_t *tile_list, int32_t *n_live)
     }
     if (p.depth_out) p.depth_out[ray] = 0.0f;
     if (p.total_weight) p.total_weight[ray] = 0.0f;
+    for (int s = 0; s < p.S; s++) {
+        if (p.weights_out) p.weights_out[ray * p.S + s] = 0.0f;
+        if (p.rdepth_out) p.rdepth_out[ray * p.S + s] = 0.0f;
+    }
 }
 
 // frame-global sky mean from the per-tile partial sums, fixed summation order (deterministic)
@@ -1155,6 +1163,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     p.pack = (const uint8_t *)sp->d_mlp_pack; p.pack_stride = sp->mlp_pack_stride;
     p.sky = sp->d_sky; p.sky_avg = sp->d_sky_avg;
     p.net_out = sp->d_net_out; p.depth_out = sp->d_depth_out; p.total_weight = sp->d_total_weight;
+    p.weights_out = sp->d_weights_out; p.rdepth_out = sp->d_rand_depth_out;
     p.debug = g_debug_buffer;
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
     p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;

@@ -1,0 +1,85 @@
+"""Reference-side integration: run SceneDreamer's `Generator._forward_perpix` on the fused B200 kernel.
+
+`patch_generator(net_G)` rebinds `_forward_perpix` of a reference Generator instance
+(imaginaire/generators/scenedreamer.py:313) so that inference.py / the no-grad half of train.py
+(`dis_forward`, trainers/gancraft.py:215-217) run the fused path, while calls that need autograd
+(gen_update) keep the reference's own composition -- which, with dropin/ on PYTHONPATH, still runs
+on this library's DDA / positional-encoding / hash-grid kernels.
+
+The returned 12-tuple has the reference's order (scenedreamer.py:427-428).  Callers in the reference
+use only `net_out` (index 0) and, in the depth variant, `weights` (2) and `rand_depth` (4)
+(scenedreamer.py:462-467, :618-621, :812-816); the per-sample network outputs that the fused kernel
+never materialises (net_out_s, net_out_c, ...) are returned as None.
+"""
+import types
+
+import torch
+
+from . import render
+
+
+def _params_from_generator(gen):
+    sd = {}
+    for prefix, mod in (('render_net', gen.render_net), ('sky_net', gen.sky_net), ('hash_encoder', gen.hash_encoder)):
+        for k, v in mod.state_dict().items():
+            sd[prefix + '.' + k] = v
+    return sd
+
+
+class _FusedState:
+    def __init__(self, gen, precision):
+        lt = gen.label_trans
+        self.lut = render.reduced_label_lut(lt.mcid2rdid_lut, lt.ignore_id, lt.dirt_id)
+        self.precision = precision
+        self.renderer = None
+        self.key = None
+
+    def get(self, gen):
+        P = _params_from_generator(gen)
+        dims = tuple(gen.voxel.voxel_t.shape)
+        key = (dims, tuple((k, v.data_ptr(), v._version) for k, v in P.items()))
+        if self.key != key:
+            he = gen.hash_encoder
+            self.renderer = render.FusedPerPixelRenderer(
+                P, dims, self.lut, he.per_level_scale, precision=self.precision, preblend=True,
+                base_res=he.base_resolution, log2_T=he.log2_hashmap_size, L=he.num_levels)
+            self.key = key
+        return self.renderer
+
+
+def fused_forward_perpix(self, blk_feats, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc):
+    """Replacement body of Generator._forward_perpix (same arguments, same return order)."""
+    st = self._sdb200
+    supported = (self.clip_feat_map is True and self.keep_sky_out and self.keep_sky_out_avgpool and
+                 self.sky_global_avgpool and not self.sample_use_box_boundaries and self.raw_noise_std == 0 and
+                 self.pe_params[2] == 0 and self.pe_params_sky[0] == 5 and bool(self.pe_params_sky[1]))
+    if torch.is_grad_enabled() or not supported or not voxel_id.is_cuda:
+        return st.reference_forward(blk_feats, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc)
+    r = st.get(self)
+    uniforms = None
+    if not self.coarse_deterministic_sampling:
+        N, H, W = voxel_id.shape[:3]
+        uniforms = torch.rand(N, H, W, self.num_samples + 1, 1, dtype=torch.float32, device=voxel_id.device)
+    sky_avg = getattr(self, 'sky_avg', None)
+    if sky_avg is not None:
+        sky_avg = sky_avg.reshape(-1, 64)
+    out = r.forward(voxel_id.contiguous(), depth2.contiguous(), raydirs.contiguous(), cam_ori_t, z, global_enc,
+                    num_samples=self.num_samples, sample_depth=self.sample_depth, dists_scale=self.dists_scale,
+                    uniforms=uniforms, sky_avg=sky_avg, want_samples=True)
+    sky_mask = voxel_id[:, :, :, [-1], :] == 0
+    sky_only_mask = voxel_id[:, :, :, [0], :] == 0
+    total = out['total_weight'].unsqueeze(-1).unsqueeze(-1)
+    return (out['net_out'], None, out['weights'], total, out['rand_depth'], None, None, out['sky'].unsqueeze(-2), None,
+            sky_mask, sky_only_mask, None)
+
+
+def patch_generator(gen, precision=render.PRECISION_FP16X3):
+    """Rebind `_forward_perpix` of a reference Generator (or its .module) to the fused kernel."""
+    gen = getattr(gen, 'module', gen)
+    if hasattr(gen, '_sdb200'):
+        return gen
+    st = _FusedState(gen, precision)
+    st.reference_forward = gen._forward_perpix            # bound method of the unmodified reference
+    gen._sdb200 = st
+    gen._forward_perpix = types.MethodType(fused_forward_perpix, gen)
+    return gen

@@ -36,6 +36,7 @@ class _RenderParams(ctypes.Structure):
         ('d_mlp_pack', ctypes.c_void_p), ('mlp_pack_stride', ctypes.c_int64), ('precision', ctypes.c_int32),
         ('d_sky', ctypes.c_void_p), ('d_sky_avg', ctypes.c_void_p),
         ('d_net_out', ctypes.c_void_p), ('d_depth_out', ctypes.c_void_p), ('d_total_weight', ctypes.c_void_p),
+        ('d_weights_out', ctypes.c_void_p), ('d_rand_depth_out', ctypes.c_void_p),
         ('d_workspace', ctypes.c_void_p),
     ]
 
@@ -166,11 +167,12 @@ def sky_features(P, raydirs, z, prefix='sky_net', pe=(5, True)):
 def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_dims, label_lut, mlp_pack, sky, sky_avg,
                         table=None, table3=None, num_samples=24, sample_depth=3.0, dists_scale=0.25, uniforms=None,
                         precision=PRECISION_FP16X3, per_level_scale=None, base_res=16, log2_T=19, L=16,
-                        want_depth=True):
+                        want_depth=True, want_samples=False):
     """Fused a2-a12.  Shapes follow the reference:
     voxel_id [N,H,W,M,1] int32, depth2 [N,2,H,W,M,1], raydirs [N,H,W,1,3], cam_ori [N,3], global_enc [N,2],
     sky [N,H,W,64], sky_avg [N,64]; label_lut int32 [n] (ignore already mapped to dirt).
-    Returns dict(net_out [N,H,W,64], depth [N,H,W], total_weight [N,H,W])."""
+    Returns dict(net_out [N,H,W,64], depth [N,H,W], total_weight [N,H,W] and, with want_samples,
+    weights / rand_depth [N,H,W,S,1] as _forward_perpix returns them)."""
     dev = voxel_id.device
     N, H, W, M = voxel_id.shape[:4]
     S = int(num_samples)
@@ -182,6 +184,8 @@ def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_di
     net_out = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
     depth = torch.empty(N, H, W, dtype=torch.float32, device=dev) if want_depth else None
     tw = torch.empty(N, H, W, dtype=torch.float32, device=dev) if want_depth else None
+    wts = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev) if want_samples else None
+    rdp = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev) if want_samples else None
     Lb = _lib.lib()
     ws = torch.empty(int(Lb.sdb_render_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
     cam_ori = cam_ori.to(dev, torch.float32).reshape(N, 3).contiguous()
@@ -210,11 +214,12 @@ def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_di
     sky_avg = sky_avg.to(dev, torch.float32).reshape(N, 64).contiguous()
     prm.d_sky, prm.d_sky_avg = _ptr(sky), _ptr(sky_avg)
     prm.d_net_out, prm.d_depth_out, prm.d_total_weight = _ptr(net_out), _ptr(depth), _ptr(tw)
+    prm.d_weights_out, prm.d_rand_depth_out = _ptr(wts), _ptr(rdp)
     prm.d_workspace = _ptr(ws)
     with torch.cuda.device(dev):
         code = Lb.sdb_render_rays_forward(ctypes.byref(prm), _stream(dev))
     _lib.check(code, 'sdb_render_rays_forward')
-    return dict(net_out=net_out, depth=depth, total_weight=tw)
+    return dict(net_out=net_out, depth=depth, total_weight=tw, weights=wts, rand_depth=rdp)
 
 
 def reduced_label_lut(mc2reduced, ignore_id=0, dirt_id=3):
@@ -259,7 +264,7 @@ class FusedPerPixelRenderer:
         return self._t3
 
     def forward(self, voxel_id, depth2, raydirs, cam_ori, z, global_enc, num_samples=24, sample_depth=3.0,
-                dists_scale=0.25, uniforms=None, sky_avg=None, sky=None):
+                dists_scale=0.25, uniforms=None, sky_avg=None, sky=None, want_samples=False):
         N = voxel_id.shape[0]
         if sky is None:
             if self.sky_impl == 'native':
@@ -278,6 +283,6 @@ class FusedPerPixelRenderer:
         out = render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, self.voxel_dims, self.lut, pack, sky,
                                   sky_avg, num_samples=num_samples, sample_depth=sample_depth, dists_scale=dists_scale,
                                   uniforms=uniforms, precision=self.precision, per_level_scale=self.pls,
-                                  base_res=self.base_res, log2_T=self.log2_T, L=self.L, **kw)
+                                  base_res=self.base_res, log2_T=self.log2_T, L=self.L, want_samples=want_samples, **kw)
         out['sky'], out['sky_avg'] = sky, sky_avg
         return out

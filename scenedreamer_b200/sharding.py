@@ -1,0 +1,43 @@
+"""Multi-GPU sharding of the render path.
+
+Rays are independent given replicated read-only state (voxel volume, hash table, MLP weights), so
+frames shard across ranks with NO data-path collective; the single collective of the path is one
+all-gather of the finished per-frame maps.  One process per GPU (torch.distributed, NCCL on GPUs,
+gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def frames_for_rank(n_frames, rank, world_size):
+    """Frame f is rendered by rank f mod world_size (round-robin keeps camera-path neighbours apart,
+    which balances sky-heavy and ground-heavy frames)."""
+    return list(range(rank, n_frames, world_size))
+
+
+def frame_owner(frame, world_size):
+    return frame % world_size
+
+
+def gather_frames(local, group=None):
+    """local: [n_local, ...] finished maps of this rank's frames (same n_local on every rank; pad the
+    last round with a repeat if n_frames % world_size != 0).  Returns [world_size * n_local, ...]
+    ordered by global frame index f = i * world_size + rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    n_local = local.shape[0]
+    out = torch.empty((world * n_local,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)      # rank-major concatenation along dim 0
+    out = out.view((world, n_local) + tuple(local.shape[1:]))
+    # out[r, i] is frame i * world + r  ->  interleave ranks
+    return out.transpose(0, 1).reshape((world * n_local,) + tuple(local.shape[1:]))
+
+
+def tile_rows_for_rank(H, rank, world_size, tile_h=8):
+    """Single-frame sharding: contiguous bands of tile rows per rank (strong scaling of one frame)."""
+    tiles = (H + tile_h - 1) // tile_h
+    per = (tiles + world_size - 1) // world_size
+    y0 = min(H, rank * per * tile_h)
+    y1 = min(H, (rank + 1) * per * tile_h)
+    return y0, y1

@@ -1,0 +1,124 @@
+"""GPU tests of the drop-in boundary: gridencoder.GridEncoder autograd (forward + both backward
+kernels) and the reference-side integration hook that replaces Generator._forward_perpix."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from scenedreamer_b200 import integration, ops, render, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+DEV = 'cuda:0'
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+@pytest.fixture(scope='module')
+def gridencoder_pkg():
+    sys.path.insert(0, os.path.join(ROOT, 'dropin'))
+    import gridencoder
+    yield gridencoder
+    sys.path.remove(os.path.join(ROOT, 'dropin'))
+
+
+def device_level_scales(L, pls, base):
+    S = torch.tensor(float(np.float32(np.log2(pls))), device=DEV)
+    return (torch.exp2(torch.arange(L, device=DEV, dtype=torch.float32) * S) * float(base) - 1.0).cpu()
+
+
+@pytest.mark.parametrize('D,L,C,base,log2T,desired', [(5, 16, 8, 16, 19, 2048), (3, 8, 2, 4, 12, 64)])
+def test_gridencoder_module_forward_backward(gridencoder_pkg, D, L, C, base, log2T, desired):
+    ge = gridencoder_pkg.GridEncoder(input_dim=D, num_levels=L, level_dim=C, base_resolution=base,
+                                     log2_hashmap_size=log2T, desired_resolution=desired).to(DEV)
+    g = torch.Generator().manual_seed(D)
+    ge.embeddings.data = ((torch.rand(ge.embeddings.shape, generator=g) * 2 - 1) * 0.1).to(DEV)
+    x = (torch.rand(2, 500, D, generator=g) * 2 - 1)
+    xd = x.to(DEV).requires_grad_(True)
+    y = ge(xd)
+    assert y.shape == (2, 500, L * C)
+    ls = device_level_scales(L, ge.per_level_scale, base)
+    ref = oracle.grid_encoder_module_forward(x, ge.embeddings.detach().cpu(), ge.offsets.cpu(), ge.per_level_scale, base,
+                                             level_scales=ls)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-7)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy.to(DEV))
+    x01 = ((x + 1) / 2).reshape(-1, D)
+    _, dy_dx = oracle.grid_encode_forward(x01, ge.embeddings.detach().cpu(), ge.offsets.cpu(), ge.per_level_scale, base, True,
+                                          level_scales=ls)
+    gl = gy.reshape(-1, L, C).permute(1, 0, 2).contiguous()
+    ege, egi = oracle.grid_encode_backward(gl, x01, ge.embeddings.detach().cpu(), ge.offsets.cpu(), ge.per_level_scale, base,
+                                           dy_dx, level_scales=ls)
+    np.testing.assert_allclose(ge.embeddings.grad.cpu().numpy(), ege.numpy(), rtol=1e-4, atol=1e-5)
+    # d/dx of the [-1,1] -> [0,1] mapping is 1/2
+    np.testing.assert_allclose(xd.grad.cpu().reshape(-1, D).numpy(), 0.5 * egi.numpy(), rtol=1e-3,
+                               atol=1e-4 * float(egi.abs().max()))
+    # no input grad requested -> only the embedding grad kernel runs
+    ge.zero_grad()
+    ge(x.to(DEV)).backward(gy.to(DEV))
+    np.testing.assert_allclose(ge.embeddings.grad.cpu().numpy(), ege.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_patched_forward_perpix_matches_oracle(golden_ops):
+    """A duck-typed stand-in for the reference Generator (same attribute names as
+    imaginaire/generators/scenedreamer.py / gancraft_base.py) through integration.patch_generator."""
+    world = synth.SyntheticVoxelWorld(size=128, seed=7)
+    pose = synth.eval_camera_poses(world, maxstep=8, pattern=0)[2]
+    o, d, u, f, c, res = synth.frame_camera(world, pose, resolution_hw=(36, 52), pad=4)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV), o, d, u, f, c, res, 6)
+    P = oracle.make_params(seed=44, stress=True)
+    offsets, pls = oracle.grid_offsets()
+
+    class Holder(torch.nn.Module):
+        def __init__(self, sd):
+            super().__init__()
+            for k, v in sd.items():
+                self.register_buffer(k.replace('.', '__'), v.to(DEV))
+
+        def state_dict(self, *a, **k):
+            return {n.replace('__', '.'): b for n, b in self.named_buffers()}
+
+    def sub(prefix):
+        return Holder({k[len(prefix) + 1:]: v for k, v in P.items() if k.startswith(prefix + '.')})
+
+    gen = types.SimpleNamespace()
+    gen.render_net, gen.sky_net, gen.hash_encoder = sub('render_net'), sub('sky_net'), sub('hash_encoder')
+    gen.hash_encoder.per_level_scale, gen.hash_encoder.base_resolution = pls, 16
+    gen.hash_encoder.log2_hashmap_size, gen.hash_encoder.num_levels = 19, 16
+    gen.voxel = types.SimpleNamespace(voxel_t=world.voxel_t.to(DEV))
+    gen.label_trans = types.SimpleNamespace(mcid2rdid_lut=torch.from_numpy(golden_ops['mc2reduced_lut']).long(),
+                                            ignore_id=0, dirt_id=3)
+    gen.clip_feat_map, gen.keep_sky_out, gen.keep_sky_out_avgpool, gen.sky_global_avgpool = True, True, True, True
+    gen.sample_use_box_boundaries, gen.raw_noise_std = False, 0.0
+    gen.pe_params, gen.pe_params_sky = [0, 0, 0, False], [5, True]
+    gen.coarse_deterministic_sampling, gen.num_samples, gen.sample_depth, gen.dists_scale = True, 24, 3, 0.25
+    called = {}
+    gen._forward_perpix = lambda *a: called.setdefault('ref', True)
+    integration.patch_generator(gen)
+    g = torch.Generator().manual_seed(8888)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    with torch.no_grad():
+        ret = gen._forward_perpix(None, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0).to(DEV),
+                                  z.to(DEV), genc.to(DEV))
+    torch.cuda.synchronize()
+    assert len(ret) == 12 and 'ref' not in called
+    S = torch.tensor(float(np.float32(np.log2(pls))), device=DEV)
+    ls = (torch.exp2(torch.arange(16, device=DEV, dtype=torch.float32) * S) * 16.0 - 1.0).cpu()
+    ref = oracle.forward_perpix(P, vid.unsqueeze(0).cpu(), dep.unsqueeze(0).cpu(), rd.unsqueeze(0).cpu(), o.unsqueeze(0), z, genc,
+                                list(world.voxel_t.shape), torch.from_numpy(golden_ops['mc2reduced_lut']), offsets, pls,
+                                level_scales=ls)
+    assert float((ret[0].cpu() - ref['net_out']).abs().max()) <= 1e-3
+    assert float((ret[2].cpu() - ref['weights']).abs().max()) <= 1e-3                      # weights [N,H,W,S,1]
+    np.testing.assert_allclose(ret[4].cpu().numpy(), ref['rand_depth'].numpy(), rtol=1e-6, atol=1e-5)   # rand_depth
+    assert float((ret[3].cpu() - ref['total_weights']).abs().max()) <= 1e-3
+    assert torch.equal(ret[9].cpu(), ref['sky_mask']) and torch.equal(ret[10].cpu(), ref['sky_only_mask'])
+    # depth variant of the reference: sum(weights * rand_depth) (scenedreamer.py:816)
+    dmap = torch.sum(ret[2] * ret[4], dim=-2)
+    assert float((dmap.cpu() - ref['depth_map']).abs().max()) <= 1e-3
+    # with autograd enabled the hook defers to the reference's own composition
+    gen._forward_perpix(None, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0).to(DEV), z.to(DEV),
+                        genc.to(DEV))
+    assert called.get('ref')

@@ -1,0 +1,58 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the frame sharding + the single all-gather."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from scenedreamer_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_frames, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    mine = sharding.frames_for_rank(n_frames, rank, world)
+    # a "rendered frame" is a tensor filled with its global frame index
+    local = torch.stack([torch.full((2, 3, 4), float(f)) for f in mine])
+    allf = sharding.gather_frames(local)
+    ok = allf.shape == (n_frames, 2, 3, 4) and all(float(allf[f].mean()) == float(f) for f in range(n_frames))
+    q.put((rank, mine, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frame_sharding_and_all_gather_world2():
+    world, n_frames = 2, 6
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3, 5]
+    assert res[0][2] and res[1][2]
+
+
+def test_partitions_are_disjoint_and_complete():
+    for world in (1, 2, 4, 8):
+        frames = sorted(f for r in range(world) for f in sharding.frames_for_rank(40, r, world))
+        assert frames == list(range(40))
+        assert all(sharding.frame_owner(f, world) == f % world for f in range(40))
+        rows = [sharding.tile_rows_for_rank(570, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 570
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+        assert all(y0 % 8 == 0 for y0, _ in rows)
