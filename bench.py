@@ -55,32 +55,41 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md): one streaming
+    `nvidia-smi -lms 100` process, lines collected by this thread."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
-        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        while not self._stop_evt.is_set():
-            try:
-                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+        except Exception:       # noqa: BLE001  (no nvidia-smi: clocks stay None)
+            pass
 
-    def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+    def stop(self, t0=None, t1=None):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=5)
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [r for _, r in self.rows]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
 
@@ -230,18 +239,19 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
-    t_wall = time.perf_counter()
+    t_begin = t_wall = time.perf_counter()
     for k in range(args.steps):
         one_step(k, evs[k], kevs[k])
         flush.zero_()                                                # L2 flush between timed iterations
     torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall
+    t_end = time.perf_counter()
+    t_wall = t_end - t_wall
     if world_size > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     kern_ms = [a.elapsed_time(b) for a, b in kevs]
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
@@ -265,6 +275,8 @@ def run_gpu_arm(args):
     if world_size > 1:
         dist.all_reduce(dtot, op=dist.ReduceOp.MAX)
     dev_tot_ms = float(dtot[0])
+    # clocks are sampled over BOTH timed loops (host-inclusive and device-only)
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
 
     if rank == 0:
         hbm, tf, which = measured_peaks()
