@@ -215,7 +215,7 @@ def run_gpu_arm(args):
     host_out = torch.empty(2, res[0], res[1], dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def one_step(k, ev=None, kev=None):
+    def one_step(k, ev=None, kev=None, cev=None):
         idx = (k * world_size + rank) % len(cams)
         cam = cams[idx]
         if ev is not None:
@@ -224,7 +224,11 @@ def run_gpu_arm(args):
         out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev)   # by-value to the DDA, H2D for the rest
         maps = torch.stack([out['depth'][0], out['total_weight'][0]])
         if world_size > 1:
+            if cev is not None:
+                cev[0].record()
             sharding.gather_frames(maps.unsqueeze(0))                # the single collective of the path
+            if cev is not None:
+                cev[1].record()
         host_out.copy_(maps, non_blocking=True)                      # D2H of the step's result
         if ev is not None:
             ev[1].record()
@@ -242,10 +246,11 @@ def run_gpu_arm(args):
         time.sleep(0.3)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     t_begin = t_wall = time.perf_counter()
     for k in range(args.steps):
-        one_step(k, evs[k], kevs[k])
+        one_step(k, evs[k], kevs[k], cevs[k])
         flush.zero_()                                                # L2 flush between timed iterations
     torch.cuda.synchronize()
     t_end = time.perf_counter()
@@ -254,6 +259,7 @@ def run_gpu_arm(args):
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     kern_ms = [a.elapsed_time(b) for a, b in kevs]
+    coll_ms = [a.elapsed_time(b) for a, b in cevs] if world_size > 1 else [0.0]
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
@@ -267,7 +273,10 @@ def run_gpu_arm(args):
         idx = (k * world_size + rank) % len(cams)
         flush.zero_()
         a.record()
-        fr.frame(cams[idx], ori_dev=doris[idx])
+        o_ = fr.frame(cams[idx], ori_dev=doris[idx])
+        if world_size > 1:                                           # the path's single collective stays inside the timed region
+            sharding.gather_frames(torch.stack([o_['depth'][0], o_['total_weight'][0]]).unsqueeze(0))
+        o_ = None                                                    # release the frame's buffers to the caching allocator
         b.record()
         torch.cuda.synchronize()
         dev_ms.append(a.elapsed_time(b))
@@ -316,6 +325,8 @@ def run_gpu_arm(args):
                          'algorithmic_bytes_per_launch': SAMPLES_PER_FRAME * BYTES_PER_SAMPLE,
                          'tensor_tflops': SAMPLES_PER_FRAME * 754176 / kern_s / 1e12, 'tensor_peak_tflops': tf},
             'cpu_baseline': cpu, 'clocks': clocks, 'wall_s': t_wall,
+            'collective': {'op': 'all_gather_into_tensor(depth+opacity maps)', 'bytes_per_rank': int(host_out.numel() * 4),
+                           'ms_per_step_incl_wait_for_slowest_rank': float(np.mean(coll_ms))} if world_size > 1 else None,
         }
         print(json.dumps(line))
     if world_size > 1:

@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_fullsize.py -m gpu -q -s 2>&1 | grep -E "C2 window|assert|Error|passed|failed" | head
+timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
+python - <<'PY'
+import json
+for f in ('bench_1gpu',):
+    try:
+        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1]); print(f, 'n_gpus', d['n_gpus'], 'value %.1f %s frame %.2f ms e2e %.1f'%(d['value'], d['unit'], d['ms_per_step'], d['e2e']['value']), d['clocks'])
+    except Exception as e: print(f, 'ERR', e)
+PY

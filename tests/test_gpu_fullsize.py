@@ -40,8 +40,9 @@ def test_c2_frame_window_parity_and_properties(golden_ops):
     net_raw = r_raw.forward(*args, sky=out['sky'], sky_avg=out['sky_avg'])['net_out']
     assert float((net_raw - net).abs().max()) <= 2e-4
     # a 48x64 window straddling the horizon vs the oracle (same frame-global sky mean)
-    ys = int(torch.nonzero((vid[..., 0, 0] != 0).any(dim=1))[0]) if live < 1 else 0
-    y0 = max(0, min(res[0] - 48, ys - 16)); x0 = 400
+    x0 = 400
+    ys = int(torch.nonzero((vid[:, x0:x0 + 64, 0, 0] != 0).any(dim=1))[0])      # first row with a hit in these columns
+    y0 = max(0, min(res[0] - 48, ys - 16))
     sl = (slice(y0, y0 + 48), slice(x0, x0 + 64))
     S = torch.tensor(float(np.float32(np.log2(pls))), device=DEV)
     ls = (torch.exp2(torch.arange(16, device=DEV, dtype=torch.float32) * S) * 16.0 - 1.0).cpu()
@@ -51,7 +52,12 @@ def test_c2_frame_window_parity_and_properties(golden_ops):
     err = float((net[0][sl].cpu() - ref['net_out'][0]).abs().max())
     derr = float((out['depth'][0][sl].cpu() - ref['depth_map'][0].squeeze(-1)).abs().max())
     print('C2 window (%d:%d, %d:%d) max err net_out %.3e depth %.3e, live fraction %.2f' % (y0, y0 + 48, x0, x0 + 64, err, derr, live))
-    assert err <= 1e-3 and derr <= 1e-3
+    # depth = sum_s w*t with t of several hundred voxels in this scene: ulp(512) = 6e-5, so 1e-3 ABSOLUTE is at
+    # the fp32 rounding level of the 24-term sum; the bar is 1e-3 absolute or 1e-5 relative, whichever is larger
+    dmax = float(ref['depth_map'].abs().max())
+    assert err <= 1e-3 and derr <= max(1e-3, 1e-5 * dmax), (err, derr, dmax)
+    wl = float((vid[sl][..., 0, 0] != 0).float().mean())
+    assert 0.2 < wl < 1.0, wl                     # the window really mixes sky and geometry
     # full-frame DDA vs oracle, bit exact
     evid, edep, _ = oracle.ray_voxel_intersection_perspective(world.voxel_t, o, d, u, f, c, res, 6)
     assert torch.equal(vid.cpu(), evid)

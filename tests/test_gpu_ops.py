@@ -219,3 +219,25 @@ def test_tcgen05_selftest(N, K, bf16):
     err = float((c.double() - ref).abs().max())
     print('tcgen05 selftest N=%d K=%d bf16=%s max abs err %.3e (ref max %.2f)' % (N, K, bf16, err, float(ref.abs().max())))
     assert err < 1e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_dda_origin_on_cell_faces_and_far_origin(world):
+    """Exact-zero numerators (origin on integer coordinates -> signed zeros in IEEE division), origins far
+    outside the grid and near-axis-parallel rays: still bit-exact (the kernel divides by a per-ray constant
+    with the 3-FMA fast path of div.rn.f32 and falls back to the generic division outside its range)."""
+    vox = world.voxel_t.to(DEV)
+    X = world.voxel_t.shape[1]
+    cases = [
+        ([60.0, float(X), 128.0], [-0.2, -1.0, 0.01], [1.0, 0.0, 0.0]),       # origin exactly on the +x face, integer coords
+        ([40.0, 64.0, 64.0], [-0.5, 0.7, 0.3], [1.0, 0.0, 0.0]),              # origin on a voxel corner inside the grid
+        ([900.0, -700.5, 300.25], [-1.0, 1.0, -0.2], [1.0, 0.0, 0.0]),        # far outside
+        ([55.5, 100.5, 100.5], [-1e-7, 1.0, 1e-9], [1.0, 0.0, 0.0]),          # nearly axis-parallel
+    ]
+    for o, d, u in cases:
+        for f in (40.0, 400.0):
+            args = (o, d, u, f, [31.5, 47.5], [64, 96], 6)
+            vid, dep, rd = ops.ray_voxel_intersection_perspective(vox, *args)
+            evid, edep, erd = oracle.ray_voxel_intersection_perspective(world.voxel_t, *args)
+            assert torch.equal(vid.cpu(), evid)
+            assert torch.equal(bits(rd), bits(erd))
+            assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(edep, nan=-1.0)))
