@@ -183,6 +183,57 @@ int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W,
                     int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
                     void *stream);
 
+/* --------------------------------------------------------------------------------------------
+ * a7 + backward of a8/a10/a11: training.  sdb_render_rays_train_forward is sdb_render_rays_forward
+ * (fp16x3, pre-blended table: p->d_table3, p->precision == 2) that additionally writes a RECORD of
+ * the pass into caller-owned device memory: per-sample hash-grid coordinates and features, the six
+ * hidden activations (bf16) with their LeakyReLU sign words, sigma, interval length and the colour
+ * head output.  sdb_render_rays_backward turns dL/d net_out into every parameter gradient of the
+ * per-pixel path -- what torch.autograd produces for Generator._forward_perpix in the reference
+ * (imaginaire/generators/scenedreamer.py:313-428 under train.py; kernel_grid_backward /
+ * kernel_input_backward gridencoder.cu:227-343 for the table and the scene code):
+ *   1. compositing backward (volum_rendering_relu, clamp, sky blend; mc_utils.py:154-161,
+ *      scenedreamer.py:373-413)                       -> dL/dc, dL/dsigma per sample, dL/dsky;
+ *   2. the data-gradient chain of LightningMLP on the tcgen05 engine (transposed weights, bf16x3)
+ *      -> dZ of every layer (bf16 record) and dL/d features;
+ *   3. table backward through the pre-blended 3-D table (vector red.add), un-blend to the raw 5-D
+ *      table, and the scene-code gradient;
+ *   4. weight gradients: bf16 GEMMs dZ^T * A over all samples (cuBLAS, fp32 accumulate/output).
+ * The same sdb_render_params as the forward call must be passed (same rays, uniforms, packs).
+ * The call reads the live-tile count back (one 4-byte D2H copy + stream synchronize).
+ * ------------------------------------------------------------------------------------------ */
+int64_t sdb_render_train_record_bytes(int32_t n_img, int32_t H, int32_t W, int32_t S);
+int sdb_render_rays_train_forward(const sdb_render_params *p, void *d_record, void *stream);
+
+/* Packed TRANSPOSED weights for step 2 (bf16 hi/lo): w1 [256,128], wh [5][256,256] (style-modulated,
+ * as for sdb_pack_mlp), wsig [256], wout [64,256]; device fp32 for ONE style code.              */
+int64_t sdb_mlp_backward_pack_bytes(void);
+int sdb_pack_mlp_backward(const float *d_w1, const float *d_wh, const float *d_wsig, const float *d_wout,
+                          void *d_pack, void *stream);
+
+typedef struct sdb_render_grads {
+    const float *d_grad_net_out;   /* in  [R, 64]  dL/d net_out                                     */
+    const void *d_bwd_pack;        /* in  sdb_pack_mlp_backward image(s)                            */
+    int64_t bwd_pack_stride;       /*     0 = all images share one pack                             */
+    const float *d_table;          /* in  raw 5-D table [L*T, 8] (for the scene-code gradient)      */
+    /* outputs (all written, none accumulated into)                                                 */
+    float *d_grad_table;           /* [L*T, 8]  dL/d hash_encoder.embeddings                        */
+    float *d_grad_global_enc;      /* [2]       dL/d scene code (summed over images)                */
+    float *d_grad_w1ext;           /* [256, 144] cols 0..127 fc_1.weight, 128+k fc_m_a.weight[:,k], 143 fc_1.bias */
+    float *d_grad_wh;              /* [5][256, 264] cols 0..255 dL/dW' (modulated weight), col 256 dL/dbeta        */
+    float *d_grad_wsig;            /* [8, 264]  row 0: cols 0..255 fc_sigma.weight, col 256 fc_sigma.bias          */
+    float *d_grad_wout;            /* [64, 264] cols 0..255 fc_out_c.weight, col 256 fc_out_c.bias                 */
+    float *d_grad_sky;             /* [R, 64]   dL/d sky features per ray                           */
+    float *d_grad_sky_avg;         /* [n_img, 64]                                                   */
+    void *d_workspace;             /* sdb_render_backward_workspace_bytes() bytes                   */
+} sdb_render_grads;
+
+int64_t sdb_render_backward_workspace_bytes(int32_t n_img, int32_t H, int32_t W, int32_t S, int32_t L, int32_t log2_T);
+int sdb_render_rays_backward(const sdb_render_params *p, const void *d_record, const sdb_render_grads *g, void *stream);
+
+/* Diagnostics only: byte offsets inside the training record / backward workspace (20 int64, see render_train.cu). */
+int sdb_debug_train_layout(int32_t n_img, int32_t H, int32_t W, int32_t S, int32_t L, int32_t log2_T, int64_t *out);
+
 /* Diagnostics only: host-mapped (pinned) int32[64] progress buffer written by CTA 0 of the fused
  * kernels (role, step, layer markers); pass NULL to disable (default).                          */
 void sdb_debug_set_progress_buffer(void *mapped);

@@ -471,3 +471,80 @@ def forward_perpix(P, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc, voxel
                 sky_used=sky_used, nosky_mask=nosky_mask, sky_mask=sky_mask, sky_only_mask=sky_only_mask,
                 new_idx=new_idx, labels=mc_masks, worldcoord2=worldcoord2, normalized=normalized,
                 depth_map=depth_map, sky_avg=sky_avg)
+
+
+# ----------------------------------------------------------------------------------------------
+# Differentiable restatement (training parity): the per-pixel stage under torch.autograd, with the
+# hash-grid forward/backward of oracle.c behind the same autograd.Function the reference uses
+# (gridencoder/grid.py:19-87: _grid_encode.forward / .backward).
+# ----------------------------------------------------------------------------------------------
+class _GridEncodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, level_scales):
+        calc = bool(inputs.requires_grad)
+        out, dy_dx = grid_encode_forward(inputs, embeddings, offsets, per_level_scale, base_resolution, calc,
+                                         level_scales=level_scales)
+        ctx.save_for_backward(inputs.detach(), embeddings.detach(), offsets)
+        ctx.dy_dx, ctx.args = dy_dx, (per_level_scale, base_resolution, level_scales)
+        L, B, C = out.shape
+        return out.permute(1, 0, 2).reshape(B, L * C)                       # grid.py:52
+
+    @staticmethod
+    def backward(ctx, grad):
+        inputs, embeddings, offsets = ctx.saved_tensors
+        pls, base, ls = ctx.args
+        L = offsets.numel() - 1
+        B = inputs.shape[0]
+        C = embeddings.shape[1]
+        g = grad.reshape(B, L, C).permute(1, 0, 2).contiguous()             # grid.py:72
+        ge, gi = grid_encode_backward(g, inputs, embeddings, offsets, pls, base, dy_dx=ctx.dy_dx, level_scales=ls)
+        return gi, ge, None, None, None, None
+
+
+def forward_perpix_autograd(P, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc, voxel_dims, mc2reduced_lut,
+                            offsets, per_level_scale, num_samples=24, sample_depth=3.0, deterministic=True,
+                            uniforms=None, dists_scale=0.25, ignore_id=0, dirt_id=3, pe_sky=(5, True),
+                            base_resolution=16, level_scales=None):
+    """forward_perpix with the autograd graph kept (small frames only): returns net_out [N,H,W,64] that can be
+    back-propagated to P[...] (leaf tensors with requires_grad), z and global_enc.  sky_avg is the batch mean as in
+    training (scenedreamer.py:395)."""
+    voxel_id = voxel_id.cpu()
+    depth2, raydirs, cam_ori_t = map(_f32, (depth2, raydirs, cam_ori_t))
+    N, H, W, M = voxel_id.shape[:4]
+    with torch.no_grad():
+        sky_mask = voxel_id[:, :, :, [-1], :] == 0
+        sky_only_mask = voxel_id[:, :, :, [0], :] == 0
+        rand_depth, new_dists, new_idx = sample_depth_batched(
+            depth2, num_samples + 1, deterministic=deterministic, sample_depth=sample_depth, uniforms=uniforms)
+        bad = torch.isnan(rand_depth) | torch.isinf(rand_depth)
+        rand_depth[bad] = 0.0
+        worldcoord2 = raydirs * rand_depth + cam_ori_t[:, None, None, None, :]
+        lut = mc2reduced_lut.to(torch.long)
+        reduced = lut[voxel_id.long()]
+        reduced[reduced == ignore_id] = dirt_id
+        mc_masks = torch.gather(reduced, -2, new_idx).long()
+        delim = torch.tensor([float(v) for v in voxel_dims], dtype=torch.float32)
+        normalized = worldcoord2 / delim * 2 - 1
+    S = normalized.shape[3]
+    genc = global_enc[:, None, None, None, :].expand(-1, H, W, S, -1)
+    x5 = torch.cat([normalized, genc], dim=-1)                              # scenedreamer.py:300-302
+    x01 = (x5 + 1) / 2                                                      # grid.py:144
+    feats = _GridEncodeFn.apply(x01.reshape(-1, 5), P['hash_encoder.embeddings'], offsets, per_level_scale,
+                                base_resolution, level_scales).reshape(N, H * W * S, -1)
+    sig, col = render_mlp(feats, z, mc_masks.reshape(N, H * W * S), P)
+    net_out_s = sig.reshape(N, H, W, S, 1)
+    net_out_c = col.reshape(N, H, W, S, 64)
+    pe = positional_encoding_pt(raydirs, pe_sky[0], -1, pe_sky[1])
+    skynet_out_c = sky_mlp(pe.reshape(N, H * W, -1), z, P).reshape(N, H, W, 1, 64)
+    weights = volum_rendering_relu(net_out_s, new_dists * dists_scale, dim=-2)
+    weights = weights * torch.logical_not(sky_only_mask).float()
+    total_weights = torch.sum(weights, dim=-2, keepdim=True)
+    is_gnd = (worldcoord2[..., [0]] <= 1.0).any(dim=-2, keepdim=True)
+    nosky_mask = torch.logical_or(torch.logical_not(sky_mask), is_gnd).float()
+    sky_weight = 1.0 - total_weights
+    sky_avg = torch.mean(skynet_out_c, dim=[1, 2], keepdim=True)
+    sky_used = skynet_out_c * (1.0 - nosky_mask) + sky_avg * nosky_mask
+    rgbs = torch.clamp(net_out_c, -1, 1) + 1
+    rgbs_sky = torch.clamp(sky_used, -1, 1) + 1
+    net_out = torch.sum(weights * rgbs, dim=-2, keepdim=True) + sky_weight * rgbs_sky
+    return net_out.squeeze(-2) - 1

@@ -32,185 +32,11 @@
 //     ~2^-16 resp. ~2^-21 relative, i.e. fp32-grade for the 1e-3 parity bar); accumulation is fp32 in TMEM;
 //   * sky-only tiles never reach the render kernel: a pre-pass writes their outputs and compacts the
 //     list of live tiles (their compositing weights are exactly zero, scenedreamer.py:376).
-#include <math.h>
-
-#include "common.cuh"
-#include "tc05.cuh"
+#include "rf_common.cuh"
 
 namespace rf {
 
-constexpr int kRows = 128, kTileW = 16, kTileH = 8;
-constexpr int kHidden = 256, kFeat = 128, kOutC = 64, kLevels = 16;
-constexpr int kKExt = 16;                       // extra K columns: labels / bias
-constexpr int kKH = kHidden + kKExt;            // 272: K of every layer fed by hidden activations
-constexpr int kMaxM = 8, kMaxS = 64, kMaxLabels = 15;
-constexpr int kEpiThreads = 256, kGatherThreads = 256;
-// warpgroup-aligned roles so that setmaxnreg can move registers from the control group to the gather group:
-//   WG0-1 epilogue (warps 0-7), WG2 control (8: weight loader, 9: MMA issuer, 10-11 idle), WG3-4 gather (12-19)
-constexpr int kLoaderWarp = 8, kMmaWarp = 9, kGatherWarp0 = 12;
-constexpr int kThreads = kEpiThreads + 128 + kGatherThreads;   // 640
-// setmaxnreg can only redistribute the registers the CTA was LAUNCHED with (640 threads x 96 = 61,440; the
-// allocator is a per-CTA pool -- USETMAXREG.TRY_ALLOC.CTAPOOL spins forever otherwise):
-//   8 epilogue warps x 96 + 4 control warps x 48 + 8 gather warps x 120 = 61,440
-constexpr int kRegsLaunch = 96, kRegsCtl = 48, kRegsGather = 120;
-static_assert(8 * 32 * kRegsLaunch + 4 * 32 * kRegsCtl + 8 * 32 * kRegsGather <= kThreads * kRegsLaunch,
-              "setmaxnreg budget exceeds the CTA's launch-time register allocation");
-constexpr int kRingBytes = 65536;
-constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kLboA = kRows * 16, kSbo = 128;
-constexpr int kHChunks = kKH / 8;               // 34 16-byte k-chunks per row
-constexpr int kHBytes = kHChunks * kRows * 16;  // 69,632 bytes per operand part
-constexpr int kSkyK0 = 48;                      // PE(raydir) 33 + zeros + bias column 47
-constexpr int kRenderK0 = kFeat + kKExt;        // 144
-
-// network shapes: SKY = false: LightningMLP (6 hidden + colour), true: SKYMLP (5 hidden + colour)
-template <bool SKY> struct Net {
-    static constexpr int NH = SKY ? 5 : 6;
-    static constexpr int NL = NH + 1;
-    static constexpr int K0 = SKY ? kSkyK0 : kRenderK0;
-};
-template <bool SKY> __host__ __device__ constexpr int layerK(int l) { return l == 0 ? Net<SKY>::K0 : kKH; }
-template <bool SKY> __host__ __device__ constexpr int layerN(int l) { return l == Net<SKY>::NL - 1 ? kOutC : kHidden; }
-template <bool SKY> __host__ __device__ constexpr int64_t layerOff(int l, int parts) {
-    int64_t o = 0;
-    for (int j = 0; j < l; j++) o += (int64_t)layerK<SKY>(j) * layerN<SKY>(j) * 2 * parts;
-    return o;
-}
-// fp32 tail of the render pack: sigma head
-constexpr int kFWsig = 0, kFBsig = 256, kFTotal = 264;
-template <bool SKY> __host__ __device__ constexpr int64_t packBytes(int parts) {
-    return layerOff<SKY>(Net<SKY>::NL, parts) + (SKY ? 0 : (int64_t)kFTotal * 4);
-}
-// Weight-ring schedule.  A ring stage holds KS consecutive k16 slabs (KS = 1 for the x3 modes, 2 for the
-// single-pass mode so that a stage is 16 KB either way).  Layers fed by hidden activations (K = 272) consume
-// the K extension first (no dependency), then the 64-column chunks in the order the two epilogue halves
-// produce them (0 and 2 first, then 1 and 3).  Loader and MMA issuer walk the same list.
-template <int KS, bool SKY> __host__ __device__ constexpr int num_stages(int l) {
-    return l == 0 ? (Net<SKY>::K0 / 16 + KS - 1) / KS : 1 + 16 / KS;   // extension + 8 chunks x (2 / KS)
-}
-// 32-column operand chunks (2 k16 steps each): chunk ids 0..3 are written by the epilogue half that owns
-// columns 0..127, ids 4..7 by the other half; both halves advance together -> consumption order 0,4,1,5,2,6,3,7
-__host__ __device__ constexpr int chunk_order(int c) { return (c >> 1) + (c & 1) * 4; }
-template <int KS, bool SKY> __host__ __device__ constexpr int stage_kk(int l, int j) {
-    if (l == 0) return j * KS;
-    if (j == 0) return 16;
-    const int i = j - 1, per = 2 / KS, c = i / per, r = i % per;
-    return chunk_order(c) * 2 + r * KS;
-}
-template <int KS, bool SKY> __host__ __device__ constexpr int stage_cnt(int l, int j) {
-    if (l == 0) { const int nk = Net<SKY>::K0 / 16; return (j * KS + KS <= nk) ? KS : nk - j * KS; }
-    return j == 0 ? 1 : KS;
-}
-// chunk barrier to wait on before stage j of a K=272 layer (-1: none)
-template <int KS> __host__ __device__ constexpr int stage_chunk_wait(int l, int j) {
-    if (l == 0 || j == 0) return -1;
-    const int i = j - 1, per = 2 / KS;
-    if (i % per != 0) return -1;
-    return chunk_order(i / per);
-}
-
-// Static schedule: the number of ring stages per sample step is padded to a multiple of the ring depth (4),
-// so the ring slot of every stage is a compile-time constant and its mbarrier parity depends only on the
-// step parity -- the issue loops become straight-line code with immediate addresses.
-template <int KS, bool SKY> __host__ __device__ constexpr int stage_index(int l, int j) {
-    int i = j;
-    for (int k = 0; k < l; k++) i += num_stages<KS, SKY>(k);
-    return i;
-}
-template <int KS, bool SKY> __host__ __device__ constexpr int stages_per_step() { return stage_index<KS, SKY>(Net<SKY>::NL, 0); }
-template <int KS, bool SKY> __host__ __device__ constexpr int stages_per_step_padded() { return (stages_per_step<KS, SKY>() + 3) / 4 * 4; }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-    return pred != 0;
-}
-
-// ---- shared memory map ---------------------------------------------------------------------------
-struct Smem {
-    uint32_t h_hi, h_lo, ring, fsec, scales, frac, sig, state, bars, tmem_slot, total;
-};
-__host__ __device__ constexpr Smem smem_map(bool x3) {
-    Smem m{};
-    uint32_t o = 0;
-    m.h_hi = o; o += kHBytes;
-    m.h_lo = o; if (x3) o += kHBytes;
-    m.ring = o; o += kRingBytes;
-    m.fsec = o; o += kFTotal * 4;
-    m.scales = o; o += kLevels * 4;
-    m.frac = o; o += ((kMaxS + 1) * 4 + 15) / 16 * 16;
-    m.sig = o; o += 2 * kRows * 4;
-    m.state = o; o += 2 * (2 * kMaxM + 6) * kRows * 4;
-    m.bars = o; o += 32 * 8;
-    m.tmem_slot = o; o += 16;
-    m.total = o;
-    return m;
-}
-// per-buffer ray state: float arrays of kRows each
-constexpr int kStAccu = 0;                   // [kMaxM]
-constexpr int kStHeads = kMaxM;              // [kMaxM]
-constexpr int kStTotal = 2 * kMaxM;          // 1
-constexpr int kStDir = 2 * kMaxM + 1;        // 3
-constexpr int kStLab = 2 * kMaxM + 4;        // 1 (uint32: 4 bits per slot)
-constexpr int kStFlags = 2 * kMaxM + 5;      // 1 (uint32: bit0 live, bit1 sky_mask, bit2 valid)
-constexpr int kStFloats = 2 * kMaxM + 6;
-
-// barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 8, B_OUTRDY, B_EPIDONE,
-       B_STRDY = B_EPIDONE + 2, B_STFREE = B_STRDY + 2, B_COUNT = B_STFREE + 2 };
-static_assert(B_COUNT <= 32, "barrier table");
-
-struct Params {
-    int n_img, H, W, M, S;
-    const int32_t *voxel_id;
-    const float *depth2, *raydirs, *cam_ori, *genc;
-    float vdim[3];
-    float sample_depth, dists_scale;
-    const float *fractions, *uniforms;
-    const int32_t *lut;
-    int n_lut;
-    const float *table;
-    int raw5d;
-    int log2_T;
-    float level_S;
-    int base_res;
-    const uint8_t *pack;
-    long long pack_stride;
-    const float *sky, *sky_avg;
-    float *net_out, *depth_out, *total_weight, *weights_out, *rdepth_out;
-    const int32_t *tile_list;      // [n_live] (render) / nullptr (sky: all tiles)
-    const int32_t *n_live;
-    int n_tiles;
-    int tiles_x, tiles_y;
-    // sky mode
-    float *sky_out;                // [R, 64]
-    float *sky_partial;            // [n_tiles, 64] per-tile column sums (deterministic mean)
-    int32_t *debug;                // optional host-mapped progress buffer (diagnostics), else nullptr
-};
-
-// progress markers (CTA 0 only): debug[role*4 + {0,1,2}] = {marker, step, layer/stage}
-#define SDB_MARK(role, marker, a, b)                                              \
-    do {                                                                          \
-        if (p.debug != nullptr && blockIdx.x == 0) {                              \
-            volatile int32_t *d__ = p.debug + (role) * 4;                         \
-            d__[0] = (marker); d__[1] = (int32_t)(a); d__[2] = (int32_t)(b);      \
-        }                                                                         \
-    } while (0)
-
-static int32_t *g_debug_buffer = nullptr;
-
-__device__ __constant__ uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u, kPrime3 = 3674653429u, kPrime4 = 2097192037u;
-
-struct TileCoord { int img, y0, x0; };
-__device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile) {
-    const int per_img = p.tiles_x * p.tiles_y;
-    TileCoord t;
-    t.img = tile / per_img;
-    const int r = tile - t.img * per_img;
-    t.y0 = (r / p.tiles_x) * kTileH;
-    t.x0 = (r % p.tiles_x) * kTileW;
-    return t;
-}
+int32_t *g_debug_buffer = nullptr;
 
 // ---- sampling (a2/a3) ------------------------------------------------------------------------------
 struct Sample { float depth, nd; int idx; };
@@ -244,12 +70,6 @@ __device__ __forceinline__ Sample sample_at(const Params &p, const float *st, in
 }
 
 // ---- gather (a5/a6) ----------------------------------------------------------------------------------
-__device__ __forceinline__ void ld8(const float *g, float (&v)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
-    const float4 b = __ldg(reinterpret_cast<const float4 *>(g) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
 template <bool RAW5D>
 __device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint32_t mask, float scale, const float (&x)[5],
                                              float (&res)[8]) {
@@ -336,15 +156,18 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
 template <int PREC> __device__ __forceinline__ uint32_t one16() { return PREC == 1 ? 0x3F80u : 0x3C00u; }   // 1.0
 
 // ---- the kernel ------------------------------------------------------------------------------------
-template <int PREC, bool RAW5D, bool SKY>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const Params p)
 {
+    constexpr bool SKY = MODE == kSky, BWD = MODE == kBwd;
+    static_assert(!TRAIN || (MODE == kRender && !RAW5D), "the training record is written by the table3 render forward only");
+    static_assert(!BWD || PREC == 1, "the gradient chain runs in the range-safe bf16x3 mode");
     constexpr bool X3 = PREC != 0;
     constexpr bool BF16 = PREC == 1;
     constexpr Smem SM = smem_map(X3);
     constexpr int PARTS = X3 ? 2 : 1;
-    constexpr int NH = Net<SKY>::NH, NL = Net<SKY>::NL;
+    constexpr int NH = Net<MODE>::NH, NL = Net<MODE>::NL;
     constexpr int KS = X3 ? 1 : 2;                           // k16 slabs per ring stage
     constexpr int kStageBytes = KS * kHidden * 32 * PARTS;   // 16 KB either way
     constexpr int kStages = kRingBytes / kStageBytes;        // 4
@@ -362,6 +185,7 @@ mlp_kernel(const Params p)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_work = SKY ? p.n_tiles : *p.n_live;
+    constexpr bool STATE = MODE == kRender;      // per-ray sampling state (gather -> epilogue hand-off) exists
     const int n_iter = (n_work > (int)blockIdx.x) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int S = SKY ? 1 : p.S;
 
@@ -380,7 +204,7 @@ mlp_kernel(const Params p)
         tc05::fence_mbar_init();
     }
     if (warp == kLoaderWarp) tc05::tmem_alloc(tmem_slot, kTmemCols);
-    if (!SKY) {
+    if (STATE) {
         for (int i = tid; i < kLevels; i += kThreads) sScale[i] = exp2f(i * p.level_S) * p.base_res - 1.0f;   // gridencoder.cu:126
         for (int i = tid; i <= p.S; i += kThreads) sFrac[i] = p.fractions[i];
     }
@@ -413,7 +237,7 @@ mlp_kernel(const Params p)
             if (!SKY && loaded_img != tc.img) {
                 // sigma head of this image's pack -> shared memory (epilogue threads are the only readers)
                 const float *packF = reinterpret_cast<const float *>(p.pack + (long long)tc.img * p.pack_stride +
-                                                                     layerOff<SKY>(NL, PARTS));
+                                                                     layerOff<MODE>(NL, PARTS));
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int i = tid; i < kFTotal; i += kEpiThreads) sF[i] = __ldg(packF + i);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -424,7 +248,7 @@ mlp_kernel(const Params p)
             const long long ray = ((long long)tc.img * p.H + y) * p.W + x;
             uint32_t flags = in_img ? 4u : 0u, labs = 0;
             float dir0 = 0.0f, ori0 = 0.0f;
-            if (!SKY) {
+            if (STATE) {
                 tc05::mbar_wait(&bars[B_STRDY + buf], (it >> 1) & 1);
                 flags = __float_as_uint(st[kStFlags * kRows + row]);
                 labs = __float_as_uint(st[kStLab * kRows + row]);
@@ -441,15 +265,26 @@ mlp_kernel(const Params p)
 
             for (int s = 0; s < S; s++, n++) {
                 Sample sm{0.0f, 0.0f, 0};
-                if (!SKY) {
+                if (STATE) {
                     sm = sample_at(p, st, row, s, sFrac, ray);
                     is_gnd = is_gnd || (__fadd_rn(__fmul_rn(dir0, sm.depth), ori0) <= 1.0f);   // scenedreamer.py:354,380
                 }
                 float sig_part = 0.0f;
+                // training record addressing: step = (work item, sample), slot = (step, tile row)
+                const long long step_id = (long long)work * S + s;
+                const long long slot = step_id * kRows + row;
+                float dsig = 0.0f;
+                if constexpr (BWD) dsig = __ldg(p.tr.dsig + slot);
+                (void)slot; (void)dsig;
 #pragma unroll 1
                 for (int l = 0; l < NH; l++) {
                     const uint32_t g = n * NL + l;                   // global layer counter -> accumulator buffer
                     const uint32_t acc = tm_row + (g & 1u) * 256u + half * 128u;
+                    // kBwd: LeakyReLU sign words of the forward activation A_{6-l} this layer's data gradient passes
+                    // through (prefetched before the accumulator wait)
+                    uint4 mw = make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (BWD)
+                        mw = __ldg(reinterpret_cast<const uint4 *>(p.tr.mask + ((step_id * kNumAct + (NH - 1 - l)) * kRows + row) * 8 + half * 4));
                     if ((tid & 127) == 0) SDB_MARK(half, 1, n, l);
                     tc05::mbar_wait(&bars[B_ACC], (n * NH + l) & 1);
                     tc05::fence_after_thread_sync();
@@ -459,12 +294,42 @@ mlp_kernel(const Params p)
                         float v[32];
                         tc05::tmem_ld32(acc + c0, v);
                         tc05::tmem_ld_wait();
+                        if constexpr (BWD) {
+                            if (l == 2) {   // dA4 += dsigma * fc_sigma.weight (sigma taps A4, layers.py:115)
+                                const float *ws = sF + kFWsig + half * 128 + c0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.2f * v[j]);          // LeakyReLU(0.2)
-                        if (!SKY && l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
-                            const float *ws = sF + kFWsig + half * 128 + c0;
+                                for (int j = 0; j < 32; j++) v[j] = fmaf(dsig, ws[j], v[j]);
+                            }
+                            // dZ = dA * LeakyReLU'(z): slope 1 where the forward activation was > 0, else 0.2
+                            const uint32_t word = c0 == 0 ? mw.x : (c0 == 32 ? mw.y : (c0 == 64 ? mw.z : mw.w));
 #pragma unroll
-                            for (int j = 0; j < 32; j++) sig_part = fmaf(v[j], ws[j], sig_part);
+                            for (int j = 0; j < 32; j++) v[j] = ((word >> j) & 1u) ? v[j] : 0.2f * v[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.2f * v[j]);          // LeakyReLU(0.2)
+                            if (MODE == kRender && l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
+                                const float *ws = sF + kFWsig + half * 128 + c0;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) sig_part = fmaf(v[j], ws[j], sig_part);
+                            }
+                        }
+                        if constexpr (TRAIN || BWD) {
+                            // bf16 (round-to-nearest) copy of the chunk for the weight-gradient GEMMs:
+                            // forward: A_{l+1}[slot][128*half + c0 ..], backward: dZ_{6-l}[slot][...]
+                            uint16_t *dst = TRAIN
+                                ? p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + half * 128 + c0
+                                : p.tr.dz + ((long long)(NH - 1 - l) * p.tr.slot_cap + slot) * kHidden + half * 128 + c0;
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                reinterpret_cast<uint4 *>(dst)[q] =
+                                    make_uint4(tc05::pack2<true>(v[8 * q], v[8 * q + 1]), tc05::pack2<true>(v[8 * q + 2], v[8 * q + 3]),
+                                               tc05::pack2<true>(v[8 * q + 4], v[8 * q + 5]), tc05::pack2<true>(v[8 * q + 6], v[8 * q + 7]));
+                        }
+                        if constexpr (TRAIN) {
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) word |= (v[j] > 0.0f ? 1u : 0u) << j;
+                            p.tr.mask[((step_id * kNumAct + l) * kRows + row) * 8 + half * 4 + (c0 >> 5)] = word;
                         }
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
@@ -482,7 +347,12 @@ mlp_kernel(const Params p)
                     }
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (g & 1u)]);        // accumulator buffer (g & 1) is free again
-                    if (!SKY && l == 3) sSig[half * kRows + row] = sig_part;
+                    if (MODE == kRender && l == 3) sSig[half * kRows + row] = sig_part;
+                    if constexpr (TRAIN) {   // the constant-1 column that turns the weight-gradient GEMM's column 256 into the bias gradient
+                        if (half == 0)
+                            *reinterpret_cast<uint4 *>(p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + kHidden) =
+                                make_uint4(0x3F80u, 0u, 0u, 0u);
+                    }
                 }
                 // ---- colour layer ----
                 const uint32_t go = n * NL + NH;
@@ -491,7 +361,21 @@ mlp_kernel(const Params p)
                 if ((tid & 127) == 0) SDB_MARK(half, 4, n, NH);
                 tc05::fence_after_thread_sync();
                 float c[32];
-                tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * 32u, c);
+                tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * (BWD ? 64u : 32u), c);
+                if constexpr (BWD) {
+                    // d(hash-grid features) [128 rays x 128]: this half owns 64 columns -> fp32 record for the table backward
+                    float c2[32];
+                    tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * 64u + 32u, c2);
+                    tc05::tmem_ld_wait();
+                    tc05::fence_before_thread_sync();
+                    tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
+                    float4 *dst = reinterpret_cast<float4 *>(p.tr.dx0 + slot * kFeat + half * 64);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) dst[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) dst[8 + q] = make_float4(c2[4 * q], c2[4 * q + 1], c2[4 * q + 2], c2[4 * q + 3]);
+                    continue;
+                }
                 tc05::tmem_ld_wait();
                 tc05::fence_before_thread_sync();
                 tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
@@ -510,6 +394,12 @@ mlp_kernel(const Params p)
                     w = live ? w : 0.0f;                                                              // scenedreamer.py:376
                     Wsum += w;
                     Dsum = fmaf(w, sm.depth, Dsum);
+                    if constexpr (TRAIN) {   // what the compositing backward needs: sigma, scaled interval, colour head output
+                        if (half == 0) { p.tr.sig[slot] = sigma; p.tr.nds[slot] = __fmul_rn(sm.nd, p.dists_scale); }
+                        float4 *cd = reinterpret_cast<float4 *>(p.tr.c + slot * kOutC + half * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) cd[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                    }
                     if (half == 0 && valid) {
                         if (p.weights_out) p.weights_out[ray * S + s] = w;
                         if (p.rdepth_out) p.rdepth_out[ray * S + s] = sm.depth;
@@ -541,11 +431,14 @@ mlp_kernel(const Params p)
                 if (tid < kOutC)
                     p.sky_partial[(long long)tile * kOutC + tid] =
                         (red[tid] + red[kOutC + tid]) + (red[2 * kOutC + tid] + red[3 * kOutC + tid]);
-            } else {
+            } else if constexpr (!BWD) {
                 // ---- finalize the tile (sky blend, scenedreamer.py:380-413) ----
+                const bool sky_mask = flags & 2u;
+                const bool nosky = (!sky_mask) || is_gnd;
+                if constexpr (TRAIN) {
+                    if (half == 0) p.tr.rayflags[(long long)work * kRows + row] = (live ? 1u : 0u) | (nosky ? 2u : 0u) | (valid ? 4u : 0u);
+                }
                 if (valid) {
-                    const bool sky_mask = flags & 2u;
-                    const bool nosky = (!sky_mask) || is_gnd;
                     const float sky_w = 1.0f - Wsum;
                     const float4 *skp = reinterpret_cast<const float4 *>((nosky ? p.sky_avg + (long long)tc.img * kOutC
                                                                                  : p.sky + ray * kOutC) + half * 32);
@@ -570,8 +463,8 @@ mlp_kernel(const Params p)
         }
     } else if (warp < kGatherWarp0) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
-      constexpr int NSP = stages_per_step_padded<KS, SKY>();      // ring stages per sample step (multiple of 4)
-      constexpr int NS = stages_per_step<KS, SKY>();
+      constexpr int NSP = stages_per_step_padded<KS, MODE>();      // ring stages per sample step (multiple of 4)
+      constexpr int NS = stages_per_step<KS, MODE>();
       constexpr uint32_t kStepFlip = (NSP / 4) & 1;                 // does the stage parity pattern flip every step?
       static_assert(kStages == 4, "static schedule assumes a 4-deep ring");
       if (warp == kLoaderWarp) {
@@ -587,16 +480,16 @@ mlp_kernel(const Params p)
                     const uint32_t flip = kStepFlip & n;
 #pragma unroll
                     for (int l = 0; l < NL; l++) {
-                        const uint32_t slabB = (uint32_t)layerN<SKY>(l) * 32 * PARTS;      // one k16 slab (hi [+ lo])
-                        const uint8_t *src = pack + layerOff<SKY>(l, PARTS);
+                        const uint32_t slabB = (uint32_t)layerN<MODE>(l) * 32 * PARTS;      // one k16 slab (hi [+ lo])
+                        const uint8_t *src = pack + layerOff<MODE>(l, PARTS);
 #pragma unroll
-                        for (int j = 0; j < num_stages<KS, SKY>(l); j++) {
-                            const int i = stage_index<KS, SKY>(l, j);
+                        for (int j = 0; j < num_stages<KS, MODE>(l); j++) {
+                            const int i = stage_index<KS, MODE>(l, j);
                             const uint32_t stg = i & 3, par = ((i >> 2) & 1) ^ flip;
-                            const uint32_t bytes = slabB * stage_cnt<KS, SKY>(l, j);
+                            const uint32_t bytes = slabB * stage_cnt<KS, MODE>(l, j);
                             tc05::mbar_wait_backoff(&bars[B_WEMPTY + stg], par ^ 1, 32);
                             tc05::mbar_arrive_expect_tx(&bars[B_WFULL + stg], bytes);
-                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)stage_kk<KS, SKY>(l, j) * slabB, bytes,
+                            tc05::bulk_g2s(sRing + stg * kStageBytes, src + (size_t)stage_kk<KS, MODE>(l, j) * slabB, bytes,
                                            &bars[B_WFULL + stg]);
                         }
                     }
@@ -623,6 +516,7 @@ mlp_kernel(const Params p)
         const uint64_t dA0l = tc05::make_smem_desc(tc05::smem_u32(sHlo), kLboA, kSbo);
         const uint64_t dB0_256 = tc05::make_smem_desc(tc05::smem_u32(sRing), 256 * 16, kSbo);
         const uint64_t dB0_64 = tc05::make_smem_desc(tc05::smem_u32(sRing), kOutC * 16, kSbo);
+        const uint64_t dB0_128 = tc05::make_smem_desc(tc05::smem_u32(sRing), kFeat * 16, kSbo);
         for (int it = 0; it < n_iter; it++) {
             for (int s = 0; s < S; s++, n++) {
                 const uint32_t flip = kStepFlip & n;
@@ -638,21 +532,21 @@ mlp_kernel(const Params p)
                     if (lane == 0) SDB_MARK(2, 1, n, l);
                     if (g >= 2) tc05::mbar_wait(&bars[B_EPIDONE + buf], ((g >> 1) - 1) & 1);
                     if (l == 0) tc05::mbar_wait(&bars[B_FEAT], nodd);
-                    const int N = layerN<SKY>(l);                                  // compile-time after unrolling
+                    const int N = layerN<MODE>(l);                                  // compile-time after unrolling
                     const uint32_t idesc = tc05::make_idesc(kRows, N, BF16);
                     const uint32_t slab16 = (uint32_t)(N * 32) >> 4;              // one part of one k16 slab, in 16-byte units
                     const uint32_t dcol = tmem + buf * 256u;
-                    const uint64_t dB0 = (N == kOutC) ? dB0_64 : dB0_256;
+                    const uint64_t dB0 = (N == kOutC) ? dB0_64 : (N == kFeat ? dB0_128 : dB0_256);
                     const uint32_t cpar = (NH & 1) ? (((l - 1) & 1) ^ nodd) : ((l - 1) & 1);   // (n*NH + l-1) & 1
                     constexpr int kPair = 2;
 #pragma unroll
-                    for (int j0 = 0; j0 < num_stages<KS, SKY>(l); j0 += kPair) {
+                    for (int j0 = 0; j0 < num_stages<KS, MODE>(l); j0 += kPair) {
 #pragma unroll
                         for (int u = 0; u < kPair; u++) {
                             const int j = j0 + u;
-                            if (j < num_stages<KS, SKY>(l)) {
-                                const int i = stage_index<KS, SKY>(l, j);
-                                const int chunk = stage_chunk_wait<KS>(l, j);
+                            if (j < num_stages<KS, MODE>(l)) {
+                                const int i = stage_index<KS, MODE>(l, j);
+                                const int chunk = stage_chunk_wait<KS, MODE>(l, j);
                                 if (chunk >= 0) tc05::mbar_wait(&bars[B_CHUNK + chunk], cpar);   // operand chunk from the previous epilogue
                                 tc05::mbar_wait(&bars[B_WFULL + (i & 3)], ((i >> 2) & 1) ^ flip);
                             }
@@ -662,25 +556,25 @@ mlp_kernel(const Params p)
 #pragma unroll
                             for (int u = 0; u < kPair; u++) {
                                 const int j = j0 + u;
-                                if (j < num_stages<KS, SKY>(l)) {
-                                    const int i = stage_index<KS, SKY>(l, j);
+                                if (j < num_stages<KS, MODE>(l)) {
+                                    const int i = stage_index<KS, MODE>(l, j);
                                     const uint32_t stg = i & 3;
                                     const uint64_t dBs = dB0 + (uint64_t)(stg * (kStageBytes >> 4));
 #pragma unroll
-                                    for (int t = 0; t < stage_cnt<KS, SKY>(l, j); t++) {
-                                        const int kk = stage_kk<KS, SKY>(l, j) + t;
+                                    for (int t = 0; t < stage_cnt<KS, MODE>(l, j); t++) {
+                                        const int kk = stage_kk<KS, MODE>(l, j) + t;
                                         const uint64_t dAh = dA0h + (uint64_t)(kk * (2 * kLboA >> 4));
                                         const uint64_t dBh = dBs + (uint64_t)(t * slab16 * PARTS);
                                         const bool first = (j == 0 && t == 0);
                                         tc05::mma_f16_ss(dcol, dAh, dBh, idesc, first ? 0u : 1u);
                                         if constexpr (X3) {
-                                            const bool ext = (l > 0 && j == 0);      // A_lo of the constant extension columns is 0
+                                            const bool ext = (Net<MODE>::EXT && l > 0 && j == 0);   // A_lo of the constant extension columns is 0
                                             if (!ext) tc05::mma_f16_ss(dcol, dA0l + (uint64_t)(kk * (2 * kLboA >> 4)), dBh, idesc, 1u);
                                             tc05::mma_f16_ss(dcol, dAh, dBh + slab16, idesc, 1u);
                                         }
                                     }
                                     tc05::mma_commit(&bars[B_WEMPTY + stg]);
-                                    if (j == num_stages<KS, SKY>(l) - 1) {
+                                    if (j == num_stages<KS, MODE>(l) - 1) {
                                         if (l == NL - 1) {
                                             tc05::mma_commit(&bars[B_OUTRDY]);
                                             tc05::mma_commit(&bars[B_HFREE]);
@@ -759,6 +653,30 @@ mlp_kernel(const Params p)
                 tc05::fence_proxy_async_smem();
                 tc05::mbar_arrive(&bars[B_FEAT]);
                 n++;
+            } else if constexpr (BWD) {
+                // ---- layer-0 operand of the gradient chain: dL/dc [128 rays x 64] fp32 from the compositing backward ----
+                (void)valid; (void)ray;
+                for (int s = 0; s < S; s++, n++) {
+                    const long long slot = ((long long)work * S + s) * kRows + row;
+                    const float4 *src = reinterpret_cast<const float4 *>(p.tr.dc + slot * kOutC + half * 32);
+                    uint4 gh[4], gl[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float4 a = __ldg(src + 2 * q), b = __ldg(src + 2 * q + 1);
+                        const float v8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        split8<PREC>(v8, gh[q], gl[q]);
+                    }
+                    if (gt == 0) SDB_MARK(4, 3, n, it);
+                    if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t off = tc05::chunk_off(kRows, row, half * 4 + q);
+                        *reinterpret_cast<uint4 *>(sHhi + off) = gh[q];
+                        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = gl[q];
+                    }
+                    tc05::fence_proxy_async_smem();
+                    tc05::mbar_arrive(&bars[B_FEAT]);
+                }
             } else {
                 const int buf = it & 1;
                 float *st = sState + buf * kStFloats * kRows;
@@ -840,6 +758,16 @@ mlp_kernel(const Params p)
                             encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
                         }
                         split8<PREC>(res, fh[i], fl[i]);
+                        if constexpr (TRAIN) {   // bf16 copy of the features: X0[slot][8*level ..] (operand of the fc_1 weight gradient)
+                            const long long slot = ((long long)work * S + s) * kRows + row;
+                            *reinterpret_cast<uint4 *>(p.tr.x0 + slot * kX0Cols + level * 8) =
+                                make_uint4(tc05::pack2<true>(res[0], res[1]), tc05::pack2<true>(res[2], res[3]),
+                                           tc05::pack2<true>(res[4], res[5]), tc05::pack2<true>(res[6], res[7]));
+                        }
+                    }
+                    if constexpr (TRAIN) {
+                        const long long slot = ((long long)work * S + s) * kRows + row;
+                        if (half == 0) p.tr.x3[slot] = make_float4(x5[0], x5[1], x5[2], oob ? -1.0f : 1.0f);
                     }
                     // K-extension of layer 0: one-hot label (columns 128..142) and the constant-1 bias column 143
                     // == the reference's fc_m_a(onehot) product and fc_1's bias (layers.py:102-105)
@@ -849,6 +777,14 @@ mlp_kernel(const Params p)
                         const int k = (int)label - 8 * half;                     // position inside this thread's 8-wide chunk
                         if (k >= 0 && k < 8) oh[k >> 1] = one16<PREC>() << (16 * (k & 1));
                         if (half == 1) oh[3] |= one16<PREC>() << 16;             // column 143
+                    }
+                    if constexpr (TRAIN) {   // X0 columns 128..143: one-hot label and the constant 1 (bf16)
+                        const long long slot = ((long long)work * S + s) * kRows + row;
+                        uint32_t ob[4] = {0u, 0u, 0u, 0u};
+                        const int k = (int)label - 8 * half;
+                        if (k >= 0 && k < 8) ob[k >> 1] = 0x3F80u << (16 * (k & 1));
+                        if (half == 1) ob[3] |= 0x3F80u << 16;
+                        *reinterpret_cast<uint4 *>(p.tr.x0 + slot * kX0Cols + kFeat + 8 * half) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
                     }
                     if (gt == 0) SDB_MARK(4, 3, n, it);
                     if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
@@ -887,9 +823,14 @@ prepass_kernel(const Params p, int32_t *tile_list, int32_t *n_live)
     const bool live = valid && (__ldg(p.voxel_id + ray * p.M) != 0);
     const int any = __syncthreads_or(live ? 1 : 0);
     if (any) {
-        if (row == 0) tile_list[atomicAdd(n_live, 1)] = tile;
+        if (row == 0) {
+            const int w = atomicAdd(n_live, 1);
+            tile_list[w] = tile;
+            if (p.tr.tile_work) p.tr.tile_work[tile] = w;
+        }
         return;
     }
+    if (row == 0 && p.tr.tile_work) p.tr.tile_work[tile] = -1;
     if (!valid) return;
     // sky-only ray: weights are zero, all samples sit at the camera origin (scenedreamer.py:350-354,376)
     const bool is_gnd = __ldg(p.cam_ori + tc.img * 3) <= 1.0f;
@@ -970,17 +911,18 @@ __global__ void __launch_bounds__(256)
 pack_kernel(const float *w0, const float *b0, const float *emb, int n_labels, const float *wh, const float *bh,
             const float *wsig, const float *bsig, const float *wout, const float *bout, uint8_t *pack)
 {
+    constexpr int MODE = SKY ? kSky : kRender;
     constexpr bool X3 = PREC != 0;
     constexpr int PARTS = X3 ? 2 : 1;
-    constexpr int NL = Net<SKY>::NL;
+    constexpr int NL = Net<MODE>::NL;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long nW = 0;
-    for (int l = 0; l < NL; l++) nW += (long long)layerK<SKY>(l) * layerN<SKY>(l);
+    for (int l = 0; l < NL; l++) nW += (long long)layerK<MODE>(l) * layerN<MODE>(l);
     if (t < nW) {
         long long r = t;
         int l = 0;
-        while (r >= (long long)layerK<SKY>(l) * layerN<SKY>(l)) { r -= (long long)layerK<SKY>(l) * layerN<SKY>(l); l++; }
-        const int K = layerK<SKY>(l), N = layerN<SKY>(l);
+        while (r >= (long long)layerK<MODE>(l) * layerN<MODE>(l)) { r -= (long long)layerK<MODE>(l) * layerN<MODE>(l); l++; }
+        const int K = layerK<MODE>(l), N = layerN<MODE>(l);
         const int nn = (int)(r / K), k = (int)(r % K);
         float v = 0.0f;
         if (l == 0) {
@@ -1001,7 +943,7 @@ pack_kernel(const float *w0, const float *b0, const float *emb, int n_labels, co
         }
         const int kk = k >> 4, k16 = k & 15;
         const long long slab_off = (long long)(k16 >> 3) * N * 16 + (nn >> 3) * 128 + (nn & 7) * 16 + (k16 & 7) * 2;
-        uint8_t *base = pack + layerOff<SKY>(l, PARTS) + (long long)kk * N * 32 * PARTS;
+        uint8_t *base = pack + layerOff<MODE>(l, PARTS) + (long long)kk * N * 32 * PARTS;
         if constexpr (PREC == 1) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -1020,7 +962,7 @@ pack_kernel(const float *w0, const float *b0, const float *emb, int n_labels, co
     if (SKY) return;
     const long long u = t - nW;
     if (u >= kFTotal) return;
-    float *F = reinterpret_cast<float *>(pack + layerOff<SKY>(NL, PARTS));
+    float *F = reinterpret_cast<float *>(pack + layerOff<MODE>(NL, PARTS));
     float v = 0.0f;
     if (u < kHidden) v = wsig[u];
     else if (u == kFBsig) v = bsig[0];
@@ -1031,8 +973,9 @@ template <bool SKY>
 int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels, const float *wh, const float *bh,
                 const float *wsig, const float *bsig, const float *wout, const float *bout, int precision, void *pack,
                 cudaStream_t st) {
+    constexpr int MODE = SKY ? kSky : kRender;
     long long n = SKY ? 0 : kFTotal;
-    for (int l = 0; l < Net<SKY>::NL; l++) n += (long long)layerK<SKY>(l) * layerN<SKY>(l);
+    for (int l = 0; l < Net<MODE>::NL; l++) n += (long long)layerK<MODE>(l) * layerN<MODE>(l);
     const int blocks = (int)((n + 255) / 256);
     if (precision == 1)
         pack_kernel<1, SKY><<<blocks, 256, 0, st>>>(w0, b0, emb, n_labels, wh, bh, wsig, bsig, wout, bout, (uint8_t *)pack);
@@ -1044,16 +987,60 @@ int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels
     return SDB_OK;
 }
 
-template <int PREC, bool RAW5D, bool SKY>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN = false>
 int launch_mlp(const Params &p, int grid, cudaStream_t st) {
     const size_t smem = smem_map(PREC != 0).total;
     cudaFuncAttributes fa;
-    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, SKY>));
+    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN>));
     if (fa.numRegs < kRegsLaunch) return SDB_EUNSUPPORTED;   // setmaxnreg pool would be too small: refuse rather than hang
-    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, SKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_kernel<PREC, RAW5D, SKY><<<grid, kThreads, smem, st>>>(p);
+    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_kernel<PREC, RAW5D, MODE, TRAIN><<<grid, kThreads, smem, st>>>(p);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
+}
+
+int launch_train_forward(const Params &p, int grid, cudaStream_t st) { return launch_mlp<2, false, kRender, true>(p, grid, st); }
+int launch_bwd_chain(const Params &p, int grid, cudaStream_t st) { return launch_mlp<1, false, kBwd>(p, grid, st); }
+int launch_prepass(const Params &p, int32_t *ws, cudaStream_t st) {
+    SDB_CUDA(cudaMemsetAsync(ws, 0, 16, st));
+    prepass_kernel<<<p.n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}
+
+// ---- weight packer of the gradient chain (kBwd): B operands are the transposed forward weights -------
+//   layer 0 [256 x 64]: B[n][k] = fc_out_c.weight[k][n];  layers 1..5 [256 x 256]: B[n][k] = W'_{fc_(7-l)}[k][n]
+//   (wh[5-l], the style-modulated weight);  layer 6 [128 x 256]: B[n][k] = fc_1.weight[k][n];  fp32 tail: fc_sigma.weight
+__global__ void __launch_bounds__(256)
+pack_bwd_kernel(const float *w1, const float *wh, const float *wsig, const float *wout, uint8_t *pack)
+{
+    constexpr int MODE = kBwd, PARTS = 2, NL = Net<MODE>::NL;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long nW = 0;
+    for (int l = 0; l < NL; l++) nW += (long long)layerK<MODE>(l) * layerN<MODE>(l);
+    if (t < nW) {
+        long long r = t;
+        int l = 0;
+        while (r >= (long long)layerK<MODE>(l) * layerN<MODE>(l)) { r -= (long long)layerK<MODE>(l) * layerN<MODE>(l); l++; }
+        const int K = layerK<MODE>(l), N = layerN<MODE>(l);
+        const int nn = (int)(r / K), k = (int)(r % K);
+        float v;
+        if (l == 0) v = wout[(long long)k * kHidden + nn];
+        else if (l == NL - 1) v = w1[(long long)k * kFeat + nn];
+        else v = wh[((long long)(5 - l) * kHidden + k) * kHidden + nn];
+        const int kk = k >> 4, k16 = k & 15;
+        const long long slab_off = (long long)(k16 >> 3) * N * 16 + (nn >> 3) * 128 + (nn & 7) * 16 + (k16 & 7) * 2;
+        uint8_t *base = pack + layerOff<MODE>(l, PARTS) + (long long)kk * N * 32 * PARTS;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16 *>(base + slab_off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + (long long)N * 32 + slab_off) = lo;
+        return;
+    }
+    const long long u = t - nW;
+    if (u >= kFTotal) return;
+    float *F = reinterpret_cast<float *>(pack + layerOff<MODE>(NL, PARTS));
+    F[u] = u < kHidden ? wsig[u] : 0.0f;
 }
 
 }  // namespace rf
@@ -1061,8 +1048,8 @@ int launch_mlp(const Params &p, int grid, cudaStream_t st) {
 // Diagnostics: a host-mapped (pinned) int32[64] buffer that CTA 0 fills with progress markers.
 extern "C" void sdb_debug_set_progress_buffer(void *mapped) { rf::g_debug_buffer = (int32_t *)mapped; }
 
-extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes<false>(precision != 0 ? 2 : 1); }
-extern "C" int64_t sdb_sky_pack_bytes(int32_t precision) { return rf::packBytes<true>(precision != 0 ? 2 : 1); }
+extern "C" int64_t sdb_mlp_pack_bytes(int32_t precision) { return rf::packBytes<rf::kRender>(precision != 0 ? 2 : 1); }
+extern "C" int64_t sdb_sky_pack_bytes(int32_t precision) { return rf::packBytes<rf::kSky>(precision != 0 ? 2 : 1); }
 
 extern "C" int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d_emb, int32_t n_labels,
                             const float *d_wh, const float *d_bh, const float *d_wsig, const float *d_bsig,
@@ -1072,6 +1059,20 @@ extern "C" int sdb_pack_mlp(const float *d_w1, const float *d_b1, const float *d
     if (n_labels < 1 || n_labels > rf::kMaxLabels || precision < 0 || precision > 2) return SDB_EINVAL;
     return rf::launch_pack<false>(d_w1, d_b1, d_emb, n_labels, d_wh, d_bh, d_wsig, d_bsig, d_wout, d_bout, precision, d_pack,
                                   (cudaStream_t)stream);
+}
+
+extern "C" int64_t sdb_mlp_backward_pack_bytes(void) { return rf::packBytes<rf::kBwd>(2); }
+
+extern "C" int sdb_pack_mlp_backward(const float *d_w1, const float *d_wh, const float *d_wsig, const float *d_wout,
+                                     void *d_pack, void *stream)
+{
+    using namespace rf;
+    if (!d_w1 || !d_wh || !d_wsig || !d_wout || !d_pack) return SDB_EINVAL;
+    long long n = kFTotal;
+    for (int l = 0; l < Net<kBwd>::NL; l++) n += (long long)layerK<kBwd>(l) * layerN<kBwd>(l);
+    pack_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_w1, d_wh, d_wsig, d_wout, (uint8_t *)d_pack);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
 }
 
 extern "C" int sdb_pack_sky_mlp(const float *d_w1, const float *d_b1, const float *d_wh, const float *d_bh,
@@ -1127,18 +1128,19 @@ extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H,
     p.n_tiles = n_img * p.tiles_x * p.tiles_y;
     const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
     int rc;
-    if (precision == 1) rc = launch_mlp<1, false, true>(p, grid, st);
-    else if (precision == 2) rc = launch_mlp<2, false, true>(p, grid, st);
-    else rc = launch_mlp<0, false, true>(p, grid, st);
+    if (precision == 1) rc = launch_mlp<1, false, kSky>(p, grid, st);
+    else if (precision == 2) rc = launch_mlp<2, false, kSky>(p, grid, st);
+    else rc = launch_mlp<0, false, kSky>(p, grid, st);
     if (rc != SDB_OK) return rc;
     sky_mean_kernel<<<n_img, kOutC, 0, st>>>(p.sky_partial, d_sky_avg, p.tiles_x * p.tiles_y, 1.0f / ((float)H * (float)W));
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
 
-extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream)
+namespace rf {
+// validate the ABI struct and translate it into kernel parameters (tile list / outputs still unset)
+int params_from_abi(const sdb_render_params *sp, Params &p)
 {
-    using namespace rf;
     if (!sp) return SDB_EINVAL;
     if (!sp->d_voxel_id || !sp->d_depth2 || !sp->d_raydirs || !sp->d_cam_ori || !sp->d_global_enc || !sp->d_fractions ||
         !sp->d_label_lut || !sp->d_mlp_pack || !sp->d_sky || !sp->d_sky_avg || !sp->d_net_out || !sp->d_workspace)
@@ -1148,8 +1150,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     if (sp->M < 1 || sp->M > kMaxM || sp->S < 1 || sp->S > kMaxS || sp->L != kLevels || sp->log2_T < 4 || sp->log2_T > 24 ||
         sp->precision < 0 || sp->precision > 2 || sp->n_lut < 1)
         return SDB_EUNSUPPORTED;
-    cudaStream_t st = (cudaStream_t)stream;
-    Params p{};
+    p = Params{};
     p.n_img = sp->n_img; p.H = sp->H; p.W = sp->W; p.M = sp->M; p.S = sp->S;
     p.voxel_id = sp->d_voxel_id; p.depth2 = sp->d_depth2; p.raydirs = sp->d_raydirs; p.cam_ori = sp->d_cam_ori;
     p.genc = sp->d_global_enc;
@@ -1167,18 +1168,32 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     p.debug = g_debug_buffer;
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
     p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
+    return SDB_OK;
+}
+}  // namespace rf
+
+extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream)
+{
+    using namespace rf;
+    cudaStream_t st = (cudaStream_t)stream;
+    Params p;
+    {
+        const int rc = params_from_abi(sp, p);
+        if (rc != SDB_OK) return rc;
+    }
     int32_t *ws = (int32_t *)sp->d_workspace;
     p.n_live = ws; p.tile_list = ws + 4;
-    SDB_CUDA(cudaMemsetAsync(ws, 0, 16, st));
-    prepass_kernel<<<p.n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
-    SDB_CHECK_LAUNCH();
+    {
+        const int rc = launch_prepass(p, ws, st);
+        if (rc != SDB_OK) return rc;
+    }
     const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
     switch (sp->precision * 2 + (p.raw5d ? 1 : 0)) {
-        case 0: return launch_mlp<0, false, false>(p, grid, st);
-        case 1: return launch_mlp<0, true, false>(p, grid, st);
-        case 2: return launch_mlp<1, false, false>(p, grid, st);
-        case 3: return launch_mlp<1, true, false>(p, grid, st);
-        case 4: return launch_mlp<2, false, false>(p, grid, st);
-        default: return launch_mlp<2, true, false>(p, grid, st);
+        case 0: return launch_mlp<0, false, kRender>(p, grid, st);
+        case 1: return launch_mlp<0, true, kRender>(p, grid, st);
+        case 2: return launch_mlp<1, false, kRender>(p, grid, st);
+        case 3: return launch_mlp<1, true, kRender>(p, grid, st);
+        case 4: return launch_mlp<2, false, kRender>(p, grid, st);
+        default: return launch_mlp<2, true, kRender>(p, grid, st);
     }
 }

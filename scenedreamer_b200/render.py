@@ -286,3 +286,165 @@ class FusedPerPixelRenderer:
                                   base_res=self.base_res, log2_T=self.log2_T, L=self.L, want_samples=want_samples, **kw)
         out['sky'], out['sky_avg'] = sky, sky_avg
         return out
+
+
+# ================================================================================================
+# Training: fused forward that records the pass + the fused backward (sdb_render_rays_backward)
+# ================================================================================================
+class _RenderGrads(ctypes.Structure):
+    _fields_ = [
+        ('d_grad_net_out', ctypes.c_void_p), ('d_bwd_pack', ctypes.c_void_p), ('bwd_pack_stride', ctypes.c_int64),
+        ('d_table', ctypes.c_void_p),
+        ('d_grad_table', ctypes.c_void_p), ('d_grad_global_enc', ctypes.c_void_p), ('d_grad_w1ext', ctypes.c_void_p),
+        ('d_grad_wh', ctypes.c_void_p), ('d_grad_wsig', ctypes.c_void_p), ('d_grad_wout', ctypes.c_void_p),
+        ('d_grad_sky', ctypes.c_void_p), ('d_grad_sky_avg', ctypes.c_void_p), ('d_workspace', ctypes.c_void_p),
+    ]
+
+
+def _fill_render_params(prm, keep, voxel_id, depth2, raydirs, cam_ori, genc, voxel_dims, lut, mlp_pack, sky, sky_avg, table3,
+                        S, sample_depth, dists_scale, uniforms, precision, per_level_scale, base_res, log2_T, L, net_out,
+                        depth, tw, wts, rdp, ws):
+    """Fills an sdb_render_params for the pre-blended-table path; `keep` collects tensors that must outlive the call."""
+    dev = voxel_id.device
+    N, H, W, M = voxel_id.shape[:4]
+    if uniforms is None:
+        frac = deterministic_fractions(S, dev)
+    else:
+        frac = stratified_offsets(S, dev)
+        uniforms = uniforms.to(dev, torch.float32).reshape(N * H * W, S + 1).contiguous()
+    keep += [frac, uniforms]
+    prm.n_img, prm.H, prm.W, prm.M, prm.S = N, H, W, M, S
+    prm.d_voxel_id, prm.d_depth2, prm.d_raydirs = _ptr(voxel_id), _ptr(depth2), _ptr(raydirs)
+    prm.d_cam_ori = _ptr(cam_ori)
+    prm.voxel_dims = (ctypes.c_float * 3)(*[float(v) for v in voxel_dims])
+    prm.d_global_enc = _ptr(genc)
+    prm.sample_depth, prm.dists_scale = float(sample_depth), float(dists_scale)
+    prm.d_fractions, prm.d_uniforms = _ptr(frac), _ptr(uniforms)
+    prm.d_label_lut, prm.n_lut = _ptr(lut), int(lut.numel())
+    prm.d_table, prm.d_table3 = None, _ptr(table3)
+    prm.L, prm.log2_T, prm.level_S, prm.base_res = int(L), int(log2_T), float(np.log2(per_level_scale)), int(base_res)
+    prm.d_mlp_pack = _ptr(mlp_pack)
+    prm.mlp_pack_stride = 0
+    prm.precision = int(precision)
+    prm.d_sky, prm.d_sky_avg = _ptr(sky), _ptr(sky_avg)
+    prm.d_net_out, prm.d_depth_out, prm.d_total_weight = _ptr(net_out), _ptr(depth), _ptr(tw)
+    prm.d_weights_out, prm.d_rand_depth_out = _ptr(wts), _ptr(rdp)
+    prm.d_workspace = _ptr(ws)
+    return prm
+
+
+class _FusedRenderTrainFn(torch.autograd.Function):
+    """net_out = fused_render(embeddings, global_enc, effective LightningMLP weights, sky, sky_avg).
+
+    The effective weights are what ModLinear produces for ONE style code (W' = W * alpha, beta; layers.py:247-260):
+    the caller computes them with ordinary torch ops so that autograd carries dL/dW', dL/dbeta on to the raw
+    parameters and to the style code.  One view per call (the training configs use batch 1 per GPU)."""
+
+    @staticmethod
+    def forward(ctx, cfg, embeddings, genc, w1, b1, fc_m_a, wh, bh, wsig, bsig, wout, bout, sky, sky_avg):
+        L = _lib.lib()
+        voxel_id, depth2, raydirs = cfg['voxel_id'], cfg['depth2'], cfg['raydirs']
+        dev = voxel_id.device
+        N, H, W, M = voxel_id.shape[:4]
+        if N != 1:
+            raise RuntimeError('fused training path renders one view per call')
+        S = int(cfg['num_samples'])
+        for t, n in ((voxel_id, 'voxel_id'), (depth2, 'depth2'), (raydirs, 'raydirs')):
+            if not t.is_cuda or not t.is_contiguous():
+                raise RuntimeError('%s must be a contiguous CUDA tensor' % n)
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        embeddings_, genc_ = f32(embeddings), f32(genc).reshape(-1)[:2].contiguous()
+        w1_, b1_, wh_, bh_ = f32(w1), f32(b1), f32(wh), f32(bh)
+        emb_ = f32(fc_m_a).t().contiguous()                         # [labels, 256]
+        wsig_, bsig_, wout_, bout_ = f32(wsig).reshape(-1), f32(bsig).reshape(-1), f32(wout), f32(bout)
+        sky_, sky_avg_ = f32(sky).reshape(N, H, W, 64), f32(sky_avg).reshape(N, 64)
+        cam_ori = cfg['cam_ori'].to(dev, torch.float32).reshape(N, 3).contiguous()
+        lut = cfg['lut'].to(dev, torch.int32).contiguous()
+        prec = PRECISION_FP16X3
+        with torch.cuda.device(dev):
+            pack = torch.empty(int(L.sdb_mlp_pack_bytes(prec)), dtype=torch.uint8, device=dev)
+            _lib.check(L.sdb_pack_mlp(_ptr(w1_), _ptr(b1_), _ptr(emb_), int(emb_.shape[0]), _ptr(wh_), _ptr(bh_), _ptr(wsig_),
+                                      _ptr(bsig_), _ptr(wout_), _ptr(bout_), prec, _ptr(pack), _stream(dev)), 'sdb_pack_mlp')
+            table3 = preblend_table(embeddings_, genc_, cfg['log2_T'], cfg['per_level_scale'], cfg['base_res'], cfg['L'])
+            net_out = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
+            depth = torch.empty(N, H, W, dtype=torch.float32, device=dev)
+            tw = torch.empty(N, H, W, dtype=torch.float32, device=dev)
+            wts = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev)
+            rdp = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev)
+            ws = torch.empty(int(L.sdb_render_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+            record = torch.empty(int(L.sdb_render_train_record_bytes(N, H, W, S)), dtype=torch.uint8, device=dev)
+            prm, keep = _RenderParams(), []
+            _fill_render_params(prm, keep, voxel_id, depth2, raydirs, cam_ori, genc_, cfg['voxel_dims'], lut, pack, sky_, sky_avg_,
+                                table3, S, cfg['sample_depth'], cfg['dists_scale'], cfg.get('uniforms'), prec,
+                                cfg['per_level_scale'], cfg['base_res'], cfg['log2_T'], cfg['L'], net_out, depth, tw, wts, rdp, ws)
+            _lib.check(L.sdb_render_rays_train_forward(ctypes.byref(prm), _ptr(record), _stream(dev)),
+                       'sdb_render_rays_train_forward')
+        ctx.cfg, ctx.prm, ctx.keep = cfg, prm, keep + [cam_ori, lut, pack, table3, net_out, depth, tw, wts, rdp, ws, genc_, sky_,
+                                                       sky_avg_]
+        ctx.record = record
+        ctx.saved = (embeddings_, w1_, wh_, wsig_, wout_)
+        ctx.shapes = (tuple(fc_m_a.shape), tuple(wsig.shape), tuple(bsig.shape), tuple(sky.shape), tuple(sky_avg.shape),
+                      tuple(genc.shape))
+        ctx.mark_non_differentiable(depth, tw, wts, rdp)
+        return net_out, depth, tw, wts, rdp
+
+    @staticmethod
+    def backward(ctx, g_net_out, *_unused):
+        L = _lib.lib()
+        cfg, prm = ctx.cfg, ctx.prm
+        embeddings_, w1_, wh_, wsig_, wout_ = ctx.saved
+        dev = embeddings_.device
+        N, H, W, S = prm.n_img, prm.H, prm.W, prm.S
+        g = g_net_out.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            bpack = torch.empty(int(L.sdb_mlp_backward_pack_bytes()), dtype=torch.uint8, device=dev)
+            _lib.check(L.sdb_pack_mlp_backward(_ptr(w1_), _ptr(wh_), _ptr(wsig_), _ptr(wout_), _ptr(bpack), _stream(dev)),
+                       'sdb_pack_mlp_backward')
+            g_table = torch.empty_like(embeddings_)
+            g_genc = torch.empty(2, dtype=torch.float32, device=dev)
+            g_w1ext = torch.empty(256, 144, dtype=torch.float32, device=dev)
+            g_wh = torch.empty(5, 256, 264, dtype=torch.float32, device=dev)
+            g_wsig = torch.empty(8, 264, dtype=torch.float32, device=dev)
+            g_wout = torch.empty(64, 264, dtype=torch.float32, device=dev)
+            g_sky = torch.zeros(N, H, W, 64, dtype=torch.float32, device=dev)
+            g_sky_avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
+            wsb = torch.empty(int(L.sdb_render_backward_workspace_bytes(N, H, W, S, int(cfg['L']), int(cfg['log2_T']))),
+                              dtype=torch.uint8, device=dev)
+            gr = _RenderGrads()
+            gr.d_grad_net_out, gr.d_bwd_pack, gr.bwd_pack_stride = _ptr(g), _ptr(bpack), 0
+            gr.d_table = _ptr(embeddings_)
+            gr.d_grad_table, gr.d_grad_global_enc, gr.d_grad_w1ext = _ptr(g_table), _ptr(g_genc), _ptr(g_w1ext)
+            gr.d_grad_wh, gr.d_grad_wsig, gr.d_grad_wout = _ptr(g_wh), _ptr(g_wsig), _ptr(g_wout)
+            gr.d_grad_sky, gr.d_grad_sky_avg, gr.d_workspace = _ptr(g_sky), _ptr(g_sky_avg), _ptr(wsb)
+            _lib.check(L.sdb_render_rays_backward(ctypes.byref(prm), _ptr(ctx.record), ctypes.byref(gr), _stream(dev)),
+                       'sdb_render_rays_backward')
+        s_fcma, s_wsig, s_bsig, s_sky, s_skyavg, s_genc = ctx.shapes
+        n_lab = s_fcma[1]
+        d_genc = torch.zeros(s_genc, dtype=torch.float32, device=dev)
+        d_genc.view(-1)[:2] = g_genc
+        return (None, g_table, d_genc,
+                g_w1ext[:, :128].contiguous(), g_w1ext[:, 143].contiguous(), g_w1ext[:, 128:128 + n_lab].contiguous(),
+                g_wh[:, :, :256].contiguous(), g_wh[:, :, 256].contiguous(),
+                g_wsig[0, :256].reshape(s_wsig), g_wsig[0, 256].reshape(s_bsig),
+                g_wout[:, :256].contiguous(), g_wout[:, 256].contiguous(),
+                g_sky.reshape(s_sky), g_sky_avg.reshape(s_skyavg))
+
+
+def render_rays_train(P, voxel_id, depth2, raydirs, cam_ori, z, global_enc, voxel_dims, label_lut, per_level_scale,
+                      num_samples=24, sample_depth=3.0, dists_scale=0.25, uniforms=None, base_res=16, log2_T=19, L=16,
+                      prefix='render_net', sky_prefix='sky_net'):
+    """Differentiable fused a2-a12 for ONE view: gradients reach P['hash_encoder.embeddings'], P['render_net.*'],
+    P['sky_net.*'], z [1,256] and global_enc [1,2] (everything Generator._forward_perpix differentiates under train.py).
+    The sky branch (3 % of the FLOPs, per ray) runs through torch autograd / cuBLAS on top of the PE kernel."""
+    p = prefix + '.'
+    wh, bh = modulated_weights(P, z[0], prefix)                            # differentiable w.r.t. P and z
+    sky = sky_features(P, raydirs, z, prefix=sky_prefix)                   # [1,H,W,64]
+    sky_avg = sky.mean(dim=(1, 2))                                         # scenedreamer.py:395
+    cfg = dict(voxel_id=voxel_id, depth2=depth2, raydirs=raydirs, cam_ori=cam_ori, lut=label_lut, voxel_dims=voxel_dims,
+               num_samples=num_samples, sample_depth=sample_depth, dists_scale=dists_scale, uniforms=uniforms,
+               per_level_scale=per_level_scale, base_res=base_res, log2_T=log2_T, L=L)
+    net_out, depth, tw, wts, rdp = _FusedRenderTrainFn.apply(
+        cfg, P['hash_encoder.embeddings'], global_enc, P[p + 'fc_1.weight'], P[p + 'fc_1.bias'], P[p + 'fc_m_a.weight'],
+        wh, bh, P[p + 'fc_sigma.weight'], P[p + 'fc_sigma.bias'], P[p + 'fc_out_c.weight'], P[p + 'fc_out_c.bias'], sky,
+        sky_avg)
+    return dict(net_out=net_out, depth=depth, total_weight=tw, weights=wts, rand_depth=rdp, sky=sky, sky_avg=sky_avg)

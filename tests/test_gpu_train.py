@@ -1,0 +1,116 @@
+"""GPU parity tests of the fused training path (sdb_render_rays_train_forward / sdb_render_rays_backward)
+through the C ABI: every parameter gradient of the per-pixel stage against the CPU oracle under
+torch.autograd (oracle.forward_perpix_autograd: the reference's _grid_encode autograd.Function
+restated on oracle.c + the torch fp32 MLP / compositing) on the same seeded inputs.
+
+Tolerances (no gradient tolerance is stated by the north star; these are the ones asserted here):
+  * forward of the recording kernel: 1e-3 max-abs on net_out like the inference kernel;
+  * gradients: relative L2 error per tensor <= 1e-2 -- the data-gradient chain runs bf16x3 (2^-16
+    relative per product) and the weight-gradient GEMMs take bf16 operands (2^-9 per element,
+    fp32 accumulation over >= 10^4 samples); observed errors are printed per tensor.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from scenedreamer_b200 import ops, render, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+DEV = 'cuda:0'
+GRAD_TOL = 1e-2
+
+
+def device_level_scales(L, pls, base):
+    S = torch.tensor(float(np.float32(np.log2(pls))), device=DEV)
+    lv = torch.arange(L, device=DEV, dtype=torch.float32)
+    return (torch.exp2(lv * S) * float(base) - 1.0).cpu()
+
+
+@pytest.fixture(scope='module')
+def scene():
+    world = synth.SyntheticVoxelWorld(size=128, seed=7)
+    pose = synth.eval_camera_poses(world, maxstep=8, pattern=0)[1]
+    o, d, u, f, c, res = synth.frame_camera(world, pose, resolution_hw=(36, 52), pad=4)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV), o, d, u, f, c, res, 6)
+    return dict(world=world, o=o, vid=vid.unsqueeze(0), dep=dep.unsqueeze(0), rd=rd.unsqueeze(0))
+
+
+def _leaf(P, dev):
+    return {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in P.items()}
+
+
+GRAD_KEYS = ['hash_encoder.embeddings', 'render_net.fc_1.weight', 'render_net.fc_1.bias', 'render_net.fc_m_a.weight',
+             'render_net.fc_sigma.weight', 'render_net.fc_sigma.bias', 'render_net.fc_out_c.weight', 'render_net.fc_out_c.bias',
+             'sky_net.fc1.weight', 'sky_net.fc_z_a.weight', 'sky_net.fc5.weight', 'sky_net.fc_out_c.weight'] + \
+            ['render_net.fc_%d.%s' % (k, n) for k in (2, 3, 4, 5, 6) for n in ('weight', 'weight_alpha', 'bias_alpha',
+                                                                                'weight_beta', 'bias_beta')]
+
+
+@pytest.mark.parametrize('stress,S,stratified', [(True, 24, True), (False, 12, False)])
+def test_fused_backward_vs_oracle_autograd(scene, golden_ops, stress, S, stratified):
+    sc = scene
+    P0 = oracle.make_params(seed=21, stress=stress)
+    g = torch.Generator().manual_seed(8888)
+    z0 = oracle.style_mlp(torch.randn(1, 128, generator=g), P0)
+    genc0 = torch.tanh(torch.randn(1, 2, generator=g))
+    N, H, W = sc['vid'].shape[:3]
+    uni = torch.rand(N, H, W, S + 1, 1, generator=torch.Generator().manual_seed(5)) if stratified else None
+    G = torch.randn(N, H, W, 64, generator=torch.Generator().manual_seed(9))
+    if not stress:
+        G = G * 100.0          # spec init: outputs ~1e-3; keep the gradients in a comfortable range
+    lut_raw = torch.from_numpy(golden_ops['mc2reduced_lut'])
+    offsets, pls = oracle.grid_offsets()
+
+    # ---- oracle (CPU, torch.autograd) ----
+    Pc = _leaf(P0, 'cpu')
+    zc, gc = z0.clone().requires_grad_(True), genc0.clone().requires_grad_(True)
+    ref = oracle.forward_perpix_autograd(Pc, sc['vid'].cpu(), sc['dep'].cpu(), sc['rd'].cpu(), sc['o'].unsqueeze(0), zc, gc,
+                                         list(sc['world'].voxel_t.shape), lut_raw, offsets, pls, num_samples=S,
+                                         deterministic=uni is None, uniforms=uni,
+                                         level_scales=device_level_scales(16, pls, 16))
+    (ref * G).sum().backward()
+
+    # ---- fused (GPU) ----
+    Pg = _leaf(P0, DEV)
+    zg, gg = z0.clone().to(DEV).requires_grad_(True), genc0.clone().to(DEV).requires_grad_(True)
+    lut = render.reduced_label_lut(golden_ops['mc2reduced_lut'], 0, 3)
+    out = render.render_rays_train(Pg, sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), zg, gg,
+                                   list(sc['world'].voxel_t.shape), lut, pls, num_samples=S,
+                                   uniforms=None if uni is None else uni.to(DEV))
+    (out['net_out'] * G.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+
+    ferr = float((out['net_out'].detach().cpu() - ref.detach()).abs().max())
+    print('forward (recording kernel) max abs err %.3e (|ref| max %.3f)' % (ferr, float(ref.abs().max())))
+    assert ferr <= 1e-3
+    worst = 0.0
+    rows = [('z', zg.grad, zc.grad), ('global_enc', gg.grad, gc.grad)] + [(k, Pg[k].grad, Pc[k].grad) for k in GRAD_KEYS]
+    for name, a, b in rows:
+        assert a is not None, 'no gradient reached %s' % name
+        a, b = a.detach().cpu().double(), b.detach().double()
+        rel = float((a - b).norm() / (b.norm() + 1e-30))
+        print('%-36s rel-L2 %.3e   max|diff| %.3e   max|ref| %.3e' % (name, rel, float((a - b).abs().max()), float(b.abs().max())))
+        assert float(b.abs().max()) > 0, 'oracle gradient of %s is identically zero: vacuous test' % name
+        worst = max(worst, rel)
+    assert worst <= GRAD_TOL, worst
+
+
+def test_train_forward_equals_inference_forward(scene, golden_ops):
+    """The recording variant of the kernel computes exactly what the inference kernel computes."""
+    sc = scene
+    P = {k: v.to(DEV) for k, v in oracle.make_params(seed=3, stress=True).items()}
+    g = torch.Generator().manual_seed(1)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), {k: v.cpu() for k, v in P.items()}).to(DEV)
+    genc = torch.tanh(torch.randn(1, 2, generator=g)).to(DEV)
+    lut = render.reduced_label_lut(golden_ops['mc2reduced_lut'], 0, 3)
+    _, pls = oracle.grid_offsets()
+    with torch.no_grad():
+        tr = render.render_rays_train(P, sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), z, genc,
+                                      list(sc['world'].voxel_t.shape), lut, pls)
+    r = render.FusedPerPixelRenderer(P, sc['world'].voxel_t.shape, lut, pls)
+    r.sky_impl = 'torch'
+    inf = r.forward(sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), z, genc, want_samples=True)
+    torch.cuda.synchronize()
+    for k in ('net_out', 'depth', 'total_weight', 'weights', 'rand_depth'):
+        assert torch.equal(tr[k], inf[k]), k
