@@ -313,6 +313,20 @@ mlp_kernel(const Params p)
                                 for (int j = 0; j < 32; j++) sig_part = fmaf(v[j], ws[j], sig_part);
                             }
                         }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            uint4 hi, lo;
+                            const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
+                            split8<PREC>(v8, hi, lo);
+                            const uint32_t off = tc05::chunk_off(kRows, row, half * 16 + (c0 >> 3) + q);
+                            *reinterpret_cast<uint4 *>(sHhi + off) = hi;
+                            if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
+                        }
+                        // a 32-column K chunk of the next layer's operand is complete (all 128 rows once the four
+                        // quadrant warps of this half have arrived): the MMA issuer may start on it
+                        tc05::fence_proxy_async_smem();
+                        tc05::mbar_arrive(&bars[B_CHUNK + half * 4 + (c0 >> 5)]);
+                        // the training record is written AFTER the chunk has been handed to the MMA issuer (off the critical path)
                         if constexpr (TRAIN || BWD) {
                             // bf16 (round-to-nearest) copy of the chunk for the weight-gradient GEMMs:
                             // forward: A_{l+1}[slot][128*half + c0 ..], backward: dZ_{6-l}[slot][...]
@@ -331,19 +345,6 @@ mlp_kernel(const Params p)
                             for (int j = 0; j < 32; j++) word |= (v[j] > 0.0f ? 1u : 0u) << j;
                             p.tr.mask[((step_id * kNumAct + l) * kRows + row) * 8 + half * 4 + (c0 >> 5)] = word;
                         }
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            uint4 hi, lo;
-                            const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
-                            split8<PREC>(v8, hi, lo);
-                            const uint32_t off = tc05::chunk_off(kRows, row, half * 16 + (c0 >> 3) + q);
-                            *reinterpret_cast<uint4 *>(sHhi + off) = hi;
-                            if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
-                        }
-                        // a 32-column K chunk of the next layer's operand is complete (all 128 rows once the four
-                        // quadrant warps of this half have arrived): the MMA issuer may start on it
-                        tc05::fence_proxy_async_smem();
-                        tc05::mbar_arrive(&bars[B_CHUNK + half * 4 + (c0 >> 5)]);
                     }
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (g & 1u)]);        // accumulator buffer (g & 1) is free again

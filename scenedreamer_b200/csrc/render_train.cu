@@ -18,6 +18,7 @@
 //                                   XOR-indexing is an involution) and the scene-code gradient;
 //   4. weight gradients           : plain bf16 GEMMs dZ^T * A over all samples through cuBLAS (fp32 out).
 #include <cublas_v2.h>
+#include <stdlib.h>
 
 #include "rf_common.cuh"
 
@@ -204,31 +205,80 @@ composite_backward_kernel(const Params p, const float *__restrict__ g_out, float
 
 // ---- 3a. scatter d(features) into the pre-blended table gradient --------------------------------------
 // thread = (slot, level), level-major grid so that a wave of CTAs works on one 16 MB level slice (L2-resident).
+// A warp is 32 neighbouring rays of one tile at one sample step: on the coarse levels they fall into the same cell,
+// so their 8 corner rows coincide and a plain scatter serialises on a handful of addresses (the reference's
+// kernel_grid_backward has the same hot spot, gridencoder.cu:307-311).  For level < agg_levels the warp therefore
+// groups equal row indices with match.any, reduces each group with shuffles and lets the group leader issue the
+// two vector reductions; with more than 4 distinct rows in the warp (fine levels) every lane scatters on its own.
+__device__ __forceinline__ void red_add8(float *dst, const float (&v)[8]) {
+    atomicAdd(reinterpret_cast<float4 *>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(reinterpret_cast<float4 *>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+
 __global__ void __launch_bounds__(256)
-table3_backward_kernel(const Params p, long long n_slots, const float *__restrict__ dx0, float *__restrict__ dt3)
+table3_backward_kernel(const Params p, long long n_slots, const float *__restrict__ dx0, float *__restrict__ dt3, int agg_levels)
 {
     const long long slot = blockIdx.x * 256ll + threadIdx.x;
-    if (slot >= n_slots) return;
-    const int level = blockIdx.y;
-    const float4 x = p.tr.x3[slot];
-    if (x.w < 0.0f) return;                                    // outside the volume / sky-only ray: no table contribution
-    float g[8];
-    ld8(dx0 + slot * kFeat + level * 8, g);
-    bool any = false;
+    const int level = blockIdx.y, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    bool active = slot < n_slots;
+    float4 x = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    if (active) x = p.tr.x3[slot];
+    active = active && !(x.w < 0.0f);                          // outside the volume / sky-only ray: no table contribution
+    float g[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (active) {
+        ld8(dx0 + slot * kFeat + level * 8, g);
+        bool any = false;
 #pragma unroll
-    for (int c = 0; c < 8; c++) any = any || (g[c] != 0.0f);
-    if (!any) return;
+        for (int c = 0; c < 8; c++) any = any || (g[c] != 0.0f);
+        active = any;
+    }
+    const bool agg = level < agg_levels;                       // block-uniform
+    if (!agg && !active) return;
+    if (agg && __ballot_sync(full, active) == 0u) return;      // warp-uniform
     const float scale = exp2f(level * p.level_S) * p.base_res - 1.0f;      // gridencoder.cu:126
     const uint32_t mask = (1u << p.log2_T) - 1u;
     const float xs[3] = {x.x, x.y, x.z};
     const Corners3 cn = corners3(mask, scale, xs);
     float *gt = dt3 + ((size_t)level << p.log2_T) * 8;
+    if (!agg) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[c] = cn.w[i] * g[c];
+            red_add8(gt + (size_t)cn.idx[i] * 8, v);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const float w = cn.w[i];
-        float4 *dst = reinterpret_cast<float4 *>(gt + (size_t)cn.idx[i] * 8);
-        atomicAdd(dst, make_float4(w * g[0], w * g[1], w * g[2], w * g[3]));
-        atomicAdd(dst + 1, make_float4(w * g[4], w * g[5], w * g[6], w * g[7]));
+        const uint32_t key = active ? cn.idx[i] : 0xffffffffu;      // inactive lanes form their own (ignored) group
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[c] = active ? cn.w[i] * g[c] : 0.0f;
+        const unsigned grp = __match_any_sync(full, key);
+        const int leader = __ffs(grp) - 1;
+        unsigned leaders = __ballot_sync(full, lane == leader);
+        if (__popc(leaders) > 4) {
+            if (active) red_add8(gt + (size_t)key * 8, v);
+            continue;
+        }
+        while (leaders) {
+            const int L = __ffs(leaders) - 1;
+            leaders &= leaders - 1;
+            const unsigned m = __shfl_sync(full, grp, L);
+            const bool mine = (m >> lane) & 1u;
+            float s[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float t = mine ? v[c] : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(full, t, o);
+                s[c] = t;
+            }
+            if (lane == L && key != 0xffffffffu) red_add8(gt + (size_t)key * 8, s);
+        }
     }
 }
 
@@ -430,7 +480,10 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
     // 3. table gradient: scatter into the pre-blended table, transpose of the pre-blend, scene code
     {
         dim3 grid((unsigned)((n_slots + 255) / 256), kLevels);
-        table3_backward_kernel<<<grid, 256, 0, st>>>(p, n_slots, dx0, dt3);
+        // SDB_TABLE_AGG_LEVELS: tuning knob (levels 0..n-1 use the warp-aggregated scatter); default from profiles/
+        int agg_levels = 12;
+        if (const char *e = getenv("SDB_TABLE_AGG_LEVELS")) agg_levels = atoi(e);
+        table3_backward_kernel<<<grid, 256, 0, st>>>(p, n_slots, dx0, dt3, agg_levels);
         SDB_CHECK_LAUNCH();
         int rc = sdb_preblend_table(dt3, g->d_grad_table, sp->L, p.log2_T, p.level_S, p.base_res, p.genc, stream);
         if (rc != SDB_OK) return rc;

@@ -1,10 +1,13 @@
 """Reference-side integration: run SceneDreamer's `Generator._forward_perpix` on the fused B200 kernel.
 
 `patch_generator(net_G)` rebinds `_forward_perpix` of a reference Generator instance
-(imaginaire/generators/scenedreamer.py:313) so that inference.py / the no-grad half of train.py
-(`dis_forward`, trainers/gancraft.py:215-217) run the fused path, while calls that need autograd
-(gen_update) keep the reference's own composition -- which, with dropin/ on PYTHONPATH, still runs
-on this library's DDA / positional-encoding / hash-grid kernels.
+(imaginaire/generators/scenedreamer.py:313) so that inference.py and BOTH halves of train.py run the
+fused path: without autograd (`dis_forward`, trainers/gancraft.py:215-217) the inference kernel,
+with autograd (gen_update) the recording forward + fused backward (render.render_rays_train), whose
+gradients reach the module's own Parameters (hash_encoder.embeddings, render_net.*, sky_net.*) and
+the incoming z / global_enc.  Configurations the fused path does not cover (see `supported` below,
+or a batch of several views in one call under autograd) keep the reference's own composition --
+which, with dropin/ on PYTHONPATH, still runs on this library's DDA / PE / hash-grid kernels.
 
 The returned 12-tuple has the reference's order (scenedreamer.py:427-428).  Callers in the reference
 use only `net_out` (index 0) and, in the depth variant, `weights` (2) and `rand_depth` (4)
@@ -47,27 +50,51 @@ class _FusedState:
         return self.renderer
 
 
+def _live_params(gen):
+    """Parameters (not detached) under the reference's state-dict names, for the autograd path."""
+    P = {}
+    for prefix, mod in (('render_net', gen.render_net), ('sky_net', gen.sky_net), ('hash_encoder', gen.hash_encoder)):
+        for k, v in mod.named_parameters():
+            P[prefix + '.' + k] = v
+        for k, v in mod.named_buffers():
+            P.setdefault(prefix + '.' + k, v)
+    return P
+
+
 def fused_forward_perpix(self, blk_feats, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc):
     """Replacement body of Generator._forward_perpix (same arguments, same return order)."""
     st = self._sdb200
     supported = (self.clip_feat_map is True and self.keep_sky_out and self.keep_sky_out_avgpool and
                  self.sky_global_avgpool and not self.sample_use_box_boundaries and self.raw_noise_std == 0 and
                  self.pe_params[2] == 0 and self.pe_params_sky[0] == 5 and bool(self.pe_params_sky[1]))
-    if torch.is_grad_enabled() or not supported or not voxel_id.is_cuda:
+    needs_grad = torch.is_grad_enabled() and (z.requires_grad or global_enc.requires_grad or
+                                              any(q.requires_grad for q in self.render_net.parameters()) or
+                                              any(q.requires_grad for q in self.hash_encoder.parameters()))
+    if not supported or not voxel_id.is_cuda or (needs_grad and (voxel_id.shape[0] != 1 or hasattr(self, 'sky_avg'))):
         return st.reference_forward(blk_feats, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc)
-    r = st.get(self)
     uniforms = None
     if not self.coarse_deterministic_sampling:
         N, H, W = voxel_id.shape[:3]
         uniforms = torch.rand(N, H, W, self.num_samples + 1, 1, dtype=torch.float32, device=voxel_id.device)
+    sky_mask = voxel_id[:, :, :, [-1], :] == 0
+    sky_only_mask = voxel_id[:, :, :, [0], :] == 0
+    if needs_grad:
+        he = self.hash_encoder
+        out = render.render_rays_train(
+            _live_params(self), voxel_id.contiguous(), depth2.contiguous(), raydirs.contiguous(), cam_ori_t, z, global_enc,
+            [float(v) for v in self.voxel.voxel_t.shape], st.lut, he.per_level_scale, num_samples=self.num_samples,
+            sample_depth=self.sample_depth, dists_scale=self.dists_scale, uniforms=uniforms,
+            base_res=he.base_resolution, log2_T=he.log2_hashmap_size, L=he.num_levels)
+        total = out['total_weight'].unsqueeze(-1).unsqueeze(-1)
+        return (out['net_out'], None, out['weights'], total, out['rand_depth'], None, None, out['sky'].unsqueeze(-2), None,
+                sky_mask, sky_only_mask, None)
+    r = st.get(self)
     sky_avg = getattr(self, 'sky_avg', None)
     if sky_avg is not None:
         sky_avg = sky_avg.reshape(-1, 64)
     out = r.forward(voxel_id.contiguous(), depth2.contiguous(), raydirs.contiguous(), cam_ori_t, z, global_enc,
                     num_samples=self.num_samples, sample_depth=self.sample_depth, dists_scale=self.dists_scale,
                     uniforms=uniforms, sky_avg=sky_avg, want_samples=True)
-    sky_mask = voxel_id[:, :, :, [-1], :] == 0
-    sky_only_mask = voxel_id[:, :, :, [0], :] == 0
     total = out['total_weight'].unsqueeze(-1).unsqueeze(-1)
     return (out['net_out'], None, out['weights'], total, out['rand_depth'], None, None, out['sky'].unsqueeze(-2), None,
             sky_mask, sky_only_mask, None)

@@ -219,7 +219,8 @@ def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_di
     with torch.cuda.device(dev):
         code = Lb.sdb_render_rays_forward(ctypes.byref(prm), _stream(dev))
     _lib.check(code, 'sdb_render_rays_forward')
-    return dict(net_out=net_out, depth=depth, total_weight=tw, weights=wts, rand_depth=rdp)
+    # `workspace`: int32[0] = number of live (non sky-only) 16x8 ray tiles the kernel shaded (diagnostics / bench bookkeeping)
+    return dict(net_out=net_out, depth=depth, total_weight=tw, weights=wts, rand_depth=rdp, workspace=ws)
 
 
 def reduced_label_lut(mc2reduced, ignore_id=0, dirt_id=3):

@@ -75,10 +75,13 @@ def test_patched_forward_perpix_matches_oracle(golden_ops):
         def __init__(self, sd):
             super().__init__()
             for k, v in sd.items():
-                self.register_buffer(k.replace('.', '__'), v.to(DEV))
+                self.register_parameter(k.replace('.', '__'), torch.nn.Parameter(v.to(DEV)))
 
         def state_dict(self, *a, **k):
-            return {n.replace('__', '.'): b for n, b in self.named_buffers()}
+            return {n.replace('__', '.'): b.detach() for n, b in super().named_parameters()}
+
+        def named_parameters(self, *a, **k):
+            return [(n.replace('__', '.'), b) for n, b in super().named_parameters(*a, **k)]
 
     def sub(prefix):
         return Holder({k[len(prefix) + 1:]: v for k, v in P.items() if k.startswith(prefix + '.')})
@@ -118,7 +121,31 @@ def test_patched_forward_perpix_matches_oracle(golden_ops):
     # depth variant of the reference: sum(weights * rand_depth) (scenedreamer.py:816)
     dmap = torch.sum(ret[2] * ret[4], dim=-2)
     assert float((dmap.cpu() - ref['depth_map']).abs().max()) <= 1e-3
-    # with autograd enabled the hook defers to the reference's own composition
-    gen._forward_perpix(None, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0).to(DEV), z.to(DEV),
-                        genc.to(DEV))
+    # with autograd enabled the hook runs the recording forward + fused backward: gradients land on the
+    # module's own Parameters and on z / global_enc (gen_update of trainers/gancraft.py)
+    zg, gg = z.clone().to(DEV).requires_grad_(True), genc.clone().to(DEV).requires_grad_(True)
+    ret_t = gen._forward_perpix(None, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0).to(DEV), zg, gg)
+    assert len(ret_t) == 12 and 'ref' not in called and ret_t[0].requires_grad
+    assert float((ret_t[0].detach() - ret[0]).abs().max()) <= 1e-3
+    G = torch.randn(ret_t[0].shape, generator=torch.Generator().manual_seed(2)).to(DEV)
+    (ret_t[0] * G).sum().backward()
+    Pc = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    zc, gc = z.clone().requires_grad_(True), genc.clone().requires_grad_(True)
+    ref_t = oracle.forward_perpix_autograd(Pc, vid.unsqueeze(0).cpu(), dep.unsqueeze(0).cpu(), rd.unsqueeze(0).cpu(), o.unsqueeze(0),
+                                           zc, gc, list(world.voxel_t.shape), torch.from_numpy(golden_ops['mc2reduced_lut']),
+                                           offsets, pls, level_scales=ls)
+    (ref_t * G.cpu()).sum().backward()
+    got = dict(gen.render_net.named_parameters())
+    for name, a, b in (('z', zg.grad, zc.grad), ('global_enc', gg.grad, gc.grad),
+                       ('embeddings', dict(gen.hash_encoder.named_parameters())['embeddings'].grad, Pc['hash_encoder.embeddings'].grad),
+                       ('fc_1.weight', got['fc_1.weight'].grad, Pc['render_net.fc_1.weight'].grad),
+                       ('fc_4.weight_alpha', got['fc_4.weight_alpha'].grad, Pc['render_net.fc_4.weight_alpha'].grad),
+                       ('sky fc3.weight', dict(gen.sky_net.named_parameters())['fc3.weight'].grad, Pc['sky_net.fc3.weight'].grad)):
+        rel = float((a.cpu().double() - b.double()).norm() / b.double().norm())
+        print('patched train grad %-20s rel-L2 %.3e' % (name, rel))
+        assert rel <= 1e-2, name
+    # a batch of several views under autograd is outside the fused training path: the reference's own composition runs
+    two = lambda t: torch.cat([t, t], 0)
+    gen._forward_perpix(None, two(vid.unsqueeze(0)), two(dep.unsqueeze(0)), two(rd.unsqueeze(0)), two(o.unsqueeze(0).to(DEV)),
+                        two(zg), gg)
     assert called.get('ref')
