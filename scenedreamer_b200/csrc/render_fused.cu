@@ -855,15 +855,25 @@ prepass_kernel(const Params p, int32_t *tile_list, int32_t *n_live)
     }
 }
 
-// frame-global sky mean from the per-tile partial sums, fixed summation order (deterministic)
-__global__ void __launch_bounds__(kOutC)
+// frame-global sky mean from the per-tile partial sums, fixed summation order (deterministic): 16 groups of 64
+// threads each add every 16th tile in order, then the 16 partial sums are added in order
+constexpr int kMeanGroups = 16;
+__global__ void __launch_bounds__(kOutC * kMeanGroups)
 sky_mean_kernel(const float *__restrict__ partial, float *__restrict__ sky_avg, int tiles_per_img, float inv_count)
 {
-    const int img = blockIdx.x, c = threadIdx.x;
+    __shared__ float red[kMeanGroups][kOutC];
+    const int img = blockIdx.x, c = threadIdx.x & (kOutC - 1), grp = threadIdx.x / kOutC;
     const float *pp = partial + (long long)img * tiles_per_img * kOutC + c;
     float acc = 0.0f;
-    for (int t = 0; t < tiles_per_img; t++) acc += pp[(long long)t * kOutC];
-    sky_avg[img * kOutC + c] = acc * inv_count;
+    for (int t = grp; t < tiles_per_img; t += kMeanGroups) acc += pp[(long long)t * kOutC];
+    red[grp][c] = acc;
+    __syncthreads();
+    if (grp == 0) {
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMeanGroups; k++) a += red[k][c];
+        sky_avg[img * kOutC + c] = a * inv_count;
+    }
 }
 
 // ---- per-scene pre-blend of the two constant encoder dims -------------------------------------------
@@ -1133,7 +1143,7 @@ extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H,
     else if (precision == 2) rc = launch_mlp<2, false, kSky>(p, grid, st);
     else rc = launch_mlp<0, false, kSky>(p, grid, st);
     if (rc != SDB_OK) return rc;
-    sky_mean_kernel<<<n_img, kOutC, 0, st>>>(p.sky_partial, d_sky_avg, p.tiles_x * p.tiles_y, 1.0f / ((float)H * (float)W));
+    sky_mean_kernel<<<n_img, kOutC * kMeanGroups, 0, st>>>(p.sky_partial, d_sky_avg, p.tiles_x * p.tiles_y, 1.0f / ((float)H * (float)W));
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
