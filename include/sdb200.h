@@ -220,9 +220,9 @@ typedef struct sdb_render_grads {
     float *d_grad_table;           /* [L*T, 8]  dL/d hash_encoder.embeddings                        */
     float *d_grad_global_enc;      /* [2]       dL/d scene code (summed over images)                */
     float *d_grad_w1ext;           /* [256, 144] cols 0..127 fc_1.weight, 128+k fc_m_a.weight[:,k], 143 fc_1.bias */
-    float *d_grad_wh;              /* [5][256, 264] cols 0..255 dL/dW' (modulated weight), col 256 dL/dbeta        */
-    float *d_grad_wsig;            /* [8, 264]  row 0: cols 0..255 fc_sigma.weight, col 256 fc_sigma.bias          */
-    float *d_grad_wout;            /* [64, 264] cols 0..255 fc_out_c.weight, col 256 fc_out_c.bias                 */
+    float *d_grad_wh;              /* [5][256, 272] cols 0..255 dL/dW' (modulated weight), col 256 dL/dbeta        */
+    float *d_grad_wsig;            /* [8, 272]  row 0: cols 0..255 fc_sigma.weight, col 256 fc_sigma.bias          */
+    float *d_grad_wout;            /* [64, 272] cols 0..255 fc_out_c.weight, col 256 fc_out_c.bias                 */
     float *d_grad_sky;             /* [R, 64]   dL/d sky features per ray                           */
     float *d_grad_sky_avg;         /* [n_img, 64]                                                   */
     void *d_workspace;             /* sdb_render_backward_workspace_bytes() bytes                   */
@@ -230,6 +230,26 @@ typedef struct sdb_render_grads {
 
 int64_t sdb_render_backward_workspace_bytes(int32_t n_img, int32_t H, int32_t W, int32_t S, int32_t L, int32_t log2_T);
 int sdb_render_rays_backward(const sdb_render_params *p, const void *d_record, const sdb_render_grads *g, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * a9 under autograd.  sdb_sky_train_forward = sdb_sky_forward (fp16x3, ONE style code / image)
+ * that also records PE(raydir), the five hidden activations (bf16) and their LeakyReLU sign
+ * words; sdb_sky_backward turns dL/d sky [R,64] (ray order; the contribution of the frame mean
+ * already added by the caller) into the SKYMLP weight gradients (gancraft_base.py:150-169 under
+ * torch.autograd): gradient chain on the tensor-core engine + bf16 GEMMs.
+ *   d_grad_w1ext [256, 48]: cols 0..32 fc1.weight, col 47 the layer-0 bias (fc1.bias + fc_z_a(z));
+ *   d_grad_wh [4][256, 272]: fc2..fc5 (cols 0..255 weight, col 256 bias); d_grad_wout [64, 272].
+ *   backward pack: sdb_pack_sky_mlp_backward(wh [4][256,256], wout [64,256]).
+ * ------------------------------------------------------------------------------------------ */
+int64_t sdb_sky_train_record_bytes(int32_t n_img, int32_t H, int32_t W);
+int sdb_sky_train_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
+                          float *d_sky, float *d_sky_avg, void *d_workspace, void *d_record, void *stream);
+int64_t sdb_sky_backward_pack_bytes(void);
+int sdb_pack_sky_mlp_backward(const float *d_wh, const float *d_wout, void *d_pack, void *stream);
+int64_t sdb_sky_backward_workspace_bytes(int32_t n_img, int32_t H, int32_t W);
+int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void *d_record, const float *d_grad_sky,
+                     const void *d_bwd_pack, float *d_grad_w1ext, float *d_grad_wh, float *d_grad_wout,
+                     void *d_workspace, void *stream);
 
 /* Diagnostics only: byte offsets inside the training record / backward workspace (20 int64, see render_train.cu). */
 int sdb_debug_train_layout(int32_t n_img, int32_t H, int32_t W, int32_t S, int32_t L, int32_t log2_T, int64_t *out);

@@ -42,6 +42,13 @@ SIGNATURES = {
     'sdb_pack_mlp_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'sdb_render_backward_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
     'sdb_render_rays_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sdb_sky_train_record_bytes': (c_i64, [c_i32, c_i32, c_i32]),
+    'sdb_sky_train_forward': (c_int, [c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sdb_sky_backward_pack_bytes': (c_i64, []),
+    'sdb_pack_sky_mlp_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sdb_sky_backward_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
+    'sdb_sky_backward': (c_int, [c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     'sdb_debug_train_layout': (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_i64)]),
     'sdb_debug_set_progress_buffer': (None, [c_void_p]),
     'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),

@@ -160,9 +160,11 @@ template <int PREC, bool RAW5D, int MODE, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const Params p)
 {
-    constexpr bool SKY = MODE == kSky, BWD = MODE == kBwd;
-    static_assert(!TRAIN || (MODE == kRender && !RAW5D), "the training record is written by the table3 render forward only");
-    static_assert(!BWD || PREC == 1, "the gradient chain runs in the range-safe bf16x3 mode");
+    constexpr bool SKY = MODE == kSky, BWD = MODE == kBwd || MODE == kSkyBwd, SKYBWD = MODE == kSkyBwd;
+    constexpr bool ONE_STEP = SKY || SKYBWD;     // per-RAY networks: every tile of the frame, one step per tile
+    constexpr int NACT = Net<MODE>::NACT;
+    static_assert(!TRAIN || ((MODE == kRender || MODE == kSky) && !RAW5D), "the training record is written by the forward networks");
+    static_assert(!BWD || PREC == 1, "the gradient chains run in the range-safe bf16x3 mode");
     constexpr bool X3 = PREC != 0;
     constexpr bool BF16 = PREC == 1;
     constexpr Smem SM = smem_map(X3);
@@ -184,10 +186,10 @@ mlp_kernel(const Params p)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM.tmem_slot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_work = SKY ? p.n_tiles : *p.n_live;
+    const int n_work = ONE_STEP ? p.n_tiles : *p.n_live;
     constexpr bool STATE = MODE == kRender;      // per-ray sampling state (gather -> epilogue hand-off) exists
     const int n_iter = (n_work > (int)blockIdx.x) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int S = SKY ? 1 : p.S;
+    const int S = ONE_STEP ? 1 : p.S;
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -230,11 +232,11 @@ mlp_kernel(const Params p)
         int loaded_img = -1;
         for (int it = 0; it < n_iter; it++) {
             const int work = blockIdx.x + it * gridDim.x;
-            const int tile = SKY ? work : p.tile_list[work];
+            const int tile = ONE_STEP ? work : p.tile_list[work];
             const TileCoord tc = tile_coord(p, tile);
             const int buf = it & 1;
             const float *st = sState + buf * kStFloats * kRows;
-            if (!SKY && loaded_img != tc.img) {
+            if (Net<MODE>::TAIL && loaded_img != tc.img) {
                 // sigma head of this image's pack -> shared memory (epilogue threads are the only readers)
                 const float *packF = reinterpret_cast<const float *>(p.pack + (long long)tc.img * p.pack_stride +
                                                                      layerOff<MODE>(NL, PARTS));
@@ -274,7 +276,7 @@ mlp_kernel(const Params p)
                 const long long step_id = (long long)work * S + s;
                 const long long slot = step_id * kRows + row;
                 float dsig = 0.0f;
-                if constexpr (BWD) dsig = __ldg(p.tr.dsig + slot);
+                if constexpr (MODE == kBwd) dsig = __ldg(p.tr.dsig + slot);
                 (void)slot; (void)dsig;
 #pragma unroll 1
                 for (int l = 0; l < NH; l++) {
@@ -284,7 +286,7 @@ mlp_kernel(const Params p)
                     // through (prefetched before the accumulator wait)
                     uint4 mw = make_uint4(0u, 0u, 0u, 0u);
                     if constexpr (BWD)
-                        mw = __ldg(reinterpret_cast<const uint4 *>(p.tr.mask + ((step_id * kNumAct + (NH - 1 - l)) * kRows + row) * 8 + half * 4));
+                        mw = __ldg(reinterpret_cast<const uint4 *>(p.tr.mask + ((step_id * kNumAct + (NACT - 1 - l)) * kRows + row) * 8 + half * 4));
                     if ((tid & 127) == 0) SDB_MARK(half, 1, n, l);
                     tc05::mbar_wait(&bars[B_ACC], (n * NH + l) & 1);
                     tc05::fence_after_thread_sync();
@@ -295,7 +297,7 @@ mlp_kernel(const Params p)
                         tc05::tmem_ld32(acc + c0, v);
                         tc05::tmem_ld_wait();
                         if constexpr (BWD) {
-                            if (l == 2) {   // dA4 += dsigma * fc_sigma.weight (sigma taps A4, layers.py:115)
+                            if (MODE == kBwd && l == 2) {   // dA4 += dsigma * fc_sigma.weight (sigma taps A4, layers.py:115)
                                 const float *ws = sF + kFWsig + half * 128 + c0;
 #pragma unroll
                                 for (int j = 0; j < 32; j++) v[j] = fmaf(dsig, ws[j], v[j]);
@@ -332,12 +334,14 @@ mlp_kernel(const Params p)
                             // forward: A_{l+1}[slot][128*half + c0 ..], backward: dZ_{6-l}[slot][...]
                             uint16_t *dst = TRAIN
                                 ? p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + half * 128 + c0
-                                : p.tr.dz + ((long long)(NH - 1 - l) * p.tr.slot_cap + slot) * kHidden + half * 128 + c0;
+                                : p.tr.dz + ((long long)(NACT - 1 - l) * p.tr.slot_cap + slot) * kHidden + half * 128 + c0;
 #pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                reinterpret_cast<uint4 *>(dst)[q] =
-                                    make_uint4(tc05::pack2<true>(v[8 * q], v[8 * q + 1]), tc05::pack2<true>(v[8 * q + 2], v[8 * q + 3]),
-                                               tc05::pack2<true>(v[8 * q + 4], v[8 * q + 5]), tc05::pack2<true>(v[8 * q + 6], v[8 * q + 7]));
+                            for (int q = 0; q < 2; q++)
+                                st_global_v8(dst + 16 * q,
+                                             make_uint4(tc05::pack2<true>(v[16 * q], v[16 * q + 1]), tc05::pack2<true>(v[16 * q + 2], v[16 * q + 3]),
+                                                        tc05::pack2<true>(v[16 * q + 4], v[16 * q + 5]), tc05::pack2<true>(v[16 * q + 6], v[16 * q + 7])),
+                                             make_uint4(tc05::pack2<true>(v[16 * q + 8], v[16 * q + 9]), tc05::pack2<true>(v[16 * q + 10], v[16 * q + 11]),
+                                                        tc05::pack2<true>(v[16 * q + 12], v[16 * q + 13]), tc05::pack2<true>(v[16 * q + 14], v[16 * q + 15])));
                         }
                         if constexpr (TRAIN) {
                             uint32_t word = 0;
@@ -351,8 +355,8 @@ mlp_kernel(const Params p)
                     if (MODE == kRender && l == 3) sSig[half * kRows + row] = sig_part;
                     if constexpr (TRAIN) {   // the constant-1 column that turns the weight-gradient GEMM's column 256 into the bias gradient
                         if (half == 0)
-                            *reinterpret_cast<uint4 *>(p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + kHidden) =
-                                make_uint4(0x3F80u, 0u, 0u, 0u);
+                            st_global_v8(p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + kHidden,
+                                         make_uint4(0x3F80u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
                     }
                 }
                 // ---- colour layer ----
@@ -361,6 +365,30 @@ mlp_kernel(const Params p)
                 tc05::mbar_wait(&bars[B_OUTRDY], n & 1);
                 if ((tid & 127) == 0) SDB_MARK(half, 4, n, NH);
                 tc05::fence_after_thread_sync();
+                if constexpr (SKYBWD) {
+                    // last layer of the sky chain: dA1 [128 x 256] -> dZ1 = dA1 * LeakyReLU'(z1) -> bf16 record only
+                    const uint4 mw = __ldg(reinterpret_cast<const uint4 *>(p.tr.mask + ((step_id * kNumAct + 0) * kRows + row) * 8 + half * 4));
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        float v[32];
+                        tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * 128u + c0, v);
+                        tc05::tmem_ld_wait();
+                        const uint32_t word = c0 == 0 ? mw.x : (c0 == 32 ? mw.y : (c0 == 64 ? mw.z : mw.w));
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = ((word >> j) & 1u) ? v[j] : 0.2f * v[j];
+                        uint16_t *dst = p.tr.dz + slot * kHidden + half * 128 + c0;
+#pragma unroll
+                        for (int q = 0; q < 2; q++)
+                            st_global_v8(dst + 16 * q,
+                                         make_uint4(tc05::pack2<true>(v[16 * q], v[16 * q + 1]), tc05::pack2<true>(v[16 * q + 2], v[16 * q + 3]),
+                                                    tc05::pack2<true>(v[16 * q + 4], v[16 * q + 5]), tc05::pack2<true>(v[16 * q + 6], v[16 * q + 7])),
+                                         make_uint4(tc05::pack2<true>(v[16 * q + 8], v[16 * q + 9]), tc05::pack2<true>(v[16 * q + 10], v[16 * q + 11]),
+                                                    tc05::pack2<true>(v[16 * q + 12], v[16 * q + 13]), tc05::pack2<true>(v[16 * q + 14], v[16 * q + 15])));
+                    }
+                    tc05::fence_before_thread_sync();
+                    tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
+                    continue;
+                }
                 float c[32];
                 tc05::tmem_ld32(tm_row + (go & 1u) * 256u + half * (BWD ? 64u : 32u), c);
                 if constexpr (BWD) {
@@ -370,11 +398,11 @@ mlp_kernel(const Params p)
                     tc05::tmem_ld_wait();
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
-                    float4 *dst = reinterpret_cast<float4 *>(p.tr.dx0 + slot * kFeat + half * 64);
+                    float *dst = p.tr.dx0 + slot * kFeat + half * 64;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) dst[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                    for (int q = 0; q < 4; q++) st_global_v8f(dst + 8 * q, &c[8 * q]);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) dst[8 + q] = make_float4(c2[4 * q], c2[4 * q + 1], c2[4 * q + 2], c2[4 * q + 3]);
+                    for (int q = 0; q < 4; q++) st_global_v8f(dst + 32 + 8 * q, &c2[8 * q]);
                     continue;
                 }
                 tc05::tmem_ld_wait();
@@ -397,9 +425,9 @@ mlp_kernel(const Params p)
                     Dsum = fmaf(w, sm.depth, Dsum);
                     if constexpr (TRAIN) {   // what the compositing backward needs: sigma, scaled interval, colour head output
                         if (half == 0) { p.tr.sig[slot] = sigma; p.tr.nds[slot] = __fmul_rn(sm.nd, p.dists_scale); }
-                        float4 *cd = reinterpret_cast<float4 *>(p.tr.c + slot * kOutC + half * 32);
+                        float *cd = p.tr.c + slot * kOutC + half * 32;
 #pragma unroll
-                        for (int q = 0; q < 8; q++) cd[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                        for (int q = 0; q < 4; q++) st_global_v8f(cd + 8 * q, &c[8 * q]);
                     }
                     if (half == 0 && valid) {
                         if (p.weights_out) p.weights_out[ray * S + s] = w;
@@ -474,7 +502,7 @@ mlp_kernel(const Params p)
             uint32_t n = 0;
             for (int it = 0; it < n_iter; it++) {
                 const int work = blockIdx.x + it * gridDim.x;
-                const int tile = SKY ? work : p.tile_list[work];
+                const int tile = ONE_STEP ? work : p.tile_list[work];
                 const TileCoord tc = tile_coord(p, tile);
                 const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
                 for (int s = 0; s < S; s++, n++) {
@@ -606,7 +634,7 @@ mlp_kernel(const Params p)
         uint32_t n = 0;
         for (int it = 0; it < n_iter; it++) {
             const int work = blockIdx.x + it * gridDim.x;
-            const int tile = SKY ? work : p.tile_list[work];
+            const int tile = ONE_STEP ? work : p.tile_list[work];
             const TileCoord tc = tile_coord(p, tile);
             const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
             const bool valid = (y < p.H) && (x < p.W);
@@ -640,6 +668,16 @@ mlp_kernel(const Params p)
                         const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&pe[8 * c]);
                         split8<PREC>(v8, ch[c], cl[c]);
                     }
+                    if constexpr (TRAIN) {   // bf16 copy of the layer-0 operand: X0[slot][48] (fc1 weight / bias gradient)
+                        uint16_t *dst = p.tr.x0 + ((long long)work * kRows + row) * kSkyK0;
+#pragma unroll
+                        for (int q = 0; q < 3; q++)
+                            st_global_v8(dst + 16 * q,
+                                         make_uint4(tc05::pack2<true>(pe[16 * q], pe[16 * q + 1]), tc05::pack2<true>(pe[16 * q + 2], pe[16 * q + 3]),
+                                                    tc05::pack2<true>(pe[16 * q + 4], pe[16 * q + 5]), tc05::pack2<true>(pe[16 * q + 6], pe[16 * q + 7])),
+                                         make_uint4(tc05::pack2<true>(pe[16 * q + 8], pe[16 * q + 9]), tc05::pack2<true>(pe[16 * q + 10], pe[16 * q + 11]),
+                                                    tc05::pack2<true>(pe[16 * q + 12], pe[16 * q + 13]), tc05::pack2<true>(pe[16 * q + 14], pe[16 * q + 15])));
+                    }
                 }
                 if (gt == 0) SDB_MARK(4, 3, n, it);
                 if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
@@ -656,16 +694,22 @@ mlp_kernel(const Params p)
                 n++;
             } else if constexpr (BWD) {
                 // ---- layer-0 operand of the gradient chain: dL/dc [128 rays x 64] fp32 from the compositing backward ----
-                (void)valid; (void)ray;
                 for (int s = 0; s < S; s++, n++) {
                     const long long slot = ((long long)work * S + s) * kRows + row;
-                    const float4 *src = reinterpret_cast<const float4 *>(p.tr.dc + slot * kOutC + half * 32);
+                    // render chain: dL/dc in slot order; sky chain: dL/dsky in RAY order (zero outside the image)
+                    const float4 *src = reinterpret_cast<const float4 *>(p.tr.dc + (SKYBWD ? ray : slot) * kOutC + half * 32);
+                    const bool have = SKYBWD ? valid : true;
                     uint4 gh[4], gl[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const float4 a = __ldg(src + 2 * q), b = __ldg(src + 2 * q + 1);
+                        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a;
+                        if (have) { a = __ldg(src + 2 * q); b = __ldg(src + 2 * q + 1); }
                         const float v8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                         split8<PREC>(v8, gh[q], gl[q]);
+                        if constexpr (SKYBWD)     // bf16 copy in slot order: operand of the fc_out_c weight-gradient GEMM
+                            *reinterpret_cast<uint4 *>(p.tr.dc16 + slot * kOutC + half * 32 + 8 * q) =
+                                make_uint4(tc05::pack2<true>(a.x, a.y), tc05::pack2<true>(a.z, a.w), tc05::pack2<true>(b.x, b.y),
+                                           tc05::pack2<true>(b.z, b.w));
                     }
                     if (gt == 0) SDB_MARK(4, 3, n, it);
                     if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
@@ -1012,6 +1056,8 @@ int launch_mlp(const Params &p, int grid, cudaStream_t st) {
 
 int launch_train_forward(const Params &p, int grid, cudaStream_t st) { return launch_mlp<2, false, kRender, true>(p, grid, st); }
 int launch_bwd_chain(const Params &p, int grid, cudaStream_t st) { return launch_mlp<1, false, kBwd>(p, grid, st); }
+int launch_sky_train_forward(const Params &p, int grid, cudaStream_t st) { return launch_mlp<2, false, kSky, true>(p, grid, st); }
+int launch_sky_bwd_chain(const Params &p, int grid, cudaStream_t st) { return launch_mlp<1, false, kSkyBwd>(p, grid, st); }
 int launch_prepass(const Params &p, int32_t *ws, cudaStream_t st) {
     SDB_CUDA(cudaMemsetAsync(ws, 0, 16, st));
     prepass_kernel<<<p.n_tiles, kRows, 0, st>>>(p, ws + 4, ws);
@@ -1022,10 +1068,12 @@ int launch_prepass(const Params &p, int32_t *ws, cudaStream_t st) {
 // ---- weight packer of the gradient chain (kBwd): B operands are the transposed forward weights -------
 //   layer 0 [256 x 64]: B[n][k] = fc_out_c.weight[k][n];  layers 1..5 [256 x 256]: B[n][k] = W'_{fc_(7-l)}[k][n]
 //   (wh[5-l], the style-modulated weight);  layer 6 [128 x 256]: B[n][k] = fc_1.weight[k][n];  fp32 tail: fc_sigma.weight
+//   sky chain (kSkyBwd): layer 0 [256 x 64]: fc_out_c^T; layers 1..4 [256 x 256]: fc5^T .. fc2^T (wh[4-l]); no tail
+template <int MODE>
 __global__ void __launch_bounds__(256)
 pack_bwd_kernel(const float *w1, const float *wh, const float *wsig, const float *wout, uint8_t *pack)
 {
-    constexpr int MODE = kBwd, PARTS = 2, NL = Net<MODE>::NL;
+    constexpr int PARTS = 2, NL = Net<MODE>::NL;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long nW = 0;
     for (int l = 0; l < NL; l++) nW += (long long)layerK<MODE>(l) * layerN<MODE>(l);
@@ -1037,8 +1085,8 @@ pack_bwd_kernel(const float *w1, const float *wh, const float *wsig, const float
         const int nn = (int)(r / K), k = (int)(r % K);
         float v;
         if (l == 0) v = wout[(long long)k * kHidden + nn];
-        else if (l == NL - 1) v = w1[(long long)k * kFeat + nn];
-        else v = wh[((long long)(5 - l) * kHidden + k) * kHidden + nn];
+        else if (MODE == kBwd && l == NL - 1) v = w1[(long long)k * kFeat + nn];
+        else v = wh[((long long)((MODE == kBwd ? 5 : 4) - l) * kHidden + k) * kHidden + nn];
         const int kk = k >> 4, k16 = k & 15;
         const long long slab_off = (long long)(k16 >> 3) * N * 16 + (nn >> 3) * 128 + (nn & 7) * 16 + (k16 & 7) * 2;
         uint8_t *base = pack + layerOff<MODE>(l, PARTS) + (long long)kk * N * 32 * PARTS;
@@ -1048,6 +1096,7 @@ pack_bwd_kernel(const float *w1, const float *wh, const float *wsig, const float
         *reinterpret_cast<__nv_bfloat16 *>(base + (long long)N * 32 + slab_off) = lo;
         return;
     }
+    if (!Net<MODE>::TAIL) return;
     const long long u = t - nW;
     if (u >= kFTotal) return;
     float *F = reinterpret_cast<float *>(pack + layerOff<MODE>(NL, PARTS));
@@ -1081,7 +1130,20 @@ extern "C" int sdb_pack_mlp_backward(const float *d_w1, const float *d_wh, const
     if (!d_w1 || !d_wh || !d_wsig || !d_wout || !d_pack) return SDB_EINVAL;
     long long n = kFTotal;
     for (int l = 0; l < Net<kBwd>::NL; l++) n += (long long)layerK<kBwd>(l) * layerN<kBwd>(l);
-    pack_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_w1, d_wh, d_wsig, d_wout, (uint8_t *)d_pack);
+    pack_bwd_kernel<kBwd><<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_w1, d_wh, d_wsig, d_wout, (uint8_t *)d_pack);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}
+
+extern "C" int64_t sdb_sky_backward_pack_bytes(void) { return rf::packBytes<rf::kSkyBwd>(2); }
+
+extern "C" int sdb_pack_sky_mlp_backward(const float *d_wh, const float *d_wout, void *d_pack, void *stream)
+{
+    using namespace rf;
+    if (!d_wh || !d_wout || !d_pack) return SDB_EINVAL;
+    long long n = 0;
+    for (int l = 0; l < Net<kSkyBwd>::NL; l++) n += (long long)layerK<kSkyBwd>(l) * layerN<kSkyBwd>(l);
+    pack_bwd_kernel<kSkyBwd><<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nullptr, d_wh, nullptr, d_wout, (uint8_t *)d_pack);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
@@ -1120,14 +1182,16 @@ extern "C" int64_t sdb_sky_workspace_bytes(int32_t n_img, int32_t H, int32_t W) 
     return sdb_num_tiles(n_img, H, W) * rf::kOutC * 4;
 }
 
-extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
-                               int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
-                               void *stream)
+// sky forward, optionally (record != nullptr, fp16x3 only) leaving the training record of the pass
+static int sky_forward_impl(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
+                            int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
+                            void *d_record, void *stream)
 {
     using namespace rf;
     if (!d_raydirs || !d_sky_pack || !d_sky || !d_sky_avg || !d_workspace) return SDB_EINVAL;
     if (n_img <= 0 || H <= 0 || W <= 0) return SDB_EINVAL;
     if (precision < 0 || precision > 2) return SDB_EUNSUPPORTED;
+    if (d_record && (precision != 2 || n_img != 1)) return SDB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     Params p{};
     p.n_img = n_img; p.H = H; p.W = W; p.M = 1; p.S = 1;
@@ -1139,13 +1203,40 @@ extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H,
     p.n_tiles = n_img * p.tiles_x * p.tiles_y;
     const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
     int rc;
-    if (precision == 1) rc = launch_mlp<1, false, kSky>(p, grid, st);
+    if (d_record) {
+        const SkyRecordLayout rl = sky_record_layout(p.n_tiles);
+        uint8_t *rec = (uint8_t *)d_record;
+        p.tr.slot_cap = (long long)p.n_tiles * kRows;
+        p.tr.x0 = reinterpret_cast<uint16_t *>(rec + rl.x0);
+        p.tr.act = reinterpret_cast<uint16_t *>(rec + rl.act);
+        p.tr.mask = reinterpret_cast<uint32_t *>(rec + rl.mask);
+        rc = launch_sky_train_forward(p, grid, st);
+    } else if (precision == 1) rc = launch_mlp<1, false, kSky>(p, grid, st);
     else if (precision == 2) rc = launch_mlp<2, false, kSky>(p, grid, st);
     else rc = launch_mlp<0, false, kSky>(p, grid, st);
     if (rc != SDB_OK) return rc;
     sky_mean_kernel<<<n_img, kOutC * kMeanGroups, 0, st>>>(p.sky_partial, d_sky_avg, p.tiles_x * p.tiles_y, 1.0f / ((float)H * (float)W));
     SDB_CHECK_LAUNCH();
     return SDB_OK;
+}
+
+extern "C" int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
+                               int64_t pack_stride, int32_t precision, float *d_sky, float *d_sky_avg, void *d_workspace,
+                               void *stream)
+{
+    return sky_forward_impl(d_raydirs, n_img, H, W, d_sky_pack, pack_stride, precision, d_sky, d_sky_avg, d_workspace, nullptr, stream);
+}
+
+extern "C" int64_t sdb_sky_train_record_bytes(int32_t n_img, int32_t H, int32_t W) {
+    if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+    return (int64_t)rf::sky_record_layout(sdb_num_tiles(n_img, H, W)).total;
+}
+
+extern "C" int sdb_sky_train_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W, const void *d_sky_pack,
+                                     float *d_sky, float *d_sky_avg, void *d_workspace, void *d_record, void *stream)
+{
+    if (!d_record) return SDB_EINVAL;
+    return sky_forward_impl(d_raydirs, n_img, H, W, d_sky_pack, 0, 2, d_sky, d_sky_avg, d_workspace, d_record, stream);
 }
 
 namespace rf {

@@ -26,7 +26,7 @@ namespace rf {
 
 // ---- record / workspace layouts --------------------------------------------------------------------
 struct RecordLayout { size_t hdr, tile_list, tile_work, rayflags, x3, x0, act, mask, sig, nds, c, total; };
-static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
+static size_t align_up(size_t v) { return rf_align_up(v); }
 static RecordLayout record_layout(long long n_tiles, int S) {
     const size_t cap = (size_t)n_tiles * S * kRows, steps = (size_t)n_tiles * S;
     RecordLayout r{};
@@ -511,4 +511,55 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         if (rc != SDB_OK) return rc;
     }
     return SDB_OK;
+}
+
+// ---- sky branch (a9) backward: SKYMLP data-gradient chain on the tensor-core engine + weight-gradient GEMMs -------------
+// (gancraft_base.py:150-169 under autograd; the positional encoding of the ray direction needs no gradient)
+extern "C" int64_t sdb_sky_backward_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
+    using namespace rf;
+    if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+    return (int64_t)sky_bwd_layout((long long)n_img * sdb_div_up(H, kTileH) * sdb_div_up(W, kTileW)).total;
+}
+
+extern "C" int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void *d_record, const float *d_grad_sky,
+                                const void *d_bwd_pack, float *d_grad_w1ext, float *d_grad_wh, float *d_grad_wout,
+                                void *d_workspace, void *stream)
+{
+    using namespace rf;
+    if (!d_record || !d_grad_sky || !d_bwd_pack || !d_grad_w1ext || !d_grad_wh || !d_grad_wout || !d_workspace) return SDB_EINVAL;
+    if (n_img != 1 || H <= 0 || W <= 0) return n_img == 1 ? SDB_EINVAL : SDB_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    Params p{};
+    p.n_img = n_img; p.H = H; p.W = W; p.M = 1; p.S = 1;
+    p.tiles_x = sdb_div_up(W, kTileW); p.tiles_y = sdb_div_up(H, kTileH);
+    p.n_tiles = n_img * p.tiles_x * p.tiles_y;
+    p.pack = (const uint8_t *)d_bwd_pack; p.pack_stride = 0;
+    p.debug = g_debug_buffer;
+    const SkyRecordLayout rl = sky_record_layout(p.n_tiles);
+    const SkyBwdLayout bl = sky_bwd_layout(p.n_tiles);
+    uint8_t *rec = (uint8_t *)const_cast<void *>(d_record), *ws = (uint8_t *)d_workspace;
+    const long long cap = (long long)p.n_tiles * kRows;
+    p.tr.slot_cap = cap;
+    p.tr.x0 = reinterpret_cast<uint16_t *>(rec + rl.x0);
+    p.tr.act = reinterpret_cast<uint16_t *>(rec + rl.act);
+    p.tr.mask = reinterpret_cast<uint32_t *>(rec + rl.mask);
+    p.tr.dc = d_grad_sky;
+    p.tr.dc16 = reinterpret_cast<uint16_t *>(ws + bl.dc16);
+    p.tr.dz = reinterpret_cast<uint16_t *>(ws + bl.dz);
+    {
+        const int grid = p.n_tiles < sdb_num_sms() ? p.n_tiles : sdb_num_sms();
+        const int rc = launch_sky_bwd_chain(p, grid, st);
+        if (rc != SDB_OK) return rc;
+    }
+    cublasHandle_t h;
+    int rc = cublas_for_stream(st, &h);
+    if (rc != SDB_OK) return rc;
+    rc = wgrad(h, p.tr.x0, kSkyK0, kSkyK0, p.tr.dz, kHidden, kHidden, cap, d_grad_w1ext);                                       // fc1 | bias
+    if (rc != SDB_OK) return rc;
+    for (int k = 0; k < 4; k++) {                                                                                               // fc2 .. fc5
+        rc = wgrad(h, p.tr.act + (size_t)k * cap * kActCols, kActCols, kActCols, p.tr.dz + (size_t)(k + 1) * cap * kHidden, kHidden,
+                   kHidden, cap, d_grad_wh + (size_t)k * kHidden * kActCols);
+        if (rc != SDB_OK) return rc;
+    }
+    return wgrad(h, p.tr.act + (size_t)4 * cap * kActCols, kActCols, kActCols, p.tr.dc16, kOutC, kOutC, cap, d_grad_wout);      // fc_out_c
 }

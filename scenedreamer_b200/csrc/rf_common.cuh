@@ -38,14 +38,19 @@ constexpr int kRenderK0 = kFeat + kKExt;        // 144
 //   kSky   : SKYMLP forward, 5 hidden layers + colour head (gancraft_base.py:150-169)
 //   kBwd   : data-gradient chain of LightningMLP: dC -> dA6 -> ... -> dA1 -> d(features); the B operands are
 //            the TRANSPOSED forward weights, there is no K extension (biases do not enter the data gradient)
-constexpr int kRender = 0, kSky = 1, kBwd = 2;
+//   kSkyBwd: data-gradient chain of SKYMLP: dSky -> dA5 -> ... -> dA1 (the PE input needs no gradient), so there are
+//            4 operand-producing layers and the last layer's output (dA1 -> dZ1, N = 256) only goes to the record
+constexpr int kRender = 0, kSky = 1, kBwd = 2, kSkyBwd = 3;
 template <int MODE> struct Net {
-    static constexpr int NH = MODE == kSky ? 5 : 6;
+    static constexpr bool ISBWD = MODE == kBwd || MODE == kSkyBwd;
+    static constexpr int NH = MODE == kSky ? 5 : (MODE == kSkyBwd ? 4 : 6);   // layers whose epilogue feeds the next layer
     static constexpr int NL = NH + 1;
-    static constexpr int K0 = MODE == kSky ? kSkyK0 : (MODE == kBwd ? kOutC : kRenderK0);
-    static constexpr bool EXT = MODE != kBwd;               // hidden operands carry the 16-column K extension
+    static constexpr int K0 = MODE == kSky ? kSkyK0 : (ISBWD ? kOutC : kRenderK0);
+    static constexpr bool EXT = !ISBWD;                     // hidden operands carry the 16-column K extension
     static constexpr int KH = EXT ? kKH : kHidden;          // K of the layers fed by hidden activations
-    static constexpr int NOUT = MODE == kBwd ? kFeat : kOutC;   // N of the last layer
+    static constexpr int NOUT = MODE == kBwd ? kFeat : (MODE == kSkyBwd ? kHidden : kOutC);   // N of the last layer
+    static constexpr int NACT = MODE == kSky || MODE == kSkyBwd ? 5 : 6;   // hidden activations of the forward network
+    static constexpr bool TAIL = MODE == kRender || MODE == kBwd;          // the pack ends with the fp32 sigma head
 };
 template <int MODE> __host__ __device__ constexpr int layerK(int l) { return l == 0 ? Net<MODE>::K0 : Net<MODE>::KH; }
 template <int MODE> __host__ __device__ constexpr int layerN(int l) { return l == Net<MODE>::NL - 1 ? Net<MODE>::NOUT : kHidden; }
@@ -57,7 +62,7 @@ template <int MODE> __host__ __device__ constexpr int64_t layerOff(int l, int pa
 // fp32 tail of the render / backward packs: sigma head
 constexpr int kFWsig = 0, kFBsig = 256, kFTotal = 264;
 template <int MODE> __host__ __device__ constexpr int64_t packBytes(int parts) {
-    return layerOff<MODE>(Net<MODE>::NL, parts) + (MODE == kSky ? 0 : (int64_t)kFTotal * 4);
+    return layerOff<MODE>(Net<MODE>::NL, parts) + (Net<MODE>::TAIL ? (int64_t)kFTotal * 4 : 0);
 }
 // Weight-ring schedule.  A ring stage holds KS consecutive k16 slabs (KS = 1 for the x3 modes, 2 for the
 // single-pass mode so that a stage is 16 KB either way).  Layers fed by hidden activations consume the K
@@ -143,20 +148,21 @@ static_assert(B_COUNT <= 32, "barrier table");
 // position of the ray tile in the live-tile list of the forward launch.  Every slot of a live tile is written
 // (rows outside the image / sky-only rays included), so the backward GEMMs may run over [0, n_live*S*128).
 constexpr int kX0Cols = kRenderK0;           // 144: features | one-hot label | 1
-constexpr int kActCols = kHidden + 8;        // 264: activations | 1 | 0 x 7  (the 1 makes the wgrad GEMM emit the bias grad)
+constexpr int kActCols = kHidden + 16;       // 272: activations | 1 | 0 x 15 (the 1 makes the wgrad GEMM emit the bias grad; 544 B rows stay 32 B aligned)
 constexpr int kNumAct = 6;
 struct TrainBuf {
     long long slot_cap;        // slots the buffers were sized for (n_tiles * S * 128)
     float4 *x3;                // [slots] (x, y, z in [0,1], w = +1 inside / -1 skip in the table backward)
-    uint16_t *x0;              // [slots][144] bf16
-    uint16_t *act;             // [6][slot_cap][264] bf16: A1..A6
+    uint16_t *x0;              // [slots][144] bf16 (render) / [slots][48] bf16 (sky: PE(raydir) | 0 | 1)
+    uint16_t *act;             // [6][slot_cap][272] bf16: A1..A6
     uint32_t *mask;            // [steps][6][128][8]: bit j of word q = (A[., 32q + j] > 0)
     float *sig, *nds;          // [slots] sigma (pre-relu), new_dists * dists_scale
     float *c;                  // [slots][64] colour head output (pre-clamp)
     uint32_t *rayflags;        // [n_live*128]: bit0 live, bit1 nosky, bit2 valid
     int32_t *tile_work;        // [n_tiles]: position in the live list or -1
     // backward chain
-    const float *dc;           // [slots][64] fp32
+    const float *dc;           // [slots][64] fp32 (render) / [R][64] fp32 in RAY order (sky: dL/dsky)
+    uint16_t *dc16;            // sky only: [slots][64] bf16 copy of dL/dsky written by the chain's operand producer
     const float *dsig;         // [slots]
     uint16_t *dz;              // [6][slot_cap][256] bf16: dZ1..dZ6
     float *dx0;                // [slots][128]
@@ -213,6 +219,20 @@ __device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile) {
     return t;
 }
 
+// 256-bit global store (STG.256): a thread's 32 contiguous bytes in ONE instruction -- the per-row record writes of
+// the training kernels touch 32 different lines per warp instruction, so halving the instruction count halves the
+// LSU work.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void *p, uint4 a, uint4 b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_v8f(float *p, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ void ld8(const float *g, float (&v)[8]) {
     const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
     const float4 b = __ldg(reinterpret_cast<const float4 *>(g) + 1);
@@ -248,9 +268,35 @@ __device__ __forceinline__ Corners3 corners3(uint32_t mask, float scale, const f
     return c;
 }
 
+// record of a sky training forward (slot = tile * 128 + row over ALL tiles of the frame) and workspace of its backward
+struct SkyRecordLayout { size_t x0, act, mask, total; };
+static inline size_t rf_align_up(size_t v) { return (v + 255) / 256 * 256; }
+static inline SkyRecordLayout sky_record_layout(long long n_tiles) {
+    const size_t cap = (size_t)n_tiles * kRows;
+    SkyRecordLayout r{};
+    size_t o = 0;
+    r.x0 = o; o = rf_align_up(o + cap * kSkyK0 * 2);
+    r.act = o; o = rf_align_up(o + (size_t)Net<kSky>::NACT * cap * kActCols * 2);
+    r.mask = o; o = rf_align_up(o + (size_t)n_tiles * kNumAct * kRows * 8 * 4);
+    r.total = o;
+    return r;
+}
+struct SkyBwdLayout { size_t dc16, dz, total; };
+static inline SkyBwdLayout sky_bwd_layout(long long n_tiles) {
+    const size_t cap = (size_t)n_tiles * kRows;
+    SkyBwdLayout b{};
+    size_t o = 0;
+    b.dc16 = o; o = rf_align_up(o + cap * kOutC * 2);
+    b.dz = o; o = rf_align_up(o + (size_t)Net<kSky>::NACT * cap * kHidden * 2);
+    b.total = o;
+    return b;
+}
+
 // launchers implemented in render_fused.cu, used by render_train.cu
 int launch_train_forward(const Params &p, int grid, cudaStream_t st);     // mlp_kernel<fp16x3, table3, kRender, TRAIN>
 int launch_bwd_chain(const Params &p, int grid, cudaStream_t st);         // mlp_kernel<bf16x3, -, kBwd>
+int launch_sky_train_forward(const Params &p, int grid, cudaStream_t st); // mlp_kernel<fp16x3, -, kSky, TRAIN>
+int launch_sky_bwd_chain(const Params &p, int grid, cudaStream_t st);     // mlp_kernel<bf16x3, -, kSkyBwd>
 int launch_prepass(const Params &p, int32_t *ws, cudaStream_t st);        // zeroes the counter, fills tile list (+ tile_work)
 int params_from_abi(const sdb_render_params *sp, Params &p);        // validate + translate the ABI struct
 extern int32_t *g_debug_buffer;

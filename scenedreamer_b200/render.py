@@ -404,9 +404,9 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             g_table = torch.empty_like(embeddings_)
             g_genc = torch.empty(2, dtype=torch.float32, device=dev)
             g_w1ext = torch.empty(256, 144, dtype=torch.float32, device=dev)
-            g_wh = torch.empty(5, 256, 264, dtype=torch.float32, device=dev)
-            g_wsig = torch.empty(8, 264, dtype=torch.float32, device=dev)
-            g_wout = torch.empty(64, 264, dtype=torch.float32, device=dev)
+            g_wh = torch.empty(5, 256, 272, dtype=torch.float32, device=dev)
+            g_wsig = torch.empty(8, 272, dtype=torch.float32, device=dev)
+            g_wout = torch.empty(64, 272, dtype=torch.float32, device=dev)
             g_sky = torch.zeros(N, H, W, 64, dtype=torch.float32, device=dev)
             g_sky_avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
             wsb = torch.empty(int(L.sdb_render_backward_workspace_bytes(N, H, W, S, int(cfg['L']), int(cfg['log2_T']))),
@@ -431,15 +431,76 @@ class _FusedRenderTrainFn(torch.autograd.Function):
                 g_sky.reshape(s_sky), g_sky_avg.reshape(s_skyavg))
 
 
+class _SkyTrainFn(torch.autograd.Function):
+    """sky [1,H,W,64] = SKYMLP(PE(raydirs)) on the tcgen05 engine, differentiable w.r.t. the weights.
+    b1 is the effective layer-0 bias fc1.bias + fc_z_a(z) (gancraft_base.py:159-160), formed by the caller in torch."""
+
+    @staticmethod
+    def forward(ctx, raydirs, w1, b1, wh, bh, wout, bout):
+        L = _lib.lib()
+        dev = raydirs.device
+        N, H, W = raydirs.shape[:3]
+        if N != 1:
+            raise RuntimeError('fused sky training path renders one view per call')
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        w1_, b1_, wh_, bh_, wout_, bout_ = f32(w1), f32(b1).reshape(-1), f32(wh), f32(bh), f32(wout), f32(bout)
+        rd = raydirs.detach().contiguous()
+        with torch.cuda.device(dev):
+            pack = torch.empty(int(L.sdb_sky_pack_bytes(PRECISION_FP16X3)), dtype=torch.uint8, device=dev)
+            _lib.check(L.sdb_pack_sky_mlp(_ptr(w1_), _ptr(b1_), _ptr(wh_), _ptr(bh_), _ptr(wout_), _ptr(bout_), PRECISION_FP16X3,
+                                          _ptr(pack), _stream(dev)), 'sdb_pack_sky_mlp')
+            sky = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
+            avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
+            ws = torch.empty(int(L.sdb_sky_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+            record = torch.empty(int(L.sdb_sky_train_record_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+            _lib.check(L.sdb_sky_train_forward(_ptr(rd), N, H, W, _ptr(pack), _ptr(sky), _ptr(avg), _ptr(ws), _ptr(record),
+                                               _stream(dev)), 'sdb_sky_train_forward')
+        ctx.dims, ctx.record, ctx.saved = (N, H, W), record, (wh_, wout_)
+        ctx.shapes = (tuple(b1.shape),)
+        return sky
+
+    @staticmethod
+    def backward(ctx, g_sky):
+        L = _lib.lib()
+        N, H, W = ctx.dims
+        wh_, wout_ = ctx.saved
+        dev = wh_.device
+        g = g_sky.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            bpack = torch.empty(int(L.sdb_sky_backward_pack_bytes()), dtype=torch.uint8, device=dev)
+            _lib.check(L.sdb_pack_sky_mlp_backward(_ptr(wh_), _ptr(wout_), _ptr(bpack), _stream(dev)), 'sdb_pack_sky_mlp_backward')
+            g_w1ext = torch.empty(256, 48, dtype=torch.float32, device=dev)
+            g_wh = torch.empty(4, 256, 272, dtype=torch.float32, device=dev)
+            g_wout = torch.empty(64, 272, dtype=torch.float32, device=dev)
+            wsb = torch.empty(int(L.sdb_sky_backward_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+            _lib.check(L.sdb_sky_backward(N, H, W, _ptr(ctx.record), _ptr(g), _ptr(bpack), _ptr(g_w1ext), _ptr(g_wh), _ptr(g_wout),
+                                          _ptr(wsb), _stream(dev)), 'sdb_sky_backward')
+        return (None, g_w1ext[:, :33].contiguous(), g_w1ext[:, 47].reshape(ctx.shapes[0]), g_wh[:, :, :256].contiguous(),
+                g_wh[:, :, 256].contiguous(), g_wout[:, :256].contiguous(), g_wout[:, 256].contiguous())
+
+
+def sky_features_train(P, raydirs, z, prefix='sky_net'):
+    """Differentiable a9 on the tensor-core engine: gradients reach P['sky_net.*'] and z [1,256]."""
+    p = prefix + '.'
+    b1 = P[p + 'fc1.bias'] + F.linear(z, P[p + 'fc_z_a.weight'])[0]                       # gancraft_base.py:159-160
+    wh = torch.stack([P[p + 'fc%d.weight' % k] for k in (2, 3, 4, 5)])
+    bh = torch.stack([P[p + 'fc%d.bias' % k] for k in (2, 3, 4, 5)])
+    return _SkyTrainFn.apply(raydirs, P[p + 'fc1.weight'], b1, wh, bh, P[p + 'fc_out_c.weight'], P[p + 'fc_out_c.bias'])
+
+
 def render_rays_train(P, voxel_id, depth2, raydirs, cam_ori, z, global_enc, voxel_dims, label_lut, per_level_scale,
                       num_samples=24, sample_depth=3.0, dists_scale=0.25, uniforms=None, base_res=16, log2_T=19, L=16,
-                      prefix='render_net', sky_prefix='sky_net'):
+                      prefix='render_net', sky_prefix='sky_net', sky_impl='native'):
     """Differentiable fused a2-a12 for ONE view: gradients reach P['hash_encoder.embeddings'], P['render_net.*'],
     P['sky_net.*'], z [1,256] and global_enc [1,2] (everything Generator._forward_perpix differentiates under train.py).
-    The sky branch (3 % of the FLOPs, per ray) runs through torch autograd / cuBLAS on top of the PE kernel."""
+    sky_impl: 'native' = the sky branch on the tensor-core engine too (sky_features_train), 'torch' = torch autograd /
+    cuBLAS fp32 on top of the PE kernel (independent cross-check)."""
     p = prefix + '.'
     wh, bh = modulated_weights(P, z[0], prefix)                            # differentiable w.r.t. P and z
-    sky = sky_features(P, raydirs, z, prefix=sky_prefix)                   # [1,H,W,64]
+    if sky_impl == 'native':
+        sky = sky_features_train(P, raydirs, z, prefix=sky_prefix)         # [1,H,W,64]
+    else:
+        sky = sky_features(P, raydirs, z, prefix=sky_prefix)
     sky_avg = sky.mean(dim=(1, 2))                                         # scenedreamer.py:395
     cfg = dict(voxel_id=voxel_id, depth2=depth2, raydirs=raydirs, cam_ori=cam_ori, lut=label_lut, voxel_dims=voxel_dims,
                num_samples=num_samples, sample_depth=sample_depth, dists_scale=dists_scale, uniforms=uniforms,

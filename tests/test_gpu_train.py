@@ -42,7 +42,8 @@ def _leaf(P, dev):
 
 GRAD_KEYS = ['hash_encoder.embeddings', 'render_net.fc_1.weight', 'render_net.fc_1.bias', 'render_net.fc_m_a.weight',
              'render_net.fc_sigma.weight', 'render_net.fc_sigma.bias', 'render_net.fc_out_c.weight', 'render_net.fc_out_c.bias',
-             'sky_net.fc1.weight', 'sky_net.fc_z_a.weight', 'sky_net.fc5.weight', 'sky_net.fc_out_c.weight'] + \
+             'sky_net.fc1.weight', 'sky_net.fc1.bias', 'sky_net.fc_z_a.weight', 'sky_net.fc2.weight', 'sky_net.fc3.bias',
+             'sky_net.fc5.weight', 'sky_net.fc_out_c.weight', 'sky_net.fc_out_c.bias'] + \
             ['render_net.fc_%d.%s' % (k, n) for k in (2, 3, 4, 5, 6) for n in ('weight', 'weight_alpha', 'bias_alpha',
                                                                                 'weight_beta', 'bias_beta')]
 
@@ -109,8 +110,37 @@ def test_train_forward_equals_inference_forward(scene, golden_ops):
         tr = render.render_rays_train(P, sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), z, genc,
                                       list(sc['world'].voxel_t.shape), lut, pls)
     r = render.FusedPerPixelRenderer(P, sc['world'].voxel_t.shape, lut, pls)
-    r.sky_impl = 'torch'
     inf = r.forward(sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), z, genc, want_samples=True)
     torch.cuda.synchronize()
-    for k in ('net_out', 'depth', 'total_weight', 'weights', 'rand_depth'):
+    for k in ('depth', 'total_weight', 'weights', 'rand_depth'):
         assert torch.equal(tr[k], inf[k]), k
+    assert torch.equal(tr['sky'], inf['sky'])                # recording and plain sky kernels: same arithmetic
+    # net_out additionally sees the frame mean of the sky features (torch reduction here, sky_mean_kernel there)
+    assert float((tr['net_out'] - inf['net_out']).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize('sky_impl', ['torch'])
+def test_train_sky_torch_crosscheck(scene, golden_ops, sky_impl):
+    """The torch/cuBLAS sky branch stays available as an independent cross-check of the native one."""
+    sc = scene
+    P = {k: v.to(DEV).requires_grad_(True) for k, v in oracle.make_params(seed=3, stress=True).items()}
+    g = torch.Generator().manual_seed(1)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), {k: v.detach().cpu() for k, v in P.items()}).to(DEV).requires_grad_(True)
+    genc = torch.tanh(torch.randn(1, 2, generator=g)).to(DEV)
+    lut = render.reduced_label_lut(golden_ops['mc2reduced_lut'], 0, 3)
+    _, pls = oracle.grid_offsets()
+    G = torch.randn(1, *sc['vid'].shape[1:3], 64, generator=torch.Generator().manual_seed(3)).to(DEV)
+    grads = {}
+    for impl in ('native', sky_impl):
+        for t in list(P.values()) + [z]:
+            t.grad = None
+        out = render.render_rays_train(P, sc['vid'], sc['dep'], sc['rd'], sc['o'].unsqueeze(0), z, genc,
+                                       list(sc['world'].voxel_t.shape), lut, pls, sky_impl=impl)
+        (out['net_out'] * G).sum().backward()
+        grads[impl] = {k: P[k].grad.clone() for k in P if k.startswith('sky_net.')}
+        grads[impl]['z'] = z.grad.clone()
+    for k in grads['native']:
+        a, b = grads['native'][k].double(), grads[sky_impl][k].double()
+        rel = float((a - b).norm() / (b.norm() + 1e-30))
+        print('sky %-28s native vs %s rel-L2 %.3e' % (k, sky_impl, rel))
+        assert rel <= 1e-2, k

@@ -98,7 +98,7 @@ def main():
     rayflags = rv(lay[3], ntiles * 128 * 4, torch.int32)[:n_live * 128]
     x3 = rv(lay[4], cap * 16, torch.float32).reshape(cap, 4)[:nsl]
     x0 = rv(lay[5], cap * 288, torch.bfloat16).reshape(cap, 144)[:nsl].float()
-    act = rv(lay[6], 6 * cap * 528, torch.bfloat16).reshape(6, cap, 264)[:, :nsl].float()
+    act = rv(lay[6], 6 * cap * 544, torch.bfloat16).reshape(6, cap, 272)[:, :nsl].float()
     mask = rv(lay[7], steps * 6 * 128 * 8 * 4, torch.int32).reshape(steps, 6, 128, 8)[:n_live * S]
     sig = rv(lay[8], cap * 4, torch.float32)[:nsl]
     nds = rv(lay[9], cap * 4, torch.float32)[:nsl]
@@ -152,9 +152,9 @@ def main():
     g_table = torch.empty_like(embeddings_)
     g_genc = torch.empty(2, device=DEV)
     g_w1ext = torch.empty(256, 144, device=DEV)
-    g_wh = torch.empty(5, 256, 264, device=DEV)
-    g_wsig = torch.empty(8, 264, device=DEV)
-    g_wout = torch.empty(64, 264, device=DEV)
+    g_wh = torch.empty(5, 256, 272, device=DEV)
+    g_wsig = torch.empty(8, 272, device=DEV)
+    g_wout = torch.empty(64, 272, device=DEV)
     g_sky = torch.zeros(N, H, W, 64, device=DEV)
     g_sky_avg = torch.empty(N, 64, device=DEV)
     wsb = torch.empty(lay[19], dtype=torch.uint8, device=DEV)
