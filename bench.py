@@ -179,6 +179,9 @@ class FrameRenderer:
         self.z, self.genc = z.to(device), genc.to(device)
         self.launches_per_frame = None
 
+    def set_early_stop(self, T):
+        self.r.early_stop = T
+
     def frame(self, cam, events=None, ori_dev=None):
         """cam = (ori, dir, up, f, c, res) with HOST tensors (the reference API takes the pose from the CPU and
         passes it by value to the DDA kernel); ori_dev: optional device-resident copy of ori for the fused kernel."""
@@ -208,6 +211,7 @@ def run_gpu_arm(args):
     precision = {'fp16': render.PRECISION_FP16, 'bf16x3': render.PRECISION_BF16X3, 'fp16x3': render.PRECISION_FP16X3}[args.precision]
     world, poses, P, z, genc, lut = build_workload(dev)
     fr = FrameRenderer(world, P, z, genc, lut, dev, precision)
+    fr.set_early_stop(0.0 if args.no_early_stop else None)
     cams = [synth.frame_camera(world, p, OUT_HW, PAD) for p in poses]
     # pinned host copies of the per-frame inputs (camera pose) and of the per-frame result
     pose_pinned = [torch.stack([c[0], c[1], c[2]]).pin_memory() for c in cams]
@@ -295,10 +299,12 @@ def run_gpu_arm(args):
         kern_s = tot_kern_ms * 1e-3 / args.steps
         achieved = SAMPLES_PER_FRAME * BYTES_PER_SAMPLE / kern_s / 1e9
         # executed tensor work: live 16x8 ray tiles x 24 steps x 128 rows, MMAs as issued (x3 split: 3 per product)
-        live_tiles = float(np.mean([int(fr.frame(cams[(k * world_size) % len(cams)], ori_dev=doris[(k * world_size) % len(cams)])
-                                        ['workspace'][:4].view(torch.int32)[0]) for k in range(min(args.steps, 8))]))
+        wss = [fr.frame(cams[(k * world_size) % len(cams)], ori_dev=doris[(k * world_size) % len(cams)])['workspace'][:8].view(torch.int32)
+               for k in range(min(args.steps, 8))]
+        live_tiles = float(np.mean([int(w[0]) for w in wss]))
+        steps_exec = float(np.mean([int(w[1]) for w in wss]))         # sample steps executed (tiles x steps, after early termination)
         mma_eq = {'fp16': (9 + 5 * 17 + 17 * 0.25), 'bf16x3': (27 + 5 * 50 + 50 * 0.25), 'fp16x3': (27 + 5 * 50 + 50 * 0.25)}[args.precision]
-        exec_tflops = live_tiles * SPP * mma_eq * (2.0 * 128 * 256 * 16) / kern_s / 1e12
+        exec_tflops = steps_exec * mma_eq * (2.0 * 128 * 256 * 16) / kern_s / 1e12
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tpath):
@@ -322,7 +328,11 @@ def run_gpu_arm(args):
             'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0, pad 30 '
                                    '(570x990 rays cast+shaded, 518400 px credited); one frame per GPU per step',
                        'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
-                       'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)'},
+                       'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)',
+                       'early_termination': ('off' if args.no_early_stop else
+                                             'ray tiles stop once every live ray has transmittance < %g (skipped samples carry less than '
+                                             'that compositing weight; credited like sky-only rays); --no-early-stop marches everything'
+                                             % render.EARLY_STOP_T)},
             'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
                     'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': tot_ms / args.steps,
                     'note': 'pose from pinned host memory -> DDA -> sky -> fused render -> depth+opacity maps to pinned host'},
@@ -341,7 +351,8 @@ def run_gpu_arm(args):
                                 'what': 'EXECUTED 16-bit MMA flops of rf::mlp_kernel<render> (live tiles x 24 steps x MMAs issued; the parity '
                                         'modes issue 3 MMAs per product) over the measured sustained cuBLAS bf16 rate',
                                 'algorithmic_tflops': SAMPLES_PER_FRAME * 754176 / kern_s / 1e12,
-                                'live_tiles_per_frame': live_tiles, 'peak_source': which + ' (bf16_tflops_sustained)'},
+                                'live_tiles_per_frame': live_tiles, 'tile_steps_executed_per_frame': steps_exec,
+                                'tile_steps_without_early_termination': live_tiles * SPP, 'peak_source': which + ' (bf16_tflops_sustained)'},
             'cpu_baseline': cpu, 'clocks': clocks, 'wall_s': t_wall,
             'collective': {'op': 'all_gather_into_tensor(depth+opacity maps)', 'bytes_per_rank': int(host_out.numel() * 4),
                            'ms_per_step_incl_wait_for_slowest_rank': float(np.mean(coll_ms))} if world_size > 1 else None,
@@ -359,6 +370,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='fp16x3', choices=['fp16', 'bf16x3', 'fp16x3'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-early-stop', action='store_true',
+                    help='march every sample of every live tile (early termination off; the reference arithmetic sample for sample)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -143,6 +143,11 @@ typedef struct sdb_render_params {
     float *d_rand_depth_out;     /* [R, S] sample depths after the NaN guard (:346-352) or NULL */
     /* scratch: sdb_render_workspace_bytes(n_img, H, W) bytes                                  */
     void *d_workspace;
+    /* early termination (sdb_render_rays_forward only): a 16x8 ray tile stops marching once the
+       transmittance exp(-sum e) of every live ray in it is below this value; the samples not
+       shaded have compositing weight < threshold (reported as 0 in d_weights_out).  0 = off =
+       the reference's arithmetic sample for sample.  The training forward ignores it.          */
+    float early_stop_transmittance;
 } sdb_render_params;
 
 int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W);

@@ -184,11 +184,19 @@ mlp_kernel(const Params p)
     float *sState = reinterpret_cast<float *>(smem + SM.state);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM.bars);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM.tmem_slot);
+    // Early termination (north star: "early termination"; inference render only).  stop_step[buf] = number of sample
+    // steps the tile in state buffer `buf` executes (S until decided).  The epilogue decides during the compositing of
+    // step s ("every live ray has transmittance < early_T") and sets s + 2: by the time ANY role starts step s + 2 it
+    // has synchronised (through the barriers it already waits on) with an epilogue that is past that compositing, so
+    // all roles read the same value and execute the same number of steps -- the barrier phase arithmetic, which only
+    // depends on the global executed-step counter n, stays consistent.
+    constexpr bool ESTOP = MODE == kRender && !TRAIN;
+    volatile int *sStop = reinterpret_cast<volatile int *>(smem + SM.stop);
+    volatile int *sVote = sStop + 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_work = ONE_STEP ? p.n_tiles : *p.n_live;
     constexpr bool STATE = MODE == kRender;      // per-ray sampling state (gather -> epilogue hand-off) exists
-    const int n_iter = (n_work > (int)blockIdx.x) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int S = ONE_STEP ? 1 : p.S;
 
     // ---- one-time setup ----
@@ -206,6 +214,25 @@ mlp_kernel(const Params p)
         tc05::fence_mbar_init();
     }
     if (warp == kLoaderWarp) tc05::tmem_alloc(tmem_slot, kTmemCols);
+    if (tid < 2) { sStop[tid] = kMaxS + 1; sVote[tid] = 0; }
+    // Work distribution over the persistent CTAs.  Static (work = blockIdx + it * grid) unless the launcher hands in a
+    // counter: then the first tile is static and every further one is drawn from the counter by ONE thread of the
+    // most-ahead role (gather thread 0) and published through a 4-deep shared ring; the other roles pick the it-th
+    // entry up when they get there (spin on the published count).  Tiles differ in cost once early termination is on,
+    // and 2,800 tiles over 148 CTAs leave a 19-vs-18 tail even when they do not.
+    volatile int *sWork = reinterpret_cast<volatile int *>(smem + SM.sched);
+    volatile int *sPub = sWork + 4;
+    if (tid == 0) *sPub = 0;
+    const bool dyn = STATE && p.work_counter != nullptr;
+    auto fetch_work = [&](int it) -> int {
+        if (!dyn) {
+            const int w = (int)blockIdx.x + it * (int)gridDim.x;
+            return w < n_work ? w : -1;
+        }
+        while (*sPub <= it) {
+        }
+        return sWork[it & 3];
+    };
     if (STATE) {
         for (int i = tid; i < kLevels; i += kThreads) sScale[i] = exp2f(i * p.level_S) * p.base_res - 1.0f;   // gridencoder.cu:126
         for (int i = tid; i <= p.S; i += kThreads) sFrac[i] = p.fractions[i];
@@ -230,8 +257,9 @@ mlp_kernel(const Params p)
         const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t n = 0;                 // global step counter
         int loaded_img = -1;
-        for (int it = 0; it < n_iter; it++) {
-            const int work = blockIdx.x + it * gridDim.x;
+        for (int it = 0;; it++) {
+            const int work = fetch_work(it);
+            if (work < 0) break;
             const int tile = ONE_STEP ? work : p.tile_list[work];
             const TileCoord tc = tile_coord(p, tile);
             const int buf = it & 1;
@@ -265,7 +293,9 @@ mlp_kernel(const Params p)
             float Wsum = 0.0f, Dsum = 0.0f, Eexcl = 0.0f;
             bool is_gnd = false;
 
+            int s_done = S;           // steps actually executed for this tile
             for (int s = 0; s < S; s++, n++) {
+                if (ESTOP && s >= 2 && s >= sStop[buf]) { s_done = s; break; }
                 Sample sm{0.0f, 0.0f, 0};
                 if (STATE) {
                     sm = sample_at(p, st, row, s, sFrac, ray);
@@ -433,6 +463,17 @@ mlp_kernel(const Params p)
                         if (p.weights_out) p.weights_out[ray * S + s] = w;
                         if (p.rdepth_out) p.rdepth_out[ray * S + s] = sm.depth;
                     }
+                    if (ESTOP && p.early_T > 0.0f) {
+                        // vote: is every ray of the tile finished (sky-only / outside the image, or opaque)?
+                        const bool done = !live || expf(-Eexcl) < p.early_T;
+                        const bool wall = __all_sync(0xffffffffu, done);
+                        if (lane == 0 && !wall) sVote[s & 1] = 1;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (tid == 0) {
+                            if (sVote[s & 1] == 0 && sStop[buf] > S) sStop[buf] = s + 2;
+                            sVote[s & 1] = 0;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float rgb = fminf(fmaxf(c[j], -1.0f), 1.0f) + 1.0f;                     // :407-408
@@ -461,6 +502,19 @@ mlp_kernel(const Params p)
                     p.sky_partial[(long long)tile * kOutC + tid] =
                         (red[tid] + red[kOutC + tid]) + (red[2 * kOutC + tid] + red[3 * kOutC + tid]);
             } else if constexpr (!BWD) {
+                if constexpr (ESTOP) {
+                    // samples the tile did not shade: their weights are below early_T (reported as 0); the ground test of
+                    // the sky-leak logic (scenedreamer.py:380) still looks at every sample position
+                    for (int s = s_done; s < S; s++) {
+                        const Sample sm = sample_at(p, st, row, s, sFrac, ray);
+                        is_gnd = is_gnd || (__fadd_rn(__fmul_rn(dir0, sm.depth), ori0) <= 1.0f);
+                        if (half == 0 && valid) {
+                            if (p.weights_out) p.weights_out[ray * S + s] = 0.0f;
+                            if (p.rdepth_out) p.rdepth_out[ray * S + s] = sm.depth;
+                        }
+                    }
+                }
+                if (tid == 0 && p.steps_done != nullptr) atomicAdd(p.steps_done, s_done);
                 // ---- finalize the tile (sky blend, scenedreamer.py:380-413) ----
                 const bool sky_mask = flags & 2u;
                 const bool nosky = (!sky_mask) || is_gnd;
@@ -500,12 +554,14 @@ mlp_kernel(const Params p)
         // =========================== WEIGHT LOADER (1-D bulk TMA) ===========================
         if (lane == 0) {
             uint32_t n = 0;
-            for (int it = 0; it < n_iter; it++) {
-                const int work = blockIdx.x + it * gridDim.x;
+            for (int it = 0;; it++) {
+                const int work = fetch_work(it);
+                if (work < 0) break;
                 const int tile = ONE_STEP ? work : p.tile_list[work];
                 const TileCoord tc = tile_coord(p, tile);
                 const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
                 for (int s = 0; s < S; s++, n++) {
+                    if (ESTOP && s >= 2 && s >= sStop[it & 1]) break;
                     const uint32_t flip = kStepFlip & n;
 #pragma unroll
                     for (int l = 0; l < NL; l++) {
@@ -546,8 +602,10 @@ mlp_kernel(const Params p)
         const uint64_t dB0_256 = tc05::make_smem_desc(tc05::smem_u32(sRing), 256 * 16, kSbo);
         const uint64_t dB0_64 = tc05::make_smem_desc(tc05::smem_u32(sRing), kOutC * 16, kSbo);
         const uint64_t dB0_128 = tc05::make_smem_desc(tc05::smem_u32(sRing), kFeat * 16, kSbo);
-        for (int it = 0; it < n_iter; it++) {
+        for (int it = 0;; it++) {
+            if (fetch_work(it) < 0) break;                              // warp-uniform
             for (int s = 0; s < S; s++, n++) {
+                if (ESTOP && s >= 2 && s >= sStop[it & 1]) break;       // warp-uniform (same shared word for every lane)
                 const uint32_t flip = kStepFlip & n;
                 const uint32_t nodd = n & 1u;
 #pragma unroll
@@ -632,8 +690,18 @@ mlp_kernel(const Params p)
         const int gt = tid - kGatherWarp0 * 32;
         const int row = gt & (kRows - 1), half = gt >> 7;
         uint32_t n = 0;
-        for (int it = 0; it < n_iter; it++) {
-            const int work = blockIdx.x + it * gridDim.x;
+        for (int it = 0;; it++) {
+            if (dyn && gt == 0) {
+                // publish the it-th work item of this CTA (slot it & 3 was last used by tile it - 4, which every role has
+                // left: this thread is past the STFREE wait of tile it - 2)
+                int w = (int)blockIdx.x;
+                if (it > 0) w = atomicAdd(p.work_counter, 1) + (int)gridDim.x;
+                sWork[it & 3] = w < n_work ? w : -1;
+                __threadfence_block();
+                *sPub = it + 1;
+            }
+            const int work = fetch_work(it);
+            if (work < 0) break;
             const int tile = ONE_STEP ? work : p.tile_list[work];
             const TileCoord tc = tile_coord(p, tile);
             const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
@@ -728,6 +796,7 @@ mlp_kernel(const Params p)
                 // ---- per-ray sampling state (first 128 gather threads) ----
                 if (gt == 0) SDB_MARK(4, 1, n, it);
                 if (it >= 2) tc05::mbar_wait_backoff(&bars[B_STFREE + buf], ((it >> 1) - 1) & 1);
+                if (gt == 0) sStop[buf] = kMaxS + 1;           // undecided (published with the state: bar.sync 2 + STRDY below)
                 if (half == 0) {
                     float accu = 0.0f, cum = 0.0f, entry0 = 0.0f, prev_exit = 0.0f;
                     uint32_t labs = 0, flags = 0;
@@ -834,6 +903,7 @@ mlp_kernel(const Params p)
                     if (gt == 0) SDB_MARK(4, 3, n, it);
                     if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
                     if (gt == 0) SDB_MARK(4, 4, n, it);
+                    if (ESTOP && s >= 2 && s >= sStop[buf]) break;           // the tile ended before this step: drop the features
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const uint32_t off = tc05::chunk_off(kRows, row, half + 2 * i);
@@ -1258,6 +1328,7 @@ int params_from_abi(const sdb_render_params *sp, Params &p)
     p.genc = sp->d_global_enc;
     for (int k = 0; k < 3; k++) p.vdim[k] = sp->voxel_dims[k];
     p.sample_depth = sp->sample_depth; p.dists_scale = sp->dists_scale;
+    p.early_T = sp->early_stop_transmittance > 0.0f ? sp->early_stop_transmittance : 0.0f;
     p.fractions = sp->d_fractions; p.uniforms = sp->d_uniforms;
     p.lut = sp->d_label_lut; p.n_lut = sp->n_lut;
     p.raw5d = sp->d_table != nullptr;
@@ -1284,7 +1355,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         if (rc != SDB_OK) return rc;
     }
     int32_t *ws = (int32_t *)sp->d_workspace;
-    p.n_live = ws; p.tile_list = ws + 4;
+    p.n_live = ws; p.tile_list = ws + 4; p.steps_done = ws + 1; p.work_counter = ws + 2;
     {
         const int rc = launch_prepass(p, ws, st);
         if (rc != SDB_OK) return rc;

@@ -111,7 +111,7 @@ __device__ __forceinline__ bool elect_one() {
 
 // ---- shared memory map ---------------------------------------------------------------------------
 struct Smem {
-    uint32_t h_hi, h_lo, ring, fsec, scales, frac, sig, state, bars, tmem_slot, total;
+    uint32_t h_hi, h_lo, ring, fsec, scales, frac, sig, state, bars, tmem_slot, stop, sched, total;
 };
 __host__ __device__ constexpr Smem smem_map(bool x3) {
     Smem m{};
@@ -126,6 +126,8 @@ __host__ __device__ constexpr Smem smem_map(bool x3) {
     m.state = o; o += 2 * (2 * kMaxM + 6) * kRows * 4;
     m.bars = o; o += 32 * 8;
     m.tmem_slot = o; o += 16;
+    m.stop = o; o += 16;                         // early termination: int stop_step[2] (per tile buffer), int vote[2]
+    m.sched = o; o += 32;                        // dynamic tile scheduler: int work[4] (ring), int published
     m.total = o;
     return m;
 }
@@ -174,6 +176,7 @@ struct Params {
     const float *depth2, *raydirs, *cam_ori, *genc;
     float vdim[3];
     float sample_depth, dists_scale;
+    float early_T;                 // > 0: a ray tile stops once every live ray's transmittance is below this (inference only)
     const float *fractions, *uniforms;
     const int32_t *lut;
     int n_lut;
@@ -188,6 +191,8 @@ struct Params {
     float *net_out, *depth_out, *total_weight, *weights_out, *rdepth_out;
     const int32_t *tile_list;      // [n_live] (render) / nullptr (sky: all tiles)
     const int32_t *n_live;
+    int32_t *steps_done;           // optional counter (workspace word 1): sample steps actually executed, summed over tiles
+    int32_t *work_counter;         // optional (workspace word 2, zeroed per launch): dynamic tile scheduling across the persistent CTAs
     int n_tiles;
     int tiles_x, tiles_y;
     // sky mode

@@ -195,3 +195,38 @@ def test_sky_forward_vs_oracle(scene):
         assert err <= tol and aerr <= tol
     t = render.sky_features(Pd, rd, z.to(DEV))
     assert float((t.cpu() - ref).abs().max()) <= 1e-4
+
+
+def test_early_termination_error_bound_and_savings(scene, lut, golden_ops):
+    """Tile-level early termination (render.EARLY_STOP_T): outputs stay within 2*T of the exact march, the samples not
+    shaded report weight 0 and were below T in the exact march, and with T = 0 the kernel is the exact march."""
+    P = oracle.make_params(seed=21, stress=True)
+    P['render_net.fc_sigma.bias'] = torch.full((1,), 150.0)      # dense medium: rays saturate within a few samples
+    g = torch.Generator().manual_seed(8888)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    _, pls = oracle.grid_offsets()
+    r = render.FusedPerPixelRenderer(to_dev(P), scene['world'].voxel_t.shape, lut, pls)
+    args = (scene['vid'], scene['dep'], scene['rd'], scene['o'].unsqueeze(0), z.to(DEV), genc.to(DEV))
+    outs = {}
+    for T in (0.0, 1e-7, 1e-3):
+        r.early_stop = T
+        o = r.forward(*args, want_samples=True)
+        torch.cuda.synchronize()
+        outs[T] = {k: o[k].clone() for k in ('net_out', 'depth', 'total_weight', 'weights', 'rand_depth')}
+    exact = outs[0.0]
+    for T in (1e-7, 1e-3):
+        d = outs[T]
+        assert float((d['net_out'] - exact['net_out']).abs().max()) <= 2.5 * T + 1e-7
+        assert float((d['total_weight'] - exact['total_weight']).abs().max()) <= T + 1e-7
+        assert torch.equal(d['rand_depth'], exact['rand_depth'])
+        skipped = (d['weights'] == 0) & (exact['weights'] != 0)
+        assert float(exact['weights'][skipped].max() if bool(skipped.any()) else 0.0) <= T
+        same = ~skipped
+        assert torch.equal(d['weights'][same], exact['weights'][same])
+        dmax = float(exact['rand_depth'].abs().max())
+        assert float((d['depth'] - exact['depth']).abs().max()) <= T * dmax + 1e-4
+        print('early stop T=%g: %.1f %% of the non-zero sample weights skipped, max |d net_out| %.2e'
+              % (T, 100.0 * float(skipped.float().sum() / max(1.0, float((exact['weights'] != 0).sum()))),
+                 float((d['net_out'] - exact['net_out']).abs().max())))
+    assert bool(((outs[1e-3]['weights'] == 0) & (exact['weights'] != 0)).any())       # something was skipped
