@@ -284,6 +284,27 @@ def run_gpu_arm(args):
         b.record()
         torch.cuda.synchronize()
         dev_ms.append(a.elapsed_time(b))
+    # the same device-only measurement with early termination OFF (every sample of every live tile marched)
+    exact_ms = []
+    if not args.no_early_stop:
+        fr.set_early_stop(0.0)
+        for k in range(-2, min(args.steps, 10)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            idx = (max(k, 0) * world_size + rank) % len(cams)
+            flush.zero_()
+            a.record()
+            o_ = fr.frame(cams[idx], ori_dev=doris[idx])
+            if world_size > 1:
+                sharding.gather_frames(torch.stack([o_['depth'][0], o_['total_weight'][0]]).unsqueeze(0))
+            o_ = None
+            b.record()
+            torch.cuda.synchronize()
+            if k >= 0:
+                exact_ms.append(a.elapsed_time(b))
+        fr.set_early_stop(None)
+    etot = torch.tensor([float(np.mean(exact_ms)) if exact_ms else 0.0], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(etot, op=dist.ReduceOp.MAX)
     dtot = torch.tensor([sum(dev_ms)], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(dtot, op=dist.ReduceOp.MAX)
@@ -322,6 +343,8 @@ def run_gpu_arm(args):
             'metric': 'rendered Msamples/sec at 960x540x24spp', 'value': value, 'unit': 'Msamples/s',
             'mpix_per_s': value / SPP, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dev_tot_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'value_exact_march': (world_size * SAMPLES_PER_FRAME / (float(etot[0]) * 1e-3) / 1e6) if float(etot[0]) > 0 else None,
+            'value_exact_march_note': 'same measurement with early termination off (every sample of every live tile shaded)',
             'dtype': {'fp16': 'f16 (f32 accumulate)', 'bf16x3': 'bf16x3 split (f32-grade), f32 accumulate',
                       'fp16x3': 'f16x3 split (f32-grade), f32 accumulate'}[args.precision] + '; table/compositing f32',
             'data': 'synthetic',
