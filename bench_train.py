@@ -83,6 +83,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--no-composition', action='store_true')
+    ap.add_argument('--views', type=int, default=8, help='number of distinct camera poses cycled through')
+    ap.add_argument('--profile', action='store_true', help='host/device time of the autograd Functions (diagnostics, stderr)')
     a = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit('bench_train.py: no CUDA device (no CPU fallback)')
@@ -102,7 +104,7 @@ def main():
     voxel = world.voxel_t.to(dev)
     vdims = [float(v) for v in world.voxel_t.shape]
     views = []
-    for k in range(8):
+    for k in range(a.views):
         o, d, u, f, c, res = synth.frame_camera(world, poses[(5 * k) % 40], (VIEW, VIEW), PAD)
         vid, dep, rd = ops.ray_voxel_intersection_perspective(voxel, o, d, u, f, c, res, 6)
         views.append((vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0).to(dev)))
@@ -143,6 +145,39 @@ def main():
         tot = float(np.mean([e[0].elapsed_time(e[2]) for e in evs]))
         return fwd, tot
 
+    if a.profile:
+        import time
+        stats = {}
+
+        def wrap(cls, name):
+            orig = getattr(cls, name)
+
+            def f(ctx, *args):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = orig(ctx, *args)
+                e1.record()
+                t1 = time.perf_counter()
+                torch.cuda.synchronize()
+                stats.setdefault(cls.__name__ + '.' + name, []).append((1e3 * (t1 - t0), e0.elapsed_time(e1)))
+                return r
+            setattr(cls, name, staticmethod(f))
+        for cls in (render._FusedRenderTrainFn, render._SkyTrainFn):
+            wrap(cls, 'forward')
+            wrap(cls, 'backward')
+        for k in range(6):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fused_step(k)
+            torch.cuda.synchronize()
+            stats.setdefault('whole step (synchronous)', []).append((1e3 * (time.perf_counter() - t0), 0.0))
+            zero_grads()
+        for k, v in stats.items():
+            v = v[2:]
+            print('%-40s host %.2f ms   device %.2f ms' % (k, np.mean([x[0] for x in v]), np.mean([x[1] for x in v])), file=sys.stderr)
+        return
     fwd_ms, tot_ms = timed(fused_step, a.steps, max(3, a.warmup))
     live = float(np.mean([float((v[0][..., 0, 0] != 0).float().mean()) for v in views]))
     line = {'metric': 'train-step per-pixel path: forward(record)+backward, 262x262 rays x 24 spp, per GPU', 'unit': 'ms',

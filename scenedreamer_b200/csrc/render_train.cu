@@ -18,6 +18,7 @@
 //                                   XOR-indexing is an involution) and the scene-code gradient;
 //   4. weight gradients           : plain bf16 GEMMs dZ^T * A over all samples through cuBLAS (fp32 out).
 #include <cublas_v2.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "rf_common.cuh"
@@ -60,7 +61,8 @@ static void bind_record(Params &p, uint8_t *rec, const RecordLayout &r) {
     p.tr.c = reinterpret_cast<float *>(rec + r.c);
 }
 
-struct BwdLayout { size_t dc32, dc16, dsig32, dsig16, dz, dx0, dt3, total; };
+constexpr size_t kCublasWsBytes = (size_t)256 << 20;   // split-K partials of the [256 x 272] x K=10^6 weight-gradient GEMMs
+struct BwdLayout { size_t dc32, dc16, dsig32, dsig16, dz, dx0, dt3, cublas, total; };
 static BwdLayout bwd_layout(long long n_tiles, int S, int L, int log2_T) {
     const size_t cap = (size_t)n_tiles * S * kRows;
     BwdLayout b{};
@@ -72,6 +74,7 @@ static BwdLayout bwd_layout(long long n_tiles, int S, int L, int log2_T) {
     b.dz = o; o = align_up(o + (size_t)kNumAct * cap * kHidden * 2);
     b.dx0 = o; o = align_up(o + cap * kFeat * 4);
     b.dt3 = o; o = align_up(o + ((size_t)L << log2_T) * 8 * 4);
+    b.cublas = o; o = align_up(o + kCublasWsBytes);
     b.total = o;
     return b;
 }
@@ -345,12 +348,16 @@ genc_backward_kernel(const float *__restrict__ table, const float *__restrict__ 
 // One handle per device, created on first use (the only process-global state of the library besides the
 // diagnostics pointer; creation is not thread-safe -- the reference's callers are single-threaded per process).
 static cublasHandle_t g_cublas[64] = {};
-static int cublas_for_stream(cudaStream_t st, cublasHandle_t *out) {
+// `ws` / `ws_bytes`: caller-owned scratch handed to cuBLAS for this call sequence.  Without it cuBLAS falls back to
+// allocating the split-K workspace itself for every GEMM whose partials exceed its small default pool -- measured here as
+// 11-18 ms of allocator stalls per backward for 1.6 ms of GEMM kernels.
+static int cublas_for_stream(cudaStream_t st, void *ws, size_t ws_bytes, cublasHandle_t *out) {
     int dev = 0;
     SDB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return SDB_EUNSUPPORTED;
     if (!g_cublas[dev] && cublasCreate(&g_cublas[dev]) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorInitializationError;
     if (cublasSetStream(g_cublas[dev], st) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
+    if (cublasSetWorkspace(g_cublas[dev], ws, ws_bytes) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
     *out = g_cublas[dev];
     return SDB_OK;
 }
@@ -453,12 +460,25 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
     SDB_CUDA(cudaStreamSynchronize(st));
     if (n_live < 0 || n_live > p.n_tiles) return SDB_EINVAL;
     const long long n_slots = (long long)n_live * p.S * kRows;
+    // The GEMMs below reduce over the slot dimension.  cuBLAS plans every NEW problem size on the host (measured: ~1.5 ms per
+    // GEMM, 12 ms per backward, whenever the live-tile count differs from the previous call -- and the plans do not stick
+    // when a few sizes alternate), so that dimension is made a constant of the frame geometry: the GEMMs always run over
+    // the buffers' full capacity and the rows of both operands beyond the live slots are zero-filled (one memset per
+    // array, a few GB at HBM speed ~ 0.8 ms for a 256x256 view) -- 8 plans per resolution, made once.
+    const int n_live_pad = p.n_tiles;
+    const long long n_slots_pad = (long long)n_live_pad * p.S * kRows;
     const size_t table_bytes = ((size_t)sp->L << p.log2_T) * 8 * 4;
 
     SDB_CUDA(cudaMemsetAsync(g->d_grad_sky_avg, 0, (size_t)p.n_img * kOutC * 4, st));
     SDB_CUDA(cudaMemsetAsync(g->d_grad_global_enc, 0, 8, st));
     SDB_CUDA(cudaMemsetAsync(dt3, 0, table_bytes, st));
 
+    // SDB_TIMING=1: per-stage device times on stderr (diagnostics; synchronises)
+    const bool timing = getenv("SDB_TIMING") != nullptr;
+    cudaEvent_t tev[8];
+    int ntev = 0;
+    auto mark = [&]() { if (timing && ntev < 8) { cudaEventCreate(&tev[ntev]); cudaEventRecord(tev[ntev], st); ntev++; } };
+    mark();
     // 1. compositing backward (every tile: sky-only tiles still feed dL/dsky)
     composite_backward_kernel<<<p.n_tiles, 256, 0, st>>>(p, g->d_grad_net_out, g->d_grad_sky, g->d_grad_sky_avg, dc32, dc16,
                                                          dsig32, dsig16);
@@ -471,12 +491,14 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         SDB_CUDA(cudaMemsetAsync(g->d_grad_wout, 0, (size_t)kOutC * kActCols * 4, st));
         return SDB_OK;
     }
+    mark();
     // 2. data-gradient chain on the tensor-core engine
     {
         const int grid = n_live < sdb_num_sms() ? n_live : sdb_num_sms();
         const int rc = launch_bwd_chain(p, grid, st);
         if (rc != SDB_OK) return rc;
     }
+    mark();
     // 3. table gradient: scatter into the pre-blended table, transpose of the pre-blend, scene code
     {
         dim3 grid((unsigned)((n_slots + 255) / 256), kLevels);
@@ -492,23 +514,44 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
                                                                           p.genc, g->d_grad_global_enc);
         SDB_CHECK_LAUNCH();
     }
+    mark();
     // 4. weight gradients (bf16 x bf16 -> fp32 GEMMs over all recorded samples)
     {
+        const long long cap0 = p.tr.slot_cap;
+        const size_t pad = (size_t)(n_slots_pad - n_slots);
+        if (pad > 0) {
+            SDB_CUDA(cudaMemsetAsync(p.tr.x0 + (size_t)n_slots * kX0Cols, 0, pad * kX0Cols * 2, st));
+            SDB_CUDA(cudaMemsetAsync(dc16 + (size_t)n_slots * kOutC, 0, pad * kOutC * 2, st));
+            SDB_CUDA(cudaMemsetAsync(dsig16 + (size_t)n_slots * 8, 0, pad * 8 * 2, st));
+            for (int k = 0; k < kNumAct; k++) {
+                SDB_CUDA(cudaMemsetAsync(p.tr.act + ((size_t)k * cap0 + n_slots) * kActCols, 0, pad * kActCols * 2, st));
+                SDB_CUDA(cudaMemsetAsync(dz + ((size_t)k * cap0 + n_slots) * kHidden, 0, pad * kHidden * 2, st));
+            }
+        }
         cublasHandle_t h;
-        int rc = cublas_for_stream(st, &h);
+        int rc = cublas_for_stream(st, ws + bl.cublas, kCublasWsBytes, &h);
         if (rc != SDB_OK) return rc;
         const long long cap = p.tr.slot_cap;
-        rc = wgrad(h, p.tr.x0, kX0Cols, kX0Cols, dz, kHidden, kHidden, n_slots, g->d_grad_w1ext);                       // fc_1 | fc_m_a | bias
+        rc = wgrad(h, p.tr.x0, kX0Cols, kX0Cols, dz, kHidden, kHidden, n_slots_pad, g->d_grad_w1ext);                       // fc_1 | fc_m_a | bias
         if (rc != SDB_OK) return rc;
         for (int k = 0; k < 5; k++) {                                                                                   // fc_2 .. fc_6
             rc = wgrad(h, p.tr.act + (size_t)k * cap * kActCols, kActCols, kActCols, dz + (size_t)(k + 1) * cap * kHidden, kHidden,
-                       kHidden, n_slots, g->d_grad_wh + (size_t)k * kHidden * kActCols);
+                       kHidden, n_slots_pad, g->d_grad_wh + (size_t)k * kHidden * kActCols);
             if (rc != SDB_OK) return rc;
         }
-        rc = wgrad(h, p.tr.act + (size_t)5 * cap * kActCols, kActCols, kActCols, dc16, kOutC, kOutC, n_slots, g->d_grad_wout);   // fc_out_c
+        rc = wgrad(h, p.tr.act + (size_t)5 * cap * kActCols, kActCols, kActCols, dc16, kOutC, kOutC, n_slots_pad, g->d_grad_wout);   // fc_out_c
         if (rc != SDB_OK) return rc;
-        rc = wgrad(h, p.tr.act + (size_t)3 * cap * kActCols, kActCols, kActCols, dsig16, 8, 8, n_slots, g->d_grad_wsig);         // fc_sigma
+        rc = wgrad(h, p.tr.act + (size_t)3 * cap * kActCols, kActCols, kActCols, dsig16, 8, 8, n_slots_pad, g->d_grad_wsig);         // fc_sigma
         if (rc != SDB_OK) return rc;
+    }
+    mark();
+    if (timing) {
+        cudaStreamSynchronize(st);
+        float ms[8] = {0};
+        for (int i = 0; i + 1 < ntev; i++) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
+        fprintf(stderr, "[sdb timing] backward: compositing %.3f ms, chain %.3f ms, table %.3f ms, weight GEMMs %.3f ms (n_live %d)\n", ms[0],
+                ms[1], ms[2], ms[3], n_live);
+        for (int i = 0; i < ntev; i++) cudaEventDestroy(tev[i]);
     }
     return SDB_OK;
 }
@@ -552,7 +595,7 @@ extern "C" int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void 
         if (rc != SDB_OK) return rc;
     }
     cublasHandle_t h;
-    int rc = cublas_for_stream(st, &h);
+    int rc = cublas_for_stream(st, ws + bl.cublas, kCublasWsBytes, &h);
     if (rc != SDB_OK) return rc;
     rc = wgrad(h, p.tr.x0, kSkyK0, kSkyK0, p.tr.dz, kHidden, kHidden, cap, d_grad_w1ext);                                       // fc1 | bias
     if (rc != SDB_OK) return rc;

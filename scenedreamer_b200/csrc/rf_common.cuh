@@ -286,13 +286,14 @@ static inline SkyRecordLayout sky_record_layout(long long n_tiles) {
     r.total = o;
     return r;
 }
-struct SkyBwdLayout { size_t dc16, dz, total; };
+struct SkyBwdLayout { size_t dc16, dz, cublas, total; };
 static inline SkyBwdLayout sky_bwd_layout(long long n_tiles) {
     const size_t cap = (size_t)n_tiles * kRows;
     SkyBwdLayout b{};
     size_t o = 0;
     b.dc16 = o; o = rf_align_up(o + cap * kOutC * 2);
     b.dz = o; o = rf_align_up(o + (size_t)Net<kSky>::NACT * cap * kHidden * 2);
+    b.cublas = o; o = rf_align_up(o + ((size_t)256 << 20));          // cuBLAS split-K scratch (kCublasWsBytes)
     b.total = o;
     return b;
 }

@@ -7,6 +7,7 @@ Tensors are torch CUDA tensors; only their data pointers, shapes and the current
 cross into the library (PyTorch is the allocator / stream plumbing, not the compute path).
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -45,13 +46,47 @@ def _f3(t):
 # ------------------------------------------------------------------------------------------------
 # voxlib
 # ------------------------------------------------------------------------------------------------
-def ray_voxel_intersection_perspective(in_voxel, cam_ori, cam_dir, cam_up, cam_f, cam_c, img_dims, max_samples):
-    """-> [voxel_id int32 [H,W,M,1], depth2 f32 [2,H,W,M,1], raydirs f32 [H,W,1,3]]  (voxlib.cpp:11)."""
+HEIGHT_BOUND_BLOCK_LOG2 = 4          # 16 x 16 column blocks; None disables the empty-space bound
+_height_bounds = {}      # id(voxel tensor OBJECT) -> (weakref to it, tensor._version, block_log2, int16 bound)
+
+
+def height_bound(in_voxel, block_log2=None):
+    """Highest occupied height per column block of `in_voxel` (sdb_build_height_bound), cached per tensor object and
+    tensor version: the reference hands the same `voxel_t` tensor to every frame of a scene (scenedreamer.py:578), an
+    in-place edit bumps `_version`, a new scene is a new tensor object.  Edits that bypass torch's version counter
+    (`.data`, numpy views) need `invalidate_height_bound(t)`."""
+    L = HEIGHT_BOUND_BLOCK_LOG2 if block_log2 is None else block_log2
+    key = id(in_voxel)
+    ent = _height_bounds.get(key)
+    if ent is not None and ent[0]() is in_voxel and ent[1] == in_voxel._version and ent[2] == L:
+        return ent[3], L
+    dims = (ctypes.c_int64 * 3)(*in_voxel.shape)
+    strides = (ctypes.c_int64 * 3)(*in_voxel.stride())
+    n = int(_lib.lib().sdb_height_bound_elems(dims, int(L)))
+    hb = torch.empty(n, dtype=torch.int16, device=in_voxel.device)
+    with torch.cuda.device(in_voxel.device):
+        code = _lib.lib().sdb_build_height_bound(_ptr(in_voxel), dims, strides, int(L), _ptr(hb), _stream(in_voxel))
+    _lib.check(code, 'sdb_build_height_bound')
+    _height_bounds[key] = (weakref.ref(in_voxel, lambda _r, k=key: _height_bounds.pop(k, None)), in_voxel._version, L, hb)
+    return hb, L
+
+
+def invalidate_height_bound(in_voxel):
+    _height_bounds.pop(id(in_voxel), None)
+
+
+def ray_voxel_intersection_perspective(in_voxel, cam_ori, cam_dir, cam_up, cam_f, cam_c, img_dims, max_samples,
+                                       empty_space_bound=True):
+    """-> [voxel_id int32 [H,W,M,1], depth2 f32 [2,H,W,M,1], raydirs f32 [H,W,1,3]]  (voxlib.cpp:11).
+    empty_space_bound: use the cached height bound of the volume (bit-identical results, see height_bound)."""
     _check_cuda(in_voxel, 'in_voxel')
     if in_voxel.dtype != torch.int32 or in_voxel.dim() != 3:
         raise RuntimeError('in_voxel must be a 3-D int32 tensor')
     H, W, M = int(img_dims[0]), int(img_dims[1]), int(max_samples)
     dev = in_voxel.device
+    hb, L = (None, 0)
+    if empty_space_bound and HEIGHT_BOUND_BLOCK_LOG2 is not None and in_voxel.shape[0] <= 32767:
+        hb, L = height_bound(in_voxel)
     with torch.cuda.device(dev):
         voxel_id = torch.empty(H, W, M, 1, dtype=torch.int32, device=dev)
         depth2 = torch.empty(2, H, W, M, 1, dtype=torch.float32, device=dev)
@@ -60,9 +95,9 @@ def ray_voxel_intersection_perspective(in_voxel, cam_ori, cam_dir, cam_up, cam_f
         strides = (ctypes.c_int64 * 3)(*in_voxel.stride())
         cc = (ctypes.c_float * 2)(float(cam_c[0]), float(cam_c[1]))
         im = (ctypes.c_int32 * 2)(H, W)
-        code = _lib.lib().sdb_ray_voxel_intersection_perspective(
+        code = _lib.lib().sdb_ray_voxel_intersection_perspective_ex(
             _ptr(in_voxel), dims, strides, _f3(cam_ori), _f3(cam_dir), _f3(cam_up), float(cam_f), cc, im, M,
-            _ptr(voxel_id), _ptr(depth2), _ptr(raydirs), _stream(in_voxel))
+            _ptr(voxel_id), _ptr(depth2), _ptr(raydirs), _ptr(hb), int(L), _stream(in_voxel))
     _lib.check(code, 'ray_voxel_intersection_perspective')
     return [voxel_id, depth2, raydirs]
 

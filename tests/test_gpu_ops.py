@@ -241,3 +241,35 @@ def test_dda_origin_on_cell_faces_and_far_origin(world):
             assert torch.equal(vid.cpu(), evid)
             assert torch.equal(bits(rd), bits(erd))
             assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(edep, nan=-1.0)))
+
+
+@pytest.mark.parametrize('block_log2', [2, 3, 4, 6])
+def test_dda_empty_space_flight_is_bit_identical(world, block_log2):
+    """The exact flight across empty column blocks (sdb_build_height_bound + ..._ex) changes nothing but the step count:
+    ids, depths and directions equal the plain cell-by-cell walk bit for bit, for every block size, for cameras above,
+    inside and outside the volume, looking down, up and along the axes -- and a stale bound is rebuilt after an edit."""
+    vox = world.voxel_t.to(DEV).clone()
+    X = world.voxel_t.shape[1]
+    old = ops.HEIGHT_BOUND_BLOCK_LOG2
+    ops.HEIGHT_BOUND_BLOCK_LOG2 = block_log2
+    try:
+        cams = [_frame(world, k, hw=(90, 150), pad=10, pattern=pat) for k, pat in ((0, 0), (2, 0), (4, 4), (7, 4))]
+        cams += [([200.0, 100.5, 77.5], [-1.0, 0.0, 0.0], [0.0, 1.0, 0.0], 60.0, [31.5, 47.5], [64, 96]),        # straight down
+                 ([30.0, 64.2, 64.7], [1.0, 0.3, 0.2], [0.0, 1.0, 0.0], 40.0, [31.5, 47.5], [64, 96]),           # from inside, up and out
+                 ([90.0, -50.5, 300.25], [-0.1, 1.0, -0.2], [1.0, 0.0, 0.0], 80.0, [31.5, 47.5], [64, 96]),      # from outside, grazing
+                 ([60.0, float(X), 128.0], [-0.2, -1.0, 0.01], [1.0, 0.0, 0.0], 40.0, [31.5, 47.5], [64, 96])]   # origin on a face
+        for cam in cams:
+            a = ops.ray_voxel_intersection_perspective(vox, *cam[:6], 6)
+            b = ops.ray_voxel_intersection_perspective(vox, *cam[:6], 6, empty_space_bound=False)
+            assert torch.equal(a[0], b[0])
+            assert torch.equal(bits(a[2]), bits(b[2]))
+            assert torch.equal(bits(torch.nan_to_num(a[1], nan=-1.0)), bits(torch.nan_to_num(b[1], nan=-1.0)))
+        # an in-place edit (a floating block high above the terrain) must invalidate the cached bound
+        vox[vox.shape[0] - 3, 100:140, 100:140] = 7
+        cam = cams[1]
+        a = ops.ray_voxel_intersection_perspective(vox, *cam[:6], 6)
+        b = ops.ray_voxel_intersection_perspective(vox, *cam[:6], 6, empty_space_bound=False)
+        assert torch.equal(a[0], b[0]) and bool((a[0] == 7).any())
+        assert torch.equal(bits(torch.nan_to_num(a[1], nan=-1.0)), bits(torch.nan_to_num(b[1], nan=-1.0)))
+    finally:
+        ops.HEIGHT_BOUND_BLOCK_LOG2 = old
