@@ -242,8 +242,6 @@ def run_gpu_arm(args):
         one_step(w)
         flush.zero_()
     torch.cuda.synchronize()
-    if world_size > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -252,9 +250,13 @@ def run_gpu_arm(args):
     kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()           # AFTER rank 0 has started its clock sampler: every rank enters the timed region together
+        torch.cuda.synchronize()
     t_begin = t_wall = time.perf_counter()
     for k in range(args.steps):
         one_step(k, evs[k], kevs[k], cevs[k])
+        torch.cuda.synchronize()                                     # the caller READS the step's result on the host
         flush.zero_()                                                # L2 flush between timed iterations
     torch.cuda.synchronize()
     t_end = time.perf_counter()
@@ -262,6 +264,14 @@ def run_gpu_arm(args):
     if world_size > 1:
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
+    if os.environ.get('SDB_BENCH_DEBUG'):
+        print('[rank %d] e2e step ms: %s' % (rank, ' '.join('%.1f' % v for v in step_ms)), file=sys.stderr)
+        print('[rank %d] ev0->kernel start ms: %s' % (rank, ' '.join('%.1f' % evs[i][0].elapsed_time(kevs[i][0]) for i in range(len(evs)))), file=sys.stderr)
+        print('[rank %d] kernel ms: %s' % (rank, ' '.join('%.1f' % a.elapsed_time(b) for a, b in kevs)), file=sys.stderr)
+        if world_size > 1:
+            print('[rank %d] kernel end->coll start ms: %s' % (rank, ' '.join('%.1f' % kevs[i][1].elapsed_time(cevs[i][0]) for i in range(len(evs)))), file=sys.stderr)
+            print('[rank %d] coll ms: %s' % (rank, ' '.join('%.1f' % a.elapsed_time(b) for a, b in cevs)), file=sys.stderr)
+            print('[rank %d] coll end->step end ms: %s' % (rank, ' '.join('%.1f' % cevs[i][1].elapsed_time(evs[i][1]) for i in range(len(evs)))), file=sys.stderr)
     kern_ms = [a.elapsed_time(b) for a, b in kevs]
     coll_ms = [a.elapsed_time(b) for a, b in cevs] if world_size > 1 else [0.0]
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
@@ -358,7 +368,7 @@ def run_gpu_arm(args):
                                              % render.EARLY_STOP_T)},
             'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
                     'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': tot_ms / args.steps,
-                    'note': 'pose from pinned host memory -> DDA -> sky -> fused render -> depth+opacity maps to pinned host'},
+                    'note': 'per step: pose from pinned host memory -> DDA -> sky -> fused render -> depth+opacity maps to pinned host, host waits for them'},
             'gpu_launches': 5 * args.steps,
             'gpu_launches_note': 'per step: dda_perspective, mlp_kernel<sky>, sky_mean, prepass, mlp_kernel<render> (all ours)',
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
