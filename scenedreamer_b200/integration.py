@@ -5,8 +5,8 @@
 fused path: without autograd (`dis_forward`, trainers/gancraft.py:215-217) the inference kernel,
 with autograd (gen_update) the recording forward + fused backward (render.render_rays_train), whose
 gradients reach the module's own Parameters (hash_encoder.embeddings, render_net.*, sky_net.*) and
-the incoming z / global_enc.  Configurations the fused path does not cover (see `supported` below,
-or a batch of several views in one call under autograd) keep the reference's own composition --
+the incoming z / global_enc (a batch of views = one recorded pass per view).  Configurations the fused path
+does not cover (see `supported` below) keep the reference's own composition --
 which, with dropin/ on PYTHONPATH, still runs on this library's DDA / PE / hash-grid kernels.
 
 The returned 12-tuple has the reference's order (scenedreamer.py:427-428).  Callers in the reference
@@ -70,7 +70,8 @@ def fused_forward_perpix(self, blk_feats, voxel_id, depth2, raydirs, cam_ori_t, 
     needs_grad = torch.is_grad_enabled() and (z.requires_grad or global_enc.requires_grad or
                                               any(q.requires_grad for q in self.render_net.parameters()) or
                                               any(q.requires_grad for q in self.hash_encoder.parameters()))
-    if not supported or not voxel_id.is_cuda or (needs_grad and (voxel_id.shape[0] != 1 or hasattr(self, 'sky_avg'))):
+    same_scene = global_enc.shape[0] == 1 or bool((global_enc == global_enc[:1]).all())
+    if not supported or not voxel_id.is_cuda or (needs_grad and (hasattr(self, 'sky_avg') or not same_scene)):
         return st.reference_forward(blk_feats, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc)
     uniforms = None
     if not self.coarse_deterministic_sampling:
@@ -79,12 +80,19 @@ def fused_forward_perpix(self, blk_feats, voxel_id, depth2, raydirs, cam_ori_t, 
     sky_mask = voxel_id[:, :, :, [-1], :] == 0
     sky_only_mask = voxel_id[:, :, :, [0], :] == 0
     if needs_grad:
+        # one recorded pass per view (one style code each); the frame mean of the sky features is per view as well
+        # (scenedreamer.py:395 averages over dims 1,2 only), so a batch is exactly the concatenation of its views
         he = self.hash_encoder
-        out = render.render_rays_train(
-            _live_params(self), voxel_id.contiguous(), depth2.contiguous(), raydirs.contiguous(), cam_ori_t, z, global_enc,
-            [float(v) for v in self.voxel.voxel_t.shape], st.lut, he.per_level_scale, num_samples=self.num_samples,
-            sample_depth=self.sample_depth, dists_scale=self.dists_scale, uniforms=uniforms,
-            base_res=he.base_resolution, log2_T=he.log2_hashmap_size, L=he.num_levels)
+        P = _live_params(self)
+        outs = []
+        for i in range(voxel_id.shape[0]):
+            outs.append(render.render_rays_train(
+                P, voxel_id[i:i + 1].contiguous(), depth2[i:i + 1].contiguous(), raydirs[i:i + 1].contiguous(),
+                cam_ori_t[i:i + 1], z[i:i + 1], global_enc[:1], [float(v) for v in self.voxel.voxel_t.shape], st.lut,
+                he.per_level_scale, num_samples=self.num_samples, sample_depth=self.sample_depth,
+                dists_scale=self.dists_scale, uniforms=None if uniforms is None else uniforms[i:i + 1],
+                base_res=he.base_resolution, log2_T=he.log2_hashmap_size, L=he.num_levels))
+        out = {k: torch.cat([o[k] for o in outs], 0) for k in ('net_out', 'total_weight', 'weights', 'rand_depth', 'sky')}
         total = out['total_weight'].unsqueeze(-1).unsqueeze(-1)
         return (out['net_out'], None, out['weights'], total, out['rand_depth'], None, None, out['sky'].unsqueeze(-2), None,
                 sky_mask, sky_only_mask, None)
