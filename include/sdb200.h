@@ -285,6 +285,11 @@ void sdb_debug_set_progress_buffer(void *mapped);
 int sdb_tc_selftest(const float *d_a, const float *d_b, float *d_c, int32_t N, int32_t K,
                     int32_t use_bf16, int32_t variant, void *stream);
 
+/* Diagnostic: C[128, G] = X^T Y for X [128 samples, 128], Y [128 samples, G] (fp32 in, bf16 inside) with both operands
+ * read MN-major from the activation tile layout of the fused kernels (samples = reduction dimension); variant 0 / 1 =
+ * the two assignments of the descriptor's LBO / SBO fields.                                                          */
+int sdb_tc_selftest_mn(const float *d_x, const float *d_y, float *d_c, int32_t G, int32_t variant, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

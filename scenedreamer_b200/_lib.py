@@ -56,6 +56,7 @@ SIGNATURES = {
                                  c_void_p]),
     'sdb_debug_train_layout': (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_i64)]),
     'sdb_debug_set_progress_buffer': (None, [c_void_p]),
+    'sdb_tc_selftest_mn': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
     'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
 }
 

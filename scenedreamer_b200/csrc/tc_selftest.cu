@@ -102,3 +102,84 @@ extern "C" int sdb_tc_selftest(const float *d_a, const float *d_b, float *d_c, i
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
+
+
+// ---- MN-major operands (diagnostic for the planned weight-gradient kernel) ---------------------------------------------
+// C[F=128, G] = X^T Y with X [S=128 samples, 128], Y [S=128, G]: the SAMPLES are the reduction dimension, and X / Y sit in
+// shared memory exactly as the fused kernels keep activations: [feature chunk of 8][128 sample rows][8 features] (16 B per
+// row).  Read as an MMA operand with M (or N) = features and K = samples this is an MN-major canonical layout: 8 features
+// contiguous, the 8 samples of a core matrix 16 B apart, next 8 samples +128 B, next 8 features +2048 B.
+// variant 0: LBO = 128 (K direction), SBO = 2048 (MN direction); variant 1: swapped.
+namespace {
+__global__ void __launch_bounds__(128)
+tc_selftest_mn_kernel(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ c, int G, int variant)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sX = smem;
+    uint8_t *sY = smem + 128 * 128 * 2;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sY + 128 * G * 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 128 * 16; i += 128) {           // X: 128 samples x 16 feature chunks
+        const int r = i / 16, kc = i % 16;
+        const float *src = x + (size_t)r * 128 + kc * 8;
+        *reinterpret_cast<uint4 *>(sX + tc05::chunk_off(128, r, kc)) =
+            make_uint4(tc05::pack2<true>(src[0], src[1]), tc05::pack2<true>(src[2], src[3]), tc05::pack2<true>(src[4], src[5]),
+                       tc05::pack2<true>(src[6], src[7]));
+    }
+    for (int i = tid; i < 128 * (G / 8); i += 128) {
+        const int r = i / (G / 8), kc = i % (G / 8);
+        const float *src = y + (size_t)r * G + kc * 8;
+        *reinterpret_cast<uint4 *>(sY + tc05::chunk_off(128, r, kc)) =
+            make_uint4(tc05::pack2<true>(src[0], src[1]), tc05::pack2<true>(src[2], src[3]), tc05::pack2<true>(src[4], src[5]),
+                       tc05::pack2<true>(src[6], src[7]));
+    }
+    uint32_t cols = 32;
+    while ((int)cols < G) cols <<= 1;
+    if (tid == 0) {
+        tc05::mbar_init(bar, 1);
+        tc05::fence_mbar_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(tmem_slot, cols);
+    tc05::fence_proxy_async_smem();
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    tc05::fence_after_thread_sync();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = tc05::make_idesc(128, G, true) | (1u << 15) | (1u << 16);       // A and B MN-major
+        const uint32_t kdir = 128, mndir = 128 * 16;
+        for (int kk = 0; kk < 8; kk++) {                  // 16 samples per MMA
+            const uint32_t lbo = variant == 0 ? kdir : mndir, sbo = variant == 0 ? mndir : kdir;
+            const uint64_t da = tc05::make_smem_desc(tc05::smem_u32(sX) + kk * 256, lbo, sbo);
+            const uint64_t db = tc05::make_smem_desc(tc05::smem_u32(sY) + kk * 256, lbo, sbo);
+            tc05::mma_f16_ss(tmem, da, db, idesc, kk > 0 ? 1u : 0u);
+        }
+        tc05::mma_commit(bar);
+    }
+    tc05::mbar_wait(bar, 0);
+    tc05::fence_after_thread_sync();
+    for (int c0 = 0; c0 < G; c0 += 32) {
+        float v[32];
+        tc05::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tc05::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if (c0 + j < G) c[(size_t)tid * G + c0 + j] = v[j];
+    }
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem, cols);
+}
+}  // namespace
+
+extern "C" int sdb_tc_selftest_mn(const float *d_x, const float *d_y, float *d_c, int32_t G, int32_t variant, void *stream)
+{
+    if (!d_x || !d_y || !d_c) return SDB_EINVAL;
+    if (G < 16 || G > 256 || G % 16) return SDB_EINVAL;
+    const size_t smem = (size_t)128 * 128 * 2 + (size_t)128 * G * 2 + 64;
+    SDB_CUDA(cudaFuncSetAttribute(tc_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_selftest_mn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(d_x, d_y, d_c, G, variant);
+    SDB_CHECK_LAUNCH();
+    return SDB_OK;
+}

@@ -273,3 +273,22 @@ def test_dda_empty_space_flight_is_bit_identical(world, block_log2):
         assert torch.equal(bits(torch.nan_to_num(a[1], nan=-1.0)), bits(torch.nan_to_num(b[1], nan=-1.0)))
     finally:
         ops.HEIGHT_BOUND_BLOCK_LOG2 = old
+
+
+@pytest.mark.parametrize('G', [64, 256])
+def test_tcgen05_mn_major_operands_from_activation_tiles(G):
+    """The activation tile layout of the fused kernels ([8-feature chunk][128 sample rows][16 B]) read as an MN-major
+    tcgen05 operand with the samples as the reduction dimension (descriptor: LBO = 128 B along K, SBO = 2048 B along MN,
+    instruction-descriptor major bits set): C = X^T Y, the shape of a weight-gradient GEMM."""
+    import ctypes
+    from scenedreamer_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(128, 128, generator=g).to(DEV)
+    y = torch.randn(128, G, generator=g).to(DEV)
+    c = torch.zeros(128, G, device=DEV)
+    code = _lib.lib().sdb_tc_selftest_mn(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(c.data_ptr()), G, 0,
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(code, 'sdb_tc_selftest_mn')
+    torch.cuda.synchronize()
+    ref = x.bfloat16().float().t() @ y.bfloat16().float()
+    assert float((c - ref).abs().max()) <= 1e-3
