@@ -6,10 +6,13 @@
 
 A "step" is ONE frame of the C2 workload: 540x960 output pixels, 24 samples/ray,
 scene_size 1024, cam_mode 0, pad 30 -> 570x990 rays raycast + shaded:
-    a1  ray/voxel DDA                        (sdb_ray_voxel_intersection_perspective)
+    a1  ray/voxel DDA                        (sdb_ray_voxel_intersection_perspective_ex, exact empty-space flight)
     a9  sky branch: PE + SKYMLP + frame mean  (sdb_sky_forward: same tcgen05 engine, per ray)
     a2-a8, a10-a12 fused per-pixel kernel    (sdb_render_rays_forward: tcgen05 MLP, hash gather, compositing)
 Credit = OUTPUT samples: 518,400 px x 24 = 12,441,600 samples per frame (padding rays are overhead).
+`value` / `e2e` are the product default (ray tiles stop once every live ray's transmittance is < 1e-7);
+`value_exact_march` is the same measurement with that early termination off (every sample of every live
+tile shaded) -- the two differ by less than 2e-7 in the rendered features.
 Each step renders a different pose of the 40-frame cam_mode-0 trajectory and L2 is flushed between
 steps (256 MiB memset outside the per-step CUDA events).
 Multi-GPU (weak scaling): every rank renders its own frames (frame f -> rank f mod N); the finished
