@@ -4,7 +4,9 @@
  *
  * Conventions
  *   - every pointer named d_* is a DEVICE pointer owned by the caller; nothing is allocated,
- *     freed or retained by the library (no ownership transfer, re-entrant, no global state);
+ *     freed or retained by the library (no ownership transfer, re-entrant; the only process-wide
+ *     state is one cuBLAS handle per device, created by the first sdb_*_backward call, and the
+ *     optional diagnostics pointer);
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - every entry point returns 0 on success, a positive cudaError_t on a CUDA failure, or a
  *     negative SDB_E* code for an argument error; no exceptions cross the ABI.  The Python

@@ -32,6 +32,11 @@
 //     ~2^-16 resp. ~2^-21 relative, i.e. fp32-grade for the 1e-3 parity bar); accumulation is fp32 in TMEM;
 //   * sky-only tiles never reach the render kernel: a pre-pass writes their outputs and compacts the
 //     list of live tiles (their compositing weights are exactly zero, scenedreamer.py:376).
+//   * early termination + dynamic tile scheduling (inference): a tile stops marching once every live ray is opaque
+//     (one-step-delayed decision, see ESTOP below); further tiles are drawn from a global counter;
+//   * training: the TRAIN variants additionally leave a per-sample record in HBM, and the same engine runs the
+//     data-gradient chains (MODE kBwd / kSkyBwd: transposed weights, LeakyReLU' from recorded sign words);
+//     render_train.cu holds the rest of the backward (compositing, table scatter, weight-gradient GEMMs).
 #include "rf_common.cuh"
 
 namespace rf {
