@@ -1,0 +1,110 @@
+"""CPU tests of host-side logic that needs no GPU: sizing entry points of the C ABI and the dispatch rules of the
+reference-side hook (scenedreamer_b200.integration.fused_forward_perpix) with the compute calls stubbed out."""
+import types
+
+import pytest
+import torch
+
+from scenedreamer_b200 import _lib, integration, render
+
+
+def test_sizing_entry_points_without_gpu():
+    L = _lib.lib()
+    assert L.sdb_render_train_record_bytes(1, 262, 262, 24) > L.sdb_render_train_record_bytes(1, 128, 128, 24) > 0
+    assert L.sdb_render_train_record_bytes(0, 262, 262, 24) == 0 and L.sdb_render_train_record_bytes(1, 262, 262, 65) == 0
+    assert L.sdb_render_backward_workspace_bytes(1, 262, 262, 24, 16, 19) > (16 << 19) * 32      # holds the table gradient
+    assert L.sdb_sky_train_record_bytes(1, 262, 262) > 0 and L.sdb_sky_backward_workspace_bytes(1, 262, 262) > 0
+    assert L.sdb_mlp_backward_pack_bytes() > 0 and L.sdb_sky_backward_pack_bytes() > 0
+    import ctypes
+    dims = (ctypes.c_int64 * 3)(103, 1024, 1024)
+    assert L.sdb_height_bound_elems(dims, 4) == 64 * 64 and L.sdb_height_bound_elems(dims, 1) == 0
+    # compute entry points refuse bad arguments before touching the device
+    assert L.sdb_render_rays_train_forward(None, None, None) != 0
+    assert L.sdb_render_rays_backward(None, None, None, None) != 0
+    assert L.sdb_sky_backward(1, 8, 8, None, None, None, None, None, None, None, None) != 0
+
+
+class _FakeTensor:
+    """Just enough of a CUDA tensor for the dispatch rules (shape, is_cuda, slicing, == 0)."""
+
+    def __init__(self, t):
+        self.t = t
+        self.shape = t.shape
+        self.is_cuda = True
+        self.device = 'cuda:0'
+
+    def __getitem__(self, idx):
+        return _FakeTensor(self.t[idx])
+
+    def __eq__(self, other):
+        return self.t == other
+
+    def contiguous(self):
+        return self
+
+
+def _fake_generator(n_views, monkeypatch, calls):
+    gen = types.SimpleNamespace()
+    lin = torch.nn.Linear(4, 4)
+    gen.render_net, gen.sky_net, gen.hash_encoder = lin, torch.nn.Linear(2, 2), torch.nn.Linear(2, 2)
+    gen.hash_encoder.per_level_scale, gen.hash_encoder.base_resolution = 1.38, 16
+    gen.hash_encoder.log2_hashmap_size, gen.hash_encoder.num_levels = 19, 16
+    gen.voxel = types.SimpleNamespace(voxel_t=torch.zeros(4, 8, 8))
+    gen.clip_feat_map, gen.keep_sky_out, gen.keep_sky_out_avgpool, gen.sky_global_avgpool = True, True, True, True
+    gen.sample_use_box_boundaries, gen.raw_noise_std = False, 0.0
+    gen.pe_params, gen.pe_params_sky = [0, 0, 0, False], [5, True]
+    gen.coarse_deterministic_sampling, gen.num_samples, gen.sample_depth, gen.dists_scale = True, 4, 3, 0.25
+    st = types.SimpleNamespace(lut=torch.zeros(4, dtype=torch.int32))
+    st.reference_forward = lambda *a: calls.append('reference') or ('ref',)
+
+    class R:
+        def forward(self, *a, **k):
+            calls.append('inference')
+            n = a[0].shape[0]
+            z = torch.zeros(n, 2, 2)
+            return dict(net_out=torch.zeros(n, 2, 2, 64), total_weight=z, weights=z, rand_depth=z, sky=torch.zeros(n, 2, 2, 64))
+    st.get = lambda g: R()
+    gen._sdb200 = st
+
+    def fake_train(P, vid, *a, **k):
+        calls.append('train')
+        z = torch.zeros(1, 2, 2)
+        return dict(net_out=torch.zeros(1, 2, 2, 64), total_weight=z, weights=z, rand_depth=z, sky=torch.zeros(1, 2, 2, 64))
+    monkeypatch.setattr(render, 'render_rays_train', fake_train)
+    vid = _FakeTensor(torch.ones(n_views, 2, 2, 6, 1, dtype=torch.int32))
+    dep = _FakeTensor(torch.zeros(n_views, 2, 2, 2, 6, 1))
+    rd = _FakeTensor(torch.zeros(n_views, 2, 2, 1, 3))
+    return gen, vid, dep, rd
+
+
+def test_hook_dispatch_rules(monkeypatch):
+    calls = []
+    gen, vid, dep, rd = _fake_generator(1, monkeypatch, calls)
+    ori, z, genc = torch.zeros(1, 3), torch.zeros(1, 4), torch.zeros(1, 2)
+    f = integration.fused_forward_perpix
+    with torch.no_grad():
+        out = f(gen, None, vid, dep, rd, ori, z, genc)
+    assert calls == ['inference'] and len(out) == 12
+    calls.clear()
+    out = f(gen, None, vid, dep, rd, ori, z, genc)                 # parameters require grad -> recording forward + fused backward
+    assert calls == ['train'] and len(out) == 12
+    calls.clear()
+    gen2, vid2, dep2, rd2 = _fake_generator(3, monkeypatch, calls)
+    out = f(gen2, None, vid2, dep2, rd2, torch.zeros(3, 3), torch.zeros(3, 4), genc)
+    assert calls == ['train'] * 3 and out[0].shape[0] == 3           # a batch = one recorded pass per view
+    calls.clear()
+    gen.sky_avg = torch.zeros(1, 64)                                 # pre-set sky mean under autograd: reference composition
+    f(gen, None, vid, dep, rd, ori, z, genc)
+    assert calls == ['reference']
+    calls.clear()
+    del gen.sky_avg
+    gen.raw_noise_std = 0.5                                          # option outside the fused path
+    with torch.no_grad():
+        f(gen, None, vid, dep, rd, ori, z, genc)
+    assert calls == ['reference']
+    calls.clear()
+    gen.raw_noise_std = 0.0
+    for q in list(gen.render_net.parameters()) + list(gen.hash_encoder.parameters()):
+        q.requires_grad_(False)
+    f(gen, None, vid, dep, rd, ori, z, genc)                        # nothing to differentiate: inference kernel even with grad mode on
+    assert calls == ['inference']
