@@ -200,7 +200,10 @@ mlp_kernel(const Params p)
     volatile int *sVote = sStop + 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_work = ONE_STEP ? p.n_tiles : *p.n_live;
+    // the render gradient chain has no dependency between the sample steps of a tile: there every (tile, step) is its own
+    // work item (work_mult = S, one step each), which balances a few hundred tiles over 148 CTAs far better than whole tiles
+    const int wmult = (MODE == kBwd && p.work_mult > 1) ? p.work_mult : 1;
+    const int n_work = ONE_STEP ? p.n_tiles : *p.n_live * wmult;
     constexpr bool STATE = MODE == kRender;      // per-ray sampling state (gather -> epilogue hand-off) exists
     const int S = ONE_STEP ? 1 : p.S;
 
@@ -265,7 +268,7 @@ mlp_kernel(const Params p)
         for (int it = 0;; it++) {
             const int work = fetch_work(it);
             if (work < 0) break;
-            const int tile = ONE_STEP ? work : p.tile_list[work];
+            const int tile = ONE_STEP ? work : p.tile_list[work / wmult];
             const TileCoord tc = tile_coord(p, tile);
             const int buf = it & 1;
             const float *st = sState + buf * kStFloats * kRows;
@@ -328,36 +331,53 @@ mlp_kernel(const Params p)
                     if ((tid & 127) == 0) SDB_MARK(half, 2, n, l);
 #pragma unroll 1
                     for (int c0 = 0; c0 < 128; c0 += 32) {
-                        float v[32];
-                        tc05::tmem_ld32(acc + c0, v);
-                        tc05::tmem_ld_wait();
-                        if constexpr (BWD) {
-                            if (MODE == kBwd && l == 2) {   // dA4 += dsigma * fc_sigma.weight (sigma taps A4, layers.py:115)
-                                const float *ws = sF + kFWsig + half * 128 + c0;
+                        // a 32-column chunk in two 16-column halves (16 live accumulator registers instead of 32: the
+                        // compositing state of the tile stays in registers next to them)
+                        uint32_t rec[16];            // TRAIN / chain: bf16 (round-to-nearest) copy of the chunk for the record
+                        uint32_t mword = 0;          // TRAIN: LeakyReLU sign bits of the chunk
+                        (void)rec; (void)mword;
+                        const uint32_t word = c0 == 0 ? mw.x : (c0 == 32 ? mw.y : (c0 == 64 ? mw.z : mw.w));
+                        (void)word;
 #pragma unroll
-                                for (int j = 0; j < 32; j++) v[j] = fmaf(dsig, ws[j], v[j]);
+                        for (int hh = 0; hh < 2; hh++) {
+                            float v[16];
+                            tc05::tmem_ld16(acc + c0 + 16 * hh, v);
+                            tc05::tmem_ld_wait();
+                            if constexpr (BWD) {
+                                if (MODE == kBwd && l == 2) {   // dA4 += dsigma * fc_sigma.weight (sigma taps A4, layers.py:115)
+                                    const float *ws = sF + kFWsig + half * 128 + c0 + 16 * hh;
+#pragma unroll
+                                    for (int j = 0; j < 16; j++) v[j] = fmaf(dsig, ws[j], v[j]);
+                                }
+                                // dZ = dA * LeakyReLU'(z): slope 1 where the forward activation was > 0, else 0.2
+#pragma unroll
+                                for (int j = 0; j < 16; j++) v[j] = ((word >> (16 * hh + j)) & 1u) ? v[j] : 0.2f * v[j];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.2f * v[j]);          // LeakyReLU(0.2)
+                                if (MODE == kRender && l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
+                                    const float *ws = sF + kFWsig + half * 128 + c0 + 16 * hh;
+#pragma unroll
+                                    for (int j = 0; j < 16; j++) sig_part = fmaf(v[j], ws[j], sig_part);
+                                }
                             }
-                            // dZ = dA * LeakyReLU'(z): slope 1 where the forward activation was > 0, else 0.2
-                            const uint32_t word = c0 == 0 ? mw.x : (c0 == 32 ? mw.y : (c0 == 64 ? mw.z : mw.w));
+                            if constexpr (TRAIN || BWD) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) v[j] = ((word >> j) & 1u) ? v[j] : 0.2f * v[j];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.2f * v[j]);          // LeakyReLU(0.2)
-                            if (MODE == kRender && l == 3) {   // sigma = fc_sigma(f) after fc_4's activation (layers.py:115)
-                                const float *ws = sF + kFWsig + half * 128 + c0;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) sig_part = fmaf(v[j], ws[j], sig_part);
+                                for (int q = 0; q < 8; q++) rec[8 * hh + q] = tc05::pack2<true>(v[2 * q], v[2 * q + 1]);
                             }
-                        }
+                            if constexpr (TRAIN) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            uint4 hi, lo;
-                            const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
-                            split8<PREC>(v8, hi, lo);
-                            const uint32_t off = tc05::chunk_off(kRows, row, half * 16 + (c0 >> 3) + q);
-                            *reinterpret_cast<uint4 *>(sHhi + off) = hi;
-                            if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
+                                for (int j = 0; j < 16; j++) mword |= (v[j] > 0.0f ? 1u : 0u) << (16 * hh + j);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                uint4 hi, lo;
+                                const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * q]);
+                                split8<PREC>(v8, hi, lo);
+                                const uint32_t off = tc05::chunk_off(kRows, row, half * 16 + (c0 >> 3) + 2 * hh + q);
+                                *reinterpret_cast<uint4 *>(sHhi + off) = hi;
+                                if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
+                            }
                         }
                         // a 32-column K chunk of the next layer's operand is complete (all 128 rows once the four
                         // quadrant warps of this half have arrived): the MMA issuer may start on it
@@ -365,25 +385,16 @@ mlp_kernel(const Params p)
                         tc05::mbar_arrive(&bars[B_CHUNK + half * 4 + (c0 >> 5)]);
                         // the training record is written AFTER the chunk has been handed to the MMA issuer (off the critical path)
                         if constexpr (TRAIN || BWD) {
-                            // bf16 (round-to-nearest) copy of the chunk for the weight-gradient GEMMs:
                             // forward: A_{l+1}[slot][128*half + c0 ..], backward: dZ_{6-l}[slot][...]
                             uint16_t *dst = TRAIN
                                 ? p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + half * 128 + c0
                                 : p.tr.dz + ((long long)(NACT - 1 - l) * p.tr.slot_cap + slot) * kHidden + half * 128 + c0;
 #pragma unroll
                             for (int q = 0; q < 2; q++)
-                                st_global_v8(dst + 16 * q,
-                                             make_uint4(tc05::pack2<true>(v[16 * q], v[16 * q + 1]), tc05::pack2<true>(v[16 * q + 2], v[16 * q + 3]),
-                                                        tc05::pack2<true>(v[16 * q + 4], v[16 * q + 5]), tc05::pack2<true>(v[16 * q + 6], v[16 * q + 7])),
-                                             make_uint4(tc05::pack2<true>(v[16 * q + 8], v[16 * q + 9]), tc05::pack2<true>(v[16 * q + 10], v[16 * q + 11]),
-                                                        tc05::pack2<true>(v[16 * q + 12], v[16 * q + 13]), tc05::pack2<true>(v[16 * q + 14], v[16 * q + 15])));
+                                st_global_v8(dst + 16 * q, make_uint4(rec[8 * q], rec[8 * q + 1], rec[8 * q + 2], rec[8 * q + 3]),
+                                             make_uint4(rec[8 * q + 4], rec[8 * q + 5], rec[8 * q + 6], rec[8 * q + 7]));
                         }
-                        if constexpr (TRAIN) {
-                            uint32_t word = 0;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) word |= (v[j] > 0.0f ? 1u : 0u) << j;
-                            p.tr.mask[((step_id * kNumAct + l) * kRows + row) * 8 + half * 4 + (c0 >> 5)] = word;
-                        }
+                        if constexpr (TRAIN) p.tr.mask[((step_id * kNumAct + l) * kRows + row) * 8 + half * 4 + (c0 >> 5)] = mword;
                     }
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (g & 1u)]);        // accumulator buffer (g & 1) is free again
@@ -562,7 +573,7 @@ mlp_kernel(const Params p)
             for (int it = 0;; it++) {
                 const int work = fetch_work(it);
                 if (work < 0) break;
-                const int tile = ONE_STEP ? work : p.tile_list[work];
+                const int tile = ONE_STEP ? work : p.tile_list[work / wmult];
                 const TileCoord tc = tile_coord(p, tile);
                 const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
                 for (int s = 0; s < S; s++, n++) {
@@ -707,7 +718,7 @@ mlp_kernel(const Params p)
             }
             const int work = fetch_work(it);
             if (work < 0) break;
-            const int tile = ONE_STEP ? work : p.tile_list[work];
+            const int tile = ONE_STEP ? work : p.tile_list[work / wmult];
             const TileCoord tc = tile_coord(p, tile);
             const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
             const bool valid = (y < p.H) && (x < p.W);

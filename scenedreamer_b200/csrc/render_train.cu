@@ -492,10 +492,15 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         return SDB_OK;
     }
     mark();
-    // 2. data-gradient chain on the tensor-core engine
+    // 2. data-gradient chain on the tensor-core engine: one work item per (live tile, sample step) -- the slot index
+    //    (work * 1 + 0) * 128 + row of such an item IS the record's (tile * S + step) * 128 + row
     {
-        const int grid = n_live < sdb_num_sms() ? n_live : sdb_num_sms();
-        const int rc = launch_bwd_chain(p, grid, st);
+        Params pc = p;
+        pc.work_mult = p.S;
+        pc.S = 1;
+        const long long items = (long long)n_live * p.S;
+        const int grid = items < sdb_num_sms() ? (int)items : sdb_num_sms();
+        const int rc = launch_bwd_chain(pc, grid, st);
         if (rc != SDB_OK) return rc;
     }
     mark();

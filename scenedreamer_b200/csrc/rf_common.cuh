@@ -193,6 +193,7 @@ struct Params {
     const int32_t *n_live;
     int32_t *steps_done;           // optional counter (workspace word 1): sample steps actually executed, summed over tiles
     int32_t *work_counter;         // optional (workspace word 2, zeroed per launch): dynamic tile scheduling across the persistent CTAs
+    int work_mult;                 // > 1: every live tile is work_mult independent work items (the gradient chain: one per sample step)
     int n_tiles;
     int tiles_x, tiles_y;
     // sky mode
