@@ -213,7 +213,7 @@ mlp_kernel(const Params p)
         for (int i = 0; i < 4; i++) { tc05::mbar_init(&bars[B_WFULL + i], 1); tc05::mbar_init(&bars[B_WEMPTY + i], 1); }
         tc05::mbar_init(&bars[B_FEAT], kGatherThreads);
         tc05::mbar_init(&bars[B_HFREE], 1);
-        for (int i = 0; i < 8; i++) tc05::mbar_init(&bars[B_CHUNK + i], kEpiThreads / 2);
+        for (int i = 0; i < 16; i++) tc05::mbar_init(&bars[B_CHUNK + i], kEpiThreads / 2);
         tc05::mbar_init(&bars[B_ACC], 1);
         tc05::mbar_init(&bars[B_OUTRDY], 1);
         tc05::mbar_init(&bars[B_EPIDONE], kEpiThreads);
@@ -378,11 +378,11 @@ mlp_kernel(const Params p)
                                 *reinterpret_cast<uint4 *>(sHhi + off) = hi;
                                 if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = lo;
                             }
+                            // a 16-column K slab of the next layer's operand is complete (all 128 rows once the four quadrant
+                            // warps of this half have arrived): the MMA issuer may start on it
+                            tc05::fence_proxy_async_smem();
+                            tc05::mbar_arrive(&bars[B_CHUNK + half * 8 + (c0 >> 4) + hh]);
                         }
-                        // a 32-column K chunk of the next layer's operand is complete (all 128 rows once the four
-                        // quadrant warps of this half have arrived): the MMA issuer may start on it
-                        tc05::fence_proxy_async_smem();
-                        tc05::mbar_arrive(&bars[B_CHUNK + half * 4 + (c0 >> 5)]);
                         // the training record is written AFTER the chunk has been handed to the MMA issuer (off the critical path)
                         if constexpr (TRAIN || BWD) {
                             // forward: A_{l+1}[slot][128*half + c0 ..], backward: dZ_{6-l}[slot][...]

@@ -71,25 +71,27 @@ template <int MODE> __host__ __device__ constexpr int64_t packBytes(int parts) {
 template <int KS, int MODE> __host__ __device__ constexpr int num_stages(int l) {
     return l == 0 ? (Net<MODE>::K0 / 16 + KS - 1) / KS : (Net<MODE>::EXT ? 1 : 0) + 16 / KS;   // [extension +] 8 chunks x (2 / KS)
 }
-// 32-column operand chunks (2 k16 steps each): chunk ids 0..3 are written by the epilogue half that owns
-// columns 0..127, ids 4..7 by the other half; both halves advance together -> consumption order 0,4,1,5,2,6,3,7
-__host__ __device__ constexpr int chunk_order(int c) { return (c >> 1) + (c & 1) * 4; }
+// The epilogue hands the next layer's operand over in 16-column pieces = one k16 slab each: slabs 0..7 come from the
+// epilogue half that owns columns 0..127, slabs 8..15 from the other half, both halves advance together.  Consumption
+// order: KS = 1 (x3 modes, one slab per ring stage): 0,8,1,9,...,7,15; KS = 2 (single-pass mode, two slabs per stage):
+// (0,1),(8,9),(2,3),(10,11),...
+template <int KS> __host__ __device__ constexpr int hidden_stage_slab(int i) {
+    return KS == 1 ? (i >> 1) + (i & 1) * 8 : ((i >> 1) * 2 + (i & 1) * 8);
+}
 template <int KS, int MODE> __host__ __device__ constexpr int stage_kk(int l, int j) {
     if (l == 0) return j * KS;
     if (Net<MODE>::EXT && j == 0) return 16;
-    const int i = j - (Net<MODE>::EXT ? 1 : 0), per = 2 / KS, c = i / per, r = i % per;
-    return chunk_order(c) * 2 + r * KS;
+    return hidden_stage_slab<KS>(j - (Net<MODE>::EXT ? 1 : 0));
 }
 template <int KS, int MODE> __host__ __device__ constexpr int stage_cnt(int l, int j) {
     if (l == 0) { const int nk = Net<MODE>::K0 / 16; return (j * KS + KS <= nk) ? KS : nk - j * KS; }
     return (Net<MODE>::EXT && j == 0) ? 1 : KS;
 }
-// chunk barrier to wait on before stage j of a hidden-fed layer (-1: none)
+// slab barrier to wait on before stage j of a hidden-fed layer (-1: none): the LAST slab of the stage (a half's threads
+// arrive on its slab barriers in order, so that one implies the earlier ones)
 template <int KS, int MODE> __host__ __device__ constexpr int stage_chunk_wait(int l, int j) {
     if (l == 0 || (Net<MODE>::EXT && j == 0)) return -1;
-    const int i = j - (Net<MODE>::EXT ? 1 : 0), per = 2 / KS;
-    if (i % per != 0) return -1;
-    return chunk_order(i / per);
+    return hidden_stage_slab<KS>(j - (Net<MODE>::EXT ? 1 : 0)) + KS - 1;
 }
 
 // Static schedule: the number of ring stages per sample step is padded to a multiple of the ring depth (4),
@@ -124,7 +126,7 @@ __host__ __device__ constexpr Smem smem_map(bool x3) {
     m.frac = o; o += ((kMaxS + 1) * 4 + 15) / 16 * 16;
     m.sig = o; o += 2 * kRows * 4;
     m.state = o; o += 2 * (2 * kMaxM + 6) * kRows * 4;
-    m.bars = o; o += 32 * 8;
+    m.bars = o; o += 40 * 8;
     m.tmem_slot = o; o += 16;
     m.stop = o; o += 16;                         // early termination: int stop_step[2] (per tile buffer), int vote[2]
     m.sched = o; o += 32;                        // dynamic tile scheduler: int work[4] (ring), int published
@@ -141,9 +143,10 @@ constexpr int kStFlags = 2 * kMaxM + 5;      // 1 (uint32: bit0 live, bit1 sky_m
 constexpr int kStFloats = 2 * kMaxM + 6;
 
 // barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 8, B_OUTRDY, B_EPIDONE,
+enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 16, B_OUTRDY, B_EPIDONE,
        B_STRDY = B_EPIDONE + 2, B_STFREE = B_STRDY + 2, B_COUNT = B_STFREE + 2 };
-static_assert(B_COUNT <= 32, "barrier table");
+constexpr int kBarSlots = 40;
+static_assert(B_COUNT <= kBarSlots, "barrier table");
 
 // ---- training-side record of one forward pass (all DEVICE pointers; see sdb_train_layout in sdb200.h) ----
 // A "slot" is one (work item, sample step, tile row): slot = (work * S + s) * 128 + row, where `work` is the
