@@ -357,7 +357,8 @@ static int cublas_for_stream(cudaStream_t st, void *ws, size_t ws_bytes, cublasH
     if (dev < 0 || dev >= 64) return SDB_EUNSUPPORTED;
     if (!g_cublas[dev] && cublasCreate(&g_cublas[dev]) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorInitializationError;
     if (cublasSetStream(g_cublas[dev], st) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
-    if (cublasSetWorkspace(g_cublas[dev], ws, ws_bytes) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
+    if (getenv("SDB_CUBLAS_OWN_WS") == nullptr || atoi(getenv("SDB_CUBLAS_OWN_WS")) != 0)      // diagnostics: 0 = cuBLAS' default pool
+        if (cublasSetWorkspace(g_cublas[dev], ws, ws_bytes) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
     *out = g_cublas[dev];
     return SDB_OK;
 }
@@ -454,6 +455,9 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
     p.tr.dc = dc32; p.tr.dsig = dsig32; p.tr.dz = dz; p.tr.dx0 = dx0;
     p.pack = (const uint8_t *)g->d_bwd_pack; p.pack_stride = g->bwd_pack_stride;
 
+    const bool timing0 = getenv("SDB_TIMING") != nullptr;
+    cudaEvent_t tev0 = nullptr;
+    if (timing0) { cudaEventCreate(&tev0); cudaEventRecord(tev0, st); }
     // number of live ray tiles of the recorded forward pass (sizes the GEMMs and the grids below)
     int32_t n_live = 0;
     SDB_CUDA(cudaMemcpyAsync(&n_live, rec + rl.hdr, 4, cudaMemcpyDeviceToHost, st));
@@ -554,8 +558,10 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         cudaStreamSynchronize(st);
         float ms[8] = {0};
         for (int i = 0; i + 1 < ntev; i++) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
-        fprintf(stderr, "[sdb timing] backward: compositing %.3f ms, chain %.3f ms, table %.3f ms, weight GEMMs %.3f ms (n_live %d)\n", ms[0],
-                ms[1], ms[2], ms[3], n_live);
+        float pre = 0.0f;
+        if (tev0) { cudaEventElapsedTime(&pre, tev0, tev[0]); cudaEventDestroy(tev0); }
+        fprintf(stderr, "[sdb timing] backward: prologue %.3f ms, compositing %.3f ms, chain %.3f ms, table %.3f ms, weight GEMMs %.3f ms (n_live %d)\n",
+                pre, ms[0], ms[1], ms[2], ms[3], n_live);
         for (int i = 0; i < ntev; i++) cudaEventDestroy(tev[i]);
     }
     return SDB_OK;

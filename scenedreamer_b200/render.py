@@ -302,6 +302,27 @@ class FusedPerPixelRenderer:
 # ================================================================================================
 # Training: fused forward that records the pass + the fused backward (sdb_render_rays_backward)
 # ================================================================================================
+# The training record and the backward workspace are several GB each (3.9 + 4.0 KB per sample).  Asking torch's caching
+# allocator for them every step makes it split and re-grow its multi-GB blocks (a 7.4 GB request right after a 6.9 GB
+# one was carved out of the cached 7.4 GB block ends in cudaMalloc) -- measured as 10-40 ms of jitter per step.  They are
+# therefore recycled through this exact-size pool: taken in forward / backward, handed back when backward is done.
+_scratch_pool = {}
+
+
+def _take_scratch(nbytes, dev):
+    lst = _scratch_pool.get((int(nbytes), str(dev)))
+    if lst:
+        return lst.pop()
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+
+
+def _give_scratch(t):
+    if t is not None:
+        lst = _scratch_pool.setdefault((int(t.numel()), str(t.device)), [])
+        if len(lst) < 2:
+            lst.append(t)
+
+
 class _RenderGrads(ctypes.Structure):
     _fields_ = [
         ('d_grad_net_out', ctypes.c_void_p), ('d_bwd_pack', ctypes.c_void_p), ('bwd_pack_stride', ctypes.c_int64),
@@ -383,7 +404,7 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             wts = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev)
             rdp = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev)
             ws = torch.empty(int(L.sdb_render_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
-            record = torch.empty(int(L.sdb_render_train_record_bytes(N, H, W, S)), dtype=torch.uint8, device=dev)
+            record = _take_scratch(L.sdb_render_train_record_bytes(N, H, W, S), dev)
             prm, keep = _RenderParams(), []
             _fill_render_params(prm, keep, voxel_id, depth2, raydirs, cam_ori, genc_, cfg['voxel_dims'], lut, pack, sky_, sky_avg_,
                                 table3, S, cfg['sample_depth'], cfg['dists_scale'], cfg.get('uniforms'), prec,
@@ -419,8 +440,7 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             g_wout = torch.empty(64, 272, dtype=torch.float32, device=dev)
             g_sky = torch.zeros(N, H, W, 64, dtype=torch.float32, device=dev)
             g_sky_avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
-            wsb = torch.empty(int(L.sdb_render_backward_workspace_bytes(N, H, W, S, int(cfg['L']), int(cfg['log2_T']))),
-                              dtype=torch.uint8, device=dev)
+            wsb = _take_scratch(L.sdb_render_backward_workspace_bytes(N, H, W, S, int(cfg['L']), int(cfg['log2_T'])), dev)
             gr = _RenderGrads()
             gr.d_grad_net_out, gr.d_bwd_pack, gr.bwd_pack_stride = _ptr(g), _ptr(bpack), 0
             gr.d_table = _ptr(embeddings_)
@@ -429,6 +449,10 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             gr.d_grad_sky, gr.d_grad_sky_avg, gr.d_workspace = _ptr(g_sky), _ptr(g_sky_avg), _ptr(wsb)
             _lib.check(L.sdb_render_rays_backward(ctypes.byref(prm), _ptr(ctx.record), ctypes.byref(gr), _stream(dev)),
                        'sdb_render_rays_backward')
+        # stream-ordered reuse: the next forward / backward run on the same stream after these kernels
+        _give_scratch(wsb)
+        _give_scratch(ctx.record)
+        ctx.record = None
         s_fcma, s_wsig, s_bsig, s_sky, s_skyavg, s_genc = ctx.shapes
         n_lab = s_fcma[1]
         d_genc = torch.zeros(s_genc, dtype=torch.float32, device=dev)
@@ -462,7 +486,7 @@ class _SkyTrainFn(torch.autograd.Function):
             sky = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
             avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
             ws = torch.empty(int(L.sdb_sky_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
-            record = torch.empty(int(L.sdb_sky_train_record_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+            record = _take_scratch(L.sdb_sky_train_record_bytes(N, H, W), dev)
             _lib.check(L.sdb_sky_train_forward(_ptr(rd), N, H, W, _ptr(pack), _ptr(sky), _ptr(avg), _ptr(ws), _ptr(record),
                                                _stream(dev)), 'sdb_sky_train_forward')
         ctx.dims, ctx.record, ctx.saved = (N, H, W), record, (wh_, wout_)
@@ -482,9 +506,12 @@ class _SkyTrainFn(torch.autograd.Function):
             g_w1ext = torch.empty(256, 48, dtype=torch.float32, device=dev)
             g_wh = torch.empty(4, 256, 272, dtype=torch.float32, device=dev)
             g_wout = torch.empty(64, 272, dtype=torch.float32, device=dev)
-            wsb = torch.empty(int(L.sdb_sky_backward_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
+            wsb = _take_scratch(L.sdb_sky_backward_workspace_bytes(N, H, W), dev)
             _lib.check(L.sdb_sky_backward(N, H, W, _ptr(ctx.record), _ptr(g), _ptr(bpack), _ptr(g_w1ext), _ptr(g_wh), _ptr(g_wout),
                                           _ptr(wsb), _stream(dev)), 'sdb_sky_backward')
+        _give_scratch(wsb)
+        _give_scratch(ctx.record)
+        ctx.record = None
         return (None, g_w1ext[:, :33].contiguous(), g_w1ext[:, 47].reshape(ctx.shapes[0]), g_wh[:, :, :256].contiguous(),
                 g_wh[:, :, 256].contiguous(), g_wout[:, :256].contiguous(), g_wout[:, 256].contiguous())
 
