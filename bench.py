@@ -97,11 +97,11 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def build_workload(device, seed=3407):
+def build_workload(device, seed=3407, scene=SCENE, pattern=0):
     import oracle
     from scenedreamer_b200 import synth
-    world = synth.SyntheticVoxelWorld(SCENE, seed)
-    poses = synth.eval_camera_poses(world, maxstep=40, pattern=0)
+    world = synth.SyntheticVoxelWorld(scene, seed)
+    poses = synth.eval_camera_poses(world, maxstep=40, pattern=pattern)
     P = oracle.make_params(seed=0, stress=True)
     g = torch.Generator().manual_seed(8888)
     z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
@@ -167,35 +167,75 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    # name: (output H x W, samples per ray, scene_size, camera pattern, description)
+    'c2': ((540, 960), 24, 1024, 0, 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0'),
+    'c3': ((540, 960), 24, 1024, 4, 'C3: 40-frame trajectory cam_mode=4, 540x960, num_samples=24, scene_size=1024, frames sharded over the ranks'),
+    'c4': ((2160, 3840), 40, 2048, 0, 'C4: single 2160x3840 frame, num_samples=40, scene_size=2048'),
+}
+FLOP_PER_SAMPLE = 754176          # LightningMLP, SURVEY.md 8(a8)
+
+
+def pin_rank_to_gpu_numa(local):
+    """One process per GPU: keep each rank's host thread on the CPUs of its GPU's NUMA node (what the reference's
+    imaginaire/utils/gpu_affinity.py does through NVML) -- torchrun does not pin, and with 8 ranks the frame loop of the
+    ranks driving GPUs 4-7 otherwise runs across the socket.  Returns the number of CPUs in the mask (None: unchanged)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                idx = int(ids[local])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n64 = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:       # noqa: BLE001  (no NVML / no permission: leave the affinity alone)
+        pass
+    return None
+
+
 class FrameRenderer:
     """The public-API call a user makes per frame: pose (host) -> DDA -> sky -> fused render."""
 
-    def __init__(self, world, P, z, genc, lut, device, precision):
+    def __init__(self, world, P, z, genc, lut, device, precision, spp):
         from scenedreamer_b200 import ops, render
         import oracle
-        self.ops, self.render, self.dev = ops, render, device
+        self.ops, self.render, self.dev, self.spp = ops, render, device, spp
         self.P = {k: v.to(device) for k, v in P.items()}
         self.voxel = world.voxel_t.to(device)
         _, pls = oracle.grid_offsets()
         self.r = render.FusedPerPixelRenderer(self.P, world.voxel_t.shape, render.reduced_label_lut(lut), pls,
                                               precision=precision, preblend=True)
         self.z, self.genc = z.to(device), genc.to(device)
-        self.launches_per_frame = None
 
     def set_early_stop(self, T):
         self.r.early_stop = T
 
-    def frame(self, cam, events=None, ori_dev=None):
-        """cam = (ori, dir, up, f, c, res) with HOST tensors (the reference API takes the pose from the CPU and
-        passes it by value to the DDA kernel); ori_dev: optional device-resident copy of ori for the fused kernel."""
+    def frame(self, cam, events=None, rows=None, sky_sum_hook=None):
+        """cam = (ori, dir, up, f, c, res) with HOST tensors: the reference API takes the pose from the CPU
+        (scenedreamer.py:569-586); it rides in the kernel arguments of the DDA and of the fused kernel, nothing is
+        copied to the device per frame.  rows = (y0, y1): only that band of the padded frame (single-frame sharding);
+        sky_sum_hook(avg_band, n_rays_band) -> frame-global sky mean (the band means of all ranks combined)."""
         o, d, u, f, c, res = cam
+        if rows is not None:
+            y0, y1 = rows
+            c, res = [c[0] - y0, c[1]], [y1 - y0, res[1]]          # same rays: the principal point moves with the window
         vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, res, 6)
         vid, dep, rd = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0)
         sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
+        if sky_sum_hook is not None:
+            sky_avg = sky_sum_hook(sky_avg, res[0] * res[1])
         if events is not None:
             events[0].record()
-        out = self.r.forward(vid, dep, rd, (o if ori_dev is None else ori_dev).unsqueeze(0), self.z, self.genc,
-                             num_samples=SPP, sky=sky, sky_avg=sky_avg)
+        out = self.r.forward(vid, dep, rd, o.unsqueeze(0), self.z, self.genc, num_samples=self.spp, sky=sky, sky_avg=sky_avg)
         if events is not None:
             events[1].record()
         return out
@@ -203,40 +243,63 @@ class FrameRenderer:
 
 def run_gpu_arm(args):
     import torch.distributed as dist
-    from scenedreamer_b200 import synth, render, sharding
+    from scenedreamer_b200 import synth, render, sharding, _lib
     world_size = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    pinned_cpus = pin_rank_to_gpu_numa(local)
+    torch.set_num_threads(max(1, min(8, (pinned_cpus or os.cpu_count() or 8) // max(1, world_size))))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world_size > 1:
         dist.init_process_group('nccl', device_id=dev)
     precision = {'fp16': render.PRECISION_FP16, 'bf16x3': render.PRECISION_BF16X3, 'fp16x3': render.PRECISION_FP16X3}[args.precision]
-    world, poses, P, z, genc, lut = build_workload(dev)
-    fr = FrameRenderer(world, P, z, genc, lut, dev, precision)
+    out_hw, spp, scene, pattern, wl_name = WORKLOADS[args.workload]
+    strong = args.mode == 'strong'
+    samples_per_frame = out_hw[0] * out_hw[1] * spp
+    world, poses, P, z, genc, lut = build_workload(dev, scene=scene, pattern=pattern)
+    fr = FrameRenderer(world, P, z, genc, lut, dev, precision, spp)
     fr.set_early_stop(0.0 if args.no_early_stop else None)
-    cams = [synth.frame_camera(world, p, OUT_HW, PAD) for p in poses]
+    cams = [synth.frame_camera(world, p, out_hw, PAD) for p in poses]
     # pinned host copies of the per-frame inputs (camera pose) and of the per-frame result
     pose_pinned = [torch.stack([c[0], c[1], c[2]]).pin_memory() for c in cams]
     res = cams[0][5]
-    host_out = torch.empty(2, res[0], res[1], dtype=torch.float32).pin_memory()
+    rows = sharding.tile_rows_for_rank(res[0], rank, world_size) if strong else None
+    band_h = (rows[1] - rows[0]) if strong else res[0]
+    band_cap = sharding.tile_rows_for_rank(res[0], 0, world_size)[1] if strong else res[0]      # tallest band (rank 0's)
+    host_out = torch.empty(2, (band_cap * world_size) if strong else res[0], res[1], dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
 
-    def one_step(k, ev=None, kev=None, cev=None):
-        idx = (k * world_size + rank) % len(cams)
+    def sky_hook(avg_band, n_band):
+        # single-frame sharding: the frame-global sky mean (scenedreamer.py:592-598) needs every band: one 64-float
+        # all-gather of the band sums, combined in rank order
+        part = torch.cat([avg_band.reshape(64) * float(n_band), torch.tensor([float(n_band)], device=dev)])
+        allp = torch.empty(world_size, 65, device=dev)
+        dist.all_gather_into_tensor(allp, part.reshape(1, 65))
+        return (allp[:, :64].sum(0) / allp[:, 64].sum()).reshape(1, 64)
+
+    def one_step(k, ev=None, kev=None, cev=None, want_host=True):
+        idx = (k if strong else (k * world_size + rank)) % len(cams)
         cam = cams[idx]
         if ev is not None:
             ev[0].record()
-        pose = pose_pinned[idx]                                      # this step's inputs, pinned host memory:
-        out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev)   # by-value to the DDA, H2D for the rest
+        pose = pose_pinned[idx]                                      # this step's inputs, pinned host memory, passed by value
+        out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev, rows=rows,
+                       sky_sum_hook=sky_hook if (strong and world_size > 1) else None)
         maps = torch.stack([out['depth'][0], out['total_weight'][0]])
+        if strong and band_h < band_cap:                             # equal-size bands for the gather (the last band may be shorter)
+            maps = torch.nn.functional.pad(maps, (0, 0, 0, band_cap - band_h))
         if world_size > 1:
             if cev is not None:
                 cev[0].record()
-            sharding.gather_frames(maps.unsqueeze(0))                # the single collective of the path
+            allm = sharding.gather_frames(maps.unsqueeze(0))         # THE collective of the path: finished maps of every rank
             if cev is not None:
                 cev[1].record()
-        host_out.copy_(maps, non_blocking=True)                      # D2H of the step's result
+            if strong:                                               # bands -> one frame [2, rows, W]
+                maps = allm.permute(1, 0, 2, 3).reshape(2, -1, res[1])
+        if want_host:
+            host_out[:, :maps.shape[1]].copy_(maps, non_blocking=True)   # D2H of the step's result
         if ev is not None:
             ev[1].record()
         return out
@@ -249,100 +312,84 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mk = lambda: [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs, kevs, cevs = mk(), mk(), mk()
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()           # AFTER rank 0 has started its clock sampler: every rank enters the timed region together
         torch.cuda.synchronize()
-    t_begin = t_wall = time.perf_counter()
+    launches0 = int(L.sdb_launch_count())
+    t_begin = time.perf_counter()
     for k in range(args.steps):
         one_step(k, evs[k], kevs[k], cevs[k])
         torch.cuda.synchronize()                                     # the caller READS the step's result on the host
         flush.zero_()                                                # L2 flush between timed iterations
     torch.cuda.synchronize()
-    t_end = time.perf_counter()
-    t_wall = t_end - t_wall
+    t_wall = time.perf_counter() - t_begin
+    launches = int(L.sdb_launch_count()) - launches0
     if world_size > 1:
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    if os.environ.get('SDB_BENCH_DEBUG'):
-        print('[rank %d] e2e step ms: %s' % (rank, ' '.join('%.1f' % v for v in step_ms)), file=sys.stderr)
-        print('[rank %d] ev0->kernel start ms: %s' % (rank, ' '.join('%.1f' % evs[i][0].elapsed_time(kevs[i][0]) for i in range(len(evs)))), file=sys.stderr)
-        print('[rank %d] kernel ms: %s' % (rank, ' '.join('%.1f' % a.elapsed_time(b) for a, b in kevs)), file=sys.stderr)
-        if world_size > 1:
-            print('[rank %d] kernel end->coll start ms: %s' % (rank, ' '.join('%.1f' % kevs[i][1].elapsed_time(cevs[i][0]) for i in range(len(evs)))), file=sys.stderr)
-            print('[rank %d] coll ms: %s' % (rank, ' '.join('%.1f' % a.elapsed_time(b) for a, b in cevs)), file=sys.stderr)
-            print('[rank %d] coll end->step end ms: %s' % (rank, ' '.join('%.1f' % cevs[i][1].elapsed_time(evs[i][1]) for i in range(len(evs)))), file=sys.stderr)
     kern_ms = [a.elapsed_time(b) for a, b in kevs]
-    coll_ms = [a.elapsed_time(b) for a, b in cevs] if world_size > 1 else [0.0]
+    pre_ms = [evs[i][0].elapsed_time(kevs[i][0]) for i in range(args.steps)]
+    coll_ms = [a.elapsed_time(b) for a, b in cevs] if world_size > 1 else [0.0] * args.steps
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     tot_ms, tot_kern_ms = float(tot[0]), float(tot[1])
+    # per-rank table (mean ms per step): e2e step, DDA+sky before the fused kernel, fused kernel window, collective incl. wait
+    mine = torch.tensor([[float(np.mean(step_ms)), float(np.mean(pre_ms)), float(np.mean(kern_ms)), float(np.mean(coll_ms)),
+                          float(np.max(step_ms)), float(pinned_cpus or 0)]], dtype=torch.float64, device=dev)
+    table = mine
+    if world_size > 1:
+        table = torch.empty(world_size, mine.shape[1], dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(table, mine)
+    table = table.cpu().tolist()
 
-    # device-only number: inputs resident, no host copies (pose tensors already on the device)
-    doris = [c[0].to(dev) for c in cams]
-    dev_ms = []
-    for k in range(args.steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        idx = (k * world_size + rank) % len(cams)
-        flush.zero_()
-        a.record()
-        o_ = fr.frame(cams[idx], ori_dev=doris[idx])
-        if world_size > 1:                                           # the path's single collective stays inside the timed region
-            sharding.gather_frames(torch.stack([o_['depth'][0], o_['total_weight'][0]]).unsqueeze(0))
-        o_ = None                                                    # release the frame's buffers to the caching allocator
-        b.record()
-        torch.cuda.synchronize()
-        dev_ms.append(a.elapsed_time(b))
-    # the same device-only measurement with early termination OFF (every sample of every live tile marched)
-    exact_ms = []
-    if not args.no_early_stop:
-        fr.set_early_stop(0.0)
-        for k in range(-2, min(args.steps, 10)):
+    def device_only(early, steps, lead=0):
+        """inputs resident, nothing copied to the host; the collective stays inside"""
+        fr.set_early_stop(early)
+        ms = []
+        for k in range(-lead, steps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            idx = (max(k, 0) * world_size + rank) % len(cams)
             flush.zero_()
             a.record()
-            o_ = fr.frame(cams[idx], ori_dev=doris[idx])
-            if world_size > 1:
-                sharding.gather_frames(torch.stack([o_['depth'][0], o_['total_weight'][0]]).unsqueeze(0))
-            o_ = None
+            one_step(max(k, 0), want_host=False)
             b.record()
             torch.cuda.synchronize()
             if k >= 0:
-                exact_ms.append(a.elapsed_time(b))
-        fr.set_early_stop(None)
-    etot = torch.tensor([float(np.mean(exact_ms)) if exact_ms else 0.0], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(etot, op=dist.ReduceOp.MAX)
-    dtot = torch.tensor([sum(dev_ms)], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(dtot, op=dist.ReduceOp.MAX)
-    dev_tot_ms = float(dtot[0])
+                ms.append(a.elapsed_time(b))
+        t = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / max(1, len(ms))
+    dev_ms = device_only(0.0 if args.no_early_stop else None, args.steps)
+    exact_ms = dev_ms if args.no_early_stop else device_only(0.0, min(args.steps, 10), lead=2)
+    fr.set_early_stop(0.0 if args.no_early_stop else None)
     # clocks are sampled over BOTH timed loops (host-inclusive and device-only)
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
 
     if rank == 0:
         hbm, tf, which = measured_peaks()
-        frames = args.steps * world_size
-        value = frames * SAMPLES_PER_FRAME / (dev_tot_ms * 1e-3) / 1e6
-        e2e = frames * SAMPLES_PER_FRAME / (tot_ms * 1e-3) / 1e6
+        frames_per_step = 1 if strong else world_size
+        value = frames_per_step * samples_per_frame / (dev_ms * 1e-3) / 1e6
+        e2e = frames_per_step * samples_per_frame / (tot_ms / args.steps * 1e-3) / 1e6
         kern_s = tot_kern_ms * 1e-3 / args.steps
-        achieved = SAMPLES_PER_FRAME * BYTES_PER_SAMPLE / kern_s / 1e9
-        # executed tensor work: live 16x8 ray tiles x 24 steps x 128 rows, MMAs as issued (x3 split: 3 per product)
-        wss = [fr.frame(cams[(k * world_size) % len(cams)], ori_dev=doris[(k * world_size) % len(cams)])['workspace'][:8].view(torch.int32)
+        # executed tensor work: live 16x8 ray tiles x steps x 128 rows, MMAs as issued (x3 split: 3 per product)
+        # (rank 0 alone: no collective in here)
+        wss = [fr.frame(cams[(k if strong else k * world_size) % len(cams)], rows=rows)['workspace'][:8].view(torch.int32).cpu()
                for k in range(min(args.steps, 8))]
         live_tiles = float(np.mean([int(w[0]) for w in wss]))
-        steps_exec = float(np.mean([int(w[1]) for w in wss]))         # sample steps executed (tiles x steps, after early termination)
+        steps_exec = float(np.mean([int(w[1]) for w in wss]))         # tile-steps executed (after early termination)
         mma_eq = {'fp16': (9 + 5 * 17 + 17 * 0.25), 'bf16x3': (27 + 5 * 50 + 50 * 0.25), 'fp16x3': (27 + 5 * 50 + 50 * 0.25)}[args.precision]
         exec_tflops = steps_exec * mma_eq * (2.0 * 128 * 256 * 16) / kern_s / 1e12
+        band_frac = band_h / float(res[0])
+        alg_tflops = samples_per_frame * band_frac * FLOP_PER_SAMPLE / kern_s / 1e12
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.precision)
+        extras = {}
         cpu = None
         if world_size == 1 and not args.no_cpu:
             # the CPU leg runs in a clean subprocess (its own OpenMP settings, no CUDA context)
@@ -352,50 +399,110 @@ def run_gpu_arm(args):
                 cpu = json.loads(o.stdout.strip().splitlines()[-1])['cpu_baseline']
             except Exception as e:          # noqa: BLE001
                 cpu = {'error': repr(e)[:200]}
+        if world_size == 1 and not args.no_extras and args.workload == 'c2':
+            extras = extra_legs(args)
         line = {
             'metric': 'rendered Msamples/sec at 960x540x24spp', 'value': value, 'unit': 'Msamples/s',
-            'mpix_per_s': value / SPP, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': dev_tot_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'value_exact_march': (world_size * SAMPLES_PER_FRAME / (float(etot[0]) * 1e-3) / 1e6) if float(etot[0]) > 0 else None,
+            'mpix_per_s': value / spp, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': dev_ms, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
+            'value_exact_march': frames_per_step * samples_per_frame / (exact_ms * 1e-3) / 1e6,
             'value_exact_march_note': 'same measurement with early termination off (every sample of every live tile shaded)',
+            'samples_credited_per_frame': samples_per_frame,
+            'samples_shaded_per_frame': steps_exec * 128 / band_frac,
+            'samples_shaded_note': 'tile-steps executed x 128 rays (rank 0, mean over frames): sky-only 16x8 tiles are never shaded, '
+                                   'tiles stop once every live ray is opaque; padding rays and dead rays inside live tiles ARE shaded',
             'dtype': {'fp16': 'f16 (f32 accumulate)', 'bf16x3': 'bf16x3 split (f32-grade), f32 accumulate',
                       'fp16x3': 'f16x3 split (f32-grade), f32 accumulate'}[args.precision] + '; table/compositing f32',
             'data': 'synthetic',
-            'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0, pad 30 '
-                                   '(570x990 rays cast+shaded, 518400 px credited); one frame per GPU per step',
+            'config': {'workload': wl_name + ', pad %d (%dx%d rays cast+shaded, %d px credited); ' % (PAD, res[0], res[1], out_hw[0] * out_hw[1]) +
+                                   ('ONE frame per step split into row bands over the GPUs' if strong else 'one frame per GPU per step'),
                        'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
                        'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)',
                        'early_termination': ('off' if args.no_early_stop else
                                              'ray tiles stop once every live ray has transmittance < %g (skipped samples carry less than '
                                              'that compositing weight; credited like sky-only rays); --no-early-stop marches everything'
-                                             % render.EARLY_STOP_T)},
+                                             % render.EARLY_STOP_T),
+                       'host_affinity': 'each rank pinned to the CPUs of its GPU (NVML affinity), %s CPUs for rank 0' % pinned_cpus},
             'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
                     'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': tot_ms / args.steps,
-                    'note': 'per step: pose from pinned host memory -> DDA -> sky -> fused render -> depth+opacity maps to pinned host, host waits for them'},
-            'gpu_launches': 5 * args.steps,
-            'gpu_launches_note': 'per step: dda_perspective, mlp_kernel<sky>, sky_mean, prepass, mlp_kernel<render> (all ours)',
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
-                         'traffic': (traffic or {}).get('dram_bytes_per_launch'),
+                    'note': 'per step: pose from pinned host memory (by value in the launch arguments) -> DDA -> sky -> fused render -> '
+                            'depth+opacity maps to pinned host, host waits for them'},
+            'gpu_launches': launches,
+            'gpu_launches_note': 'counted by the library (sdb_launch_count) over the timed region on rank 0: per step dda_perspective, '
+                                 'mlp_kernel<sky>, sky_mean, set_cam, prepass, mlp_kernel<render> (all ours)',
+            'roofline': {'bound': 'tensor', 'achieved': alg_tflops, 'peak': tf, 'unit': 'TFLOP/s', 'frac': alg_tflops / tf,
+                         'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_unit': 'B of DRAM per launch (ncu dram__bytes)',
                          'traffic_source': (traffic or {}).get('source'),
-                         'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)',
                          'kernel': 'rf::mlp_kernel<render> (+prepass)', 'kernel_ms': tot_kern_ms / args.steps,
-                         'algorithmic_bytes_per_launch': SAMPLES_PER_FRAME * BYTES_PER_SAMPLE,
-                         'note': 'HBM is the bound SURVEY 8(d) prescribes; measured DRAM traffic is ~600x below the algorithmic bytes '
-                                 '(pre-blended table + L2-resident gathers), so frac > 1 and the real limiter is the tensor pipe: see roofline_tensor',
-                         'tensor_tflops': SAMPLES_PER_FRAME * 754176 / kern_s / 1e12, 'tensor_peak_tflops': tf},
-            'roofline_tensor': {'bound': 'tensor', 'achieved': exec_tflops, 'peak': tf, 'unit': 'TFLOP/s', 'frac': exec_tflops / tf,
-                                'what': 'EXECUTED 16-bit MMA flops of rf::mlp_kernel<render> (live tiles x 24 steps x MMAs issued; the parity '
-                                        'modes issue 3 MMAs per product) over the measured sustained cuBLAS bf16 rate',
-                                'algorithmic_tflops': SAMPLES_PER_FRAME * 754176 / kern_s / 1e12,
-                                'live_tiles_per_frame': live_tiles, 'tile_steps_executed_per_frame': steps_exec,
-                                'tile_steps_without_early_termination': live_tiles * SPP, 'peak_source': which + ' (bf16_tflops_sustained)'},
+                         'peak_source': which + ' (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a long step)',
+                         'what': 'ALGORITHMIC flops: credited samples x 754,176 FLOP (LightningMLP at 1 MMA per product) / kernel time',
+                         'executed_tflops': exec_tflops, 'executed_frac': exec_tflops / tf,
+                         'executed_what': '16-bit MMA flops as issued: tile-steps executed x MMAs per step (the parity modes issue 3 MMAs '
+                                          'per product) -- the tensor-pipe occupancy; one third of it is algorithmic work',
+                         'live_tiles_per_frame': live_tiles, 'tile_steps_executed_per_frame': steps_exec,
+                         'tile_steps_without_early_termination': live_tiles * spp,
+                         'hbm': {'algorithmic_bytes_per_launch': samples_per_frame * BYTES_PER_SAMPLE,
+                                 'algorithmic_GBps': samples_per_frame * band_frac * BYTES_PER_SAMPLE / kern_s / 1e9, 'peak_GBps': hbm,
+                                 'note': 'SURVEY 8(d) prescribes 16,398 B/sample; the kernel does NOT move them (pre-blended table: 4x fewer '
+                                         'corners, L2-resident gathers): measured DRAM traffic is `traffic`, ~600x lower, so HBM is not the bound'}},
             'cpu_baseline': cpu, 'clocks': clocks, 'wall_s': t_wall,
-            'collective': {'op': 'all_gather_into_tensor(depth+opacity maps)', 'bytes_per_rank': int(host_out.numel() * 4),
+            'per_rank_ms': {'columns': ['e2e_step', 'dda_sky', 'fused_kernel_window', 'collective_incl_wait', 'e2e_step_max', 'cpus_in_affinity'],
+                            'rows': table},
+            'collective': {'op': 'all_gather_into_tensor(depth+opacity maps)', 'bytes_per_rank': int(2 * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
                            'ms_per_step_incl_wait_for_slowest_rank': float(np.mean(coll_ms))} if world_size > 1 else None,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def extra_legs(args):
+    """Reported next to the headline at N=1 (each in a subprocess, bounded): C4 throughput, the C5 train step, and the
+    reference renderer itself on this B200 (its own CUDA extensions + PyTorch, through the real Generator)."""
+    ex = {}
+
+    def run(cmd, timeout):
+        o = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        if o.returncode != 0:
+            raise RuntimeError((o.stderr or o.stdout)[-300:])
+        return o
+
+    try:
+        o = run([sys.executable, os.path.abspath(__file__), '--workload', 'c4', '--steps', '3', '--warmup', '3', '--no-cpu', '--no-extras'], 900)
+        c4 = json.loads(o.stdout.strip().splitlines()[-1])
+        ex['c4'] = {k: c4[k] for k in ('value', 'unit', 'ms_per_step', 'value_exact_march', 'samples_credited_per_frame', 'samples_shaded_per_frame')}
+        ex['c4']['config'] = c4['config']['workload']
+        ex['c4']['e2e'] = c4['e2e']['value']
+        ex['c4']['roofline_frac'] = c4['roofline']['frac']
+    except Exception as e:          # noqa: BLE001
+        ex['c4'] = {'error': repr(e)[:300]}
+    try:
+        o = run([sys.executable, os.path.join(ROOT, 'bench_train.py'), '--steps', '8', '--warmup', '3', '--no-composition'], 900)
+        ex['c5_train_step'] = json.loads(o.stdout.strip().splitlines()[-1])
+    except Exception as e:          # noqa: BLE001
+        ex['c5_train_step'] = {'error': repr(e)[:300]}
+    try:
+        import numpy as _np
+        res = {}
+        for backend in ('ref', 'dropin'):
+            out = '/tmp/sdb_bench_%s.npz' % backend
+            run([sys.executable, '-m', 'oracle.refgen', '--backend', backend, '--frames', '4', '--warm', '1', '--out', out,
+                 '--workdir', '/tmp/sdb_bench_refgen'], 900)
+            d = _np.load(out)
+            res[backend] = (float(_np.mean(d['perpix_ms'])), float(_np.mean(d['cnn_ms'])))
+        spf = SAMPLES_PER_FRAME
+        ex['reference_cuda_b200'] = {
+            'what': "the reference's own Generator.inference_givenstyle (unmodified Python staged in oracle/_ref/py) on this GPU: "
+                    "'reference' = its own CUDA extensions compiled for sm_100a + cuBLAS/ATen, unfused 40-tile loop; 'dropin_zero_edit' = the "
+                    'same Python with dropin/ on the path (class-level fused hook, one launch per frame). GPU-timeline ms per C2 frame, '
+                    'per-pixel path (raycast + sky pre-pass + _forward_perpix) and RenderCNN (_forward_global) separately',
+            'reference': {'perpix_ms': res['ref'][0], 'cnn_ms': res['ref'][1], 'msamples_per_s': spf / (res['ref'][0] * 1e-3) / 1e6},
+            'dropin_zero_edit': {'perpix_ms': res['dropin'][0], 'cnn_ms': res['dropin'][1], 'msamples_per_s': spf / (res['dropin'][0] * 1e-3) / 1e6},
+            'perpix_speedup': res['ref'][0] / res['dropin'][0]}
+    except Exception as e:          # noqa: BLE001
+        ex['reference_cuda_b200'] = {'error': repr(e)[:300]}
+    return ex
 
 
 def main():
@@ -405,7 +512,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='fp16x3', choices=['fp16', 'bf16x3', 'fp16x3'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS), help='BASELINE.json config (default: the headline, C2)')
+    ap.add_argument('--mode', default='weak', choices=['weak', 'strong'],
+                    help='weak: one frame per GPU per step (frames sharded); strong: ONE frame per step split into row bands')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extras', action='store_true', help='skip the C4 / C5 / reference-CUDA legs reported next to the headline at N=1')
     ap.add_argument('--no-early-stop', action='store_true',
                     help='march every sample of every live tile (early termination off; the reference arithmetic sample for sample)')
     args = ap.parse_args()

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'dropin'))
+sys.path.insert(0, os.path.join(ROOT, 'dropin'))      # `_gridencoder` for the reference's own gridencoder package (composition leg)
 
 VIEW, PAD, SPP, SCENE = 256, 6, 24, 1024
 
@@ -186,7 +186,14 @@ def main():
             'samples_per_view': samples, 'live_ray_fraction': live, 'steps': a.steps, 'data': 'synthetic',
             'l2': 'flushed between steps', 'record_bytes': int(render._lib.lib().sdb_render_train_record_bytes(1, H, W, SPP)),
             'backward_workspace_bytes': int(render._lib.lib().sdb_render_backward_workspace_bytes(1, H, W, SPP, 16, 19))}
+    ref_py = None
     if not a.no_composition:
+        from oracle import refgen                     # where the reference's own Python is staged (baseline leg only)
+        ref_py = refgen.reference_python_root()
+        if ref_py is None:
+            line['unfused_composition'] = {'skipped': 'reference Python not staged (oracle/build_ref.py)'}
+    if ref_py is not None:
+        sys.path.insert(1, ref_py)
         from gridencoder import GridEncoder
         ge = GridEncoder(input_dim=5, num_levels=16, level_dim=8, base_resolution=16, log2_hashmap_size=19,
                          desired_resolution=2048).to(dev)

@@ -122,7 +122,7 @@ typedef struct sdb_render_params {
     const int32_t *d_voxel_id;   /* [R, M]                                                    */
     const float *d_depth2;       /* [n_img][2][H*W][M] (reference layout [N,2,H,W,M,1])       */
     const float *d_raydirs;      /* [R, 3]                                                    */
-    const float *d_cam_ori;      /* [n_img, 3] device                                         */
+    const float *d_cam_ori;      /* [n_img, 3] device, or NULL: take cam_ori_value (n_img == 1) */
     float voxel_dims[3];         /* normalisation of world coords (scenedreamer.py:298-299)   */
     const float *d_global_enc;   /* [n_img, 2] device: scene code = encoder dims 3,4 (:300-302)*/
     float sample_depth;          /* mc_utils.py:107                                           */
@@ -166,9 +166,15 @@ typedef struct sdb_render_params {
        shaded have compositing weight < threshold (reported as 0 in d_weights_out).  0 = off =
        the reference's arithmetic sample for sample.  The training forward ignores it.          */
     float early_stop_transmittance;
+    /* camera origin BY VALUE, used when d_cam_ori == NULL (one image): the reference hands the pose
+       of a frame over from the host (scenedreamer.py:569-586); by value it rides in the launch
+       instead of a host->device copy the stream would have to wait for                          */
+    float cam_ori_value[3];
 } sdb_render_params;
 
 int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W);
+/* d_workspace after the call (int32): [0] live (not sky-only) 16x8 ray tiles, [1] tile-steps executed
+   (live tiles x S minus what early termination skipped) -- diagnostics / bench bookkeeping.        */
 int sdb_render_rays_forward(const sdb_render_params *p, void *stream);
 
 /* Per-scene collapse of the two constant encoder dimensions (inference only):
@@ -273,6 +279,10 @@ int64_t sdb_sky_backward_workspace_bytes(int32_t n_img, int32_t H, int32_t W);
 int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void *d_record, const float *d_grad_sky,
                      const void *d_bwd_pack, float *d_grad_w1ext, float *d_grad_wh, float *d_grad_wout,
                      void *d_workspace, void *stream);
+
+/* Kernels this library has launched in this process so far (every launch is counted; memsets and
+ * library GEMMs are not).  bench.py reads it around its timed region for `gpu_launches`.          */
+int64_t sdb_launch_count(void);
 
 /* Diagnostics only: byte offsets inside the training record / backward workspace (20 int64, see render_train.cu). */
 int sdb_debug_train_layout(int32_t n_img, int32_t H, int32_t W, int32_t S, int32_t L, int32_t log2_T, int64_t *out);

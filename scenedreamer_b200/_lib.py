@@ -54,6 +54,7 @@ SIGNATURES = {
     'sdb_sky_backward_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
     'sdb_sky_backward': (c_int, [c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    'sdb_launch_count': (c_i64, []),
     'sdb_debug_train_layout': (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_i64)]),
     'sdb_debug_set_progress_buffer': (None, [c_void_p]),
     'sdb_tc_selftest_mn': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
@@ -66,8 +67,16 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            # one process per GPU: only one of them may run nvcc into the shared _obj/ directory; the others wait on the lock
+            # and find the finished library (build() re-checks its stamp under the lock)
+            import fcntl
             from . import build as _build
-            _build.build()
+            with open(LIB_PATH + '.lock', 'w') as lk:
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                try:
+                    _build.build()
+                finally:
+                    fcntl.flock(lk, fcntl.LOCK_UN)
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('scenedreamer_b200: %s is missing and could not be built; '
                                'this package has no CPU or PyTorch fallback' % LIB_PATH)

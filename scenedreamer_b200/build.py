@@ -63,11 +63,13 @@ def build(force=False, verbose=False):
         objs = list(ex.map(cc, srcs))
     # cuBLAS serves the plain weight-gradient GEMMs of render_train.cu; the rpath covers processes that have not
     # already loaded a libcublas.so.12 (torch brings its own)
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-lcublas',
+    tmp = LIB + '.tmp.%d' % os.getpid()                       # link aside, then rename: nobody dlopens a half-written file
+    cmd = [nvcc, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-lcublas',
                                                 '-Xlinker', '-rpath=/usr/local/cuda/lib64']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     with open(stamp, 'w') as f:
         f.write(dig)
     return LIB

@@ -1,6 +1,12 @@
 // Library info + error strings (host only).
 #include "common.cuh"
 
+#include <atomic>
+
+static std::atomic<long long> g_launches{0};
+extern "C" void sdb_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t sdb_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
 #define SDB_STR2(x) #x
 #define SDB_STR(x) SDB_STR2(x)
 

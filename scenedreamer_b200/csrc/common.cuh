@@ -5,10 +5,15 @@
 
 #include "../../include/sdb200.h"
 
+// every kernel launch of the library is followed by exactly one SDB_CHECK_LAUNCH: it also counts the launch
+// (sdb_launch_count(), read by bench.py for its `gpu_launches` claim)
+extern "C" void sdb_count_launch_(void);
+
 #define SDB_CHECK_LAUNCH()                                   \
     do {                                                     \
         cudaError_t e__ = cudaGetLastError();                \
         if (e__ != cudaSuccess) return (int)e__;             \
+        sdb_count_launch_();                                 \
     } while (0)
 
 #define SDB_CUDA(call)                                       \

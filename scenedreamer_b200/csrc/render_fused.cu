@@ -298,7 +298,7 @@ mlp_kernel(const Params p)
             float outc[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) outc[c] = 0.0f;
-            float Wsum = 0.0f, Dsum = 0.0f, Eexcl = 0.0f;
+            float Wsum = 0.0f, Dsum = 0.0f, Dcomp = 0.0f, Eexcl = 0.0f;
             bool is_gnd = false;
 
             int s_done = S;           // steps actually executed for this tile
@@ -468,7 +468,15 @@ mlp_kernel(const Params p)
                     Eexcl = __fadd_rn(Eexcl, e);
                     w = live ? w : 0.0f;                                                              // scenedreamer.py:376
                     Wsum += w;
-                    Dsum = fmaf(w, sm.depth, Dsum);
+                    {   // depth = sum w*t with t of several hundred voxels: 1e-3 absolute is ~16 ulp of the running sum, so the
+                        // 24..64-term sum is carried compensated (exact product error + two-sum); costs 8 flops per sample
+                        const float pr = __fmul_rn(w, sm.depth);
+                        const float pe = __fmaf_rn(w, sm.depth, -pr);
+                        const float sn = __fadd_rn(Dsum, pr);
+                        const float bv = __fsub_rn(sn, Dsum);
+                        Dcomp = __fadd_rn(Dcomp, __fadd_rn(__fadd_rn(__fsub_rn(Dsum, __fsub_rn(sn, bv)), __fsub_rn(pr, bv)), pe));
+                        Dsum = sn;
+                    }
                     if constexpr (TRAIN) {   // what the compositing backward needs: sigma, scaled interval, colour head output
                         if (half == 0) { p.tr.sig[slot] = sigma; p.tr.nds[slot] = __fmul_rn(sm.nd, p.dists_scale); }
                         float *cd = p.tr.c + slot * kOutC + half * 32;
@@ -553,7 +561,7 @@ mlp_kernel(const Params p)
                         dst[q] = o;
                     }
                     if (half == 0) {
-                        if (p.depth_out) p.depth_out[ray] = Dsum;
+                        if (p.depth_out) p.depth_out[ray] = __fadd_rn(Dsum, Dcomp);
                         if (p.total_weight) p.total_weight[ray] = Wsum;
                     }
                 }
@@ -1258,9 +1266,15 @@ static int64_t sdb_num_tiles(int32_t n_img, int32_t H, int32_t W) {
     return (int64_t)n_img * sdb_div_up(H, rf::kTileH) * sdb_div_up(W, rf::kTileW);
 }
 
+// workspace (int32 words): [0] live tiles, [1] tile-steps executed, [2] work counter, [3] -, [4 .. 4+tiles) live-tile list,
+// then 4 floats: the by-value camera origin (when sdb_render_params.d_cam_ori is NULL)
 extern "C" int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
     if (n_img <= 0 || H <= 0 || W <= 0) return 0;
-    return (sdb_num_tiles(n_img, H, W) + 4) * 4;
+    return (sdb_num_tiles(n_img, H, W) + 8) * 4;
+}
+
+namespace rf {
+__global__ void set_cam_kernel(float *dst, float a, float b, float c) { dst[0] = a; dst[1] = b; dst[2] = c; }
 }
 
 extern "C" int64_t sdb_sky_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
@@ -1330,11 +1344,12 @@ namespace rf {
 int params_from_abi(const sdb_render_params *sp, Params &p)
 {
     if (!sp) return SDB_EINVAL;
-    if (!sp->d_voxel_id || !sp->d_depth2 || !sp->d_raydirs || !sp->d_cam_ori || !sp->d_global_enc || !sp->d_fractions ||
+    if (!sp->d_voxel_id || !sp->d_depth2 || !sp->d_raydirs || !sp->d_global_enc || !sp->d_fractions ||
         !sp->d_label_lut || !sp->d_mlp_pack || !sp->d_sky || !sp->d_sky_avg || !sp->d_net_out || !sp->d_workspace)
         return SDB_EINVAL;
     if ((sp->d_table == nullptr) == (sp->d_table3 == nullptr)) return SDB_EINVAL;
     if (sp->n_img <= 0 || sp->H <= 0 || sp->W <= 0) return SDB_EINVAL;
+    if (!sp->d_cam_ori && sp->n_img != 1) return SDB_EINVAL;
     if (sp->M < 1 || sp->M > kMaxM || sp->S < 1 || sp->S > kMaxS || sp->L != kLevels || sp->log2_T < 4 || sp->log2_T > 24 ||
         sp->precision < 0 || sp->precision > 2 || sp->n_lut < 1)
         return SDB_EUNSUPPORTED;
@@ -1357,6 +1372,16 @@ int params_from_abi(const sdb_render_params *sp, Params &p)
     p.debug = g_debug_buffer;
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
     p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
+    if (!sp->d_cam_ori) p.cam_ori = reinterpret_cast<const float *>((const int32_t *)sp->d_workspace + 4 + p.n_tiles);
+    return SDB_OK;
+}
+
+// by-value camera origin -> its slot behind the tile list (first thing on the stream of a render call)
+int stage_cam_ori(const sdb_render_params *sp, const Params &p, cudaStream_t st)
+{
+    if (sp->d_cam_ori) return SDB_OK;
+    set_cam_kernel<<<1, 1, 0, st>>>(const_cast<float *>(p.cam_ori), sp->cam_ori_value[0], sp->cam_ori_value[1], sp->cam_ori_value[2]);
+    SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
 }  // namespace rf
@@ -1372,6 +1397,10 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     }
     int32_t *ws = (int32_t *)sp->d_workspace;
     p.n_live = ws; p.tile_list = ws + 4; p.steps_done = ws + 1; p.work_counter = ws + 2;
+    {
+        const int rc = stage_cam_ori(sp, p, st);
+        if (rc != SDB_OK) return rc;
+    }
     {
         const int rc = launch_prepass(p, ws, st);
         if (rc != SDB_OK) return rc;

@@ -406,7 +406,7 @@ extern "C" int sdb_debug_train_layout(int32_t n_img, int32_t H, int32_t W, int32
 extern "C" int sdb_render_rays_train_forward(const sdb_render_params *sp, void *d_record, void *stream)
 {
     using namespace rf;
-    if (!d_record) return SDB_EINVAL;
+    if (!d_record || !sp || !sp->d_cam_ori) return SDB_EINVAL;      // training takes the camera origin from device memory
     cudaStream_t st = (cudaStream_t)stream;
     Params p;
     {
@@ -429,7 +429,7 @@ extern "C" int sdb_render_rays_train_forward(const sdb_render_params *sp, void *
 extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void *d_record, const sdb_render_grads *g, void *stream)
 {
     using namespace rf;
-    if (!d_record || !g) return SDB_EINVAL;
+    if (!d_record || !g || !sp || !sp->d_cam_ori) return SDB_EINVAL;
     if (!g->d_grad_net_out || !g->d_bwd_pack || !g->d_table || !g->d_grad_table || !g->d_grad_global_enc || !g->d_grad_w1ext ||
         !g->d_grad_wh || !g->d_grad_wsig || !g->d_grad_wout || !g->d_grad_sky || !g->d_grad_sky_avg || !g->d_workspace)
         return SDB_EINVAL;

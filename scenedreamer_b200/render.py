@@ -39,6 +39,7 @@ class _RenderParams(ctypes.Structure):
         ('d_weights_out', ctypes.c_void_p), ('d_rand_depth_out', ctypes.c_void_p),
         ('d_workspace', ctypes.c_void_p),
         ('early_stop_transmittance', ctypes.c_float),
+        ('cam_ori_value', ctypes.c_float * 3),
     ]
 
 
@@ -107,14 +108,26 @@ def preblend_table(embeddings, global_enc, log2_T=19, per_level_scale=None, base
     return out
 
 
+_fraction_cache = {}
+
+
 def deterministic_fractions(S, device):
-    """torch.linspace(0, 1, S+3)[1:-1] built on the CPU like the reference (mc_utils.py:118-120)."""
-    return torch.linspace(0, 1, S + 3)[1:-1].contiguous().to(device)
+    """torch.linspace(0, 1, S+3)[1:-1] built on the CPU like the reference (mc_utils.py:118-120); one upload per
+    (S, device), not one per frame."""
+    key = ('det', int(S), str(device))
+    t = _fraction_cache.get(key)
+    if t is None:
+        t = _fraction_cache[key] = torch.linspace(0, 1, S + 3)[1:-1].contiguous().to(device)
+    return t
 
 
 def stratified_offsets(S, device):
     """torch.linspace(0, 1, S+2)[:-1] (mc_utils.py:125)."""
-    return torch.linspace(0, 1, S + 2, device=device)[:-1].contiguous()
+    key = ('str', int(S), str(device))
+    t = _fraction_cache.get(key)
+    if t is None:
+        t = _fraction_cache[key] = torch.linspace(0, 1, S + 2, device=device)[:-1].contiguous()
+    return t
 
 
 def pack_sky_mlp(P, z, precision=PRECISION_FP16X3, prefix='sky_net'):
@@ -195,7 +208,11 @@ def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_di
     rdp = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev) if want_samples else None
     Lb = _lib.lib()
     ws = torch.empty(int(Lb.sdb_render_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
-    cam_ori = cam_ori.to(dev, torch.float32).reshape(N, 3).contiguous()
+    cam_by_value = None
+    if not cam_ori.is_cuda and N == 1:
+        cam_by_value = [float(v) for v in cam_ori.reshape(3)]       # host pose -> kernel arguments, no H2D copy to wait for
+    else:
+        cam_ori = cam_ori.to(dev, torch.float32).reshape(N, 3).contiguous()
     genc = global_enc.to(dev, torch.float32).reshape(N, 2).contiguous()
     if uniforms is None:
         frac = deterministic_fractions(S, dev)
@@ -206,7 +223,10 @@ def render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, voxel_di
     prm = _RenderParams()
     prm.n_img, prm.H, prm.W, prm.M, prm.S = N, H, W, M, S
     prm.d_voxel_id, prm.d_depth2, prm.d_raydirs = _ptr(voxel_id), _ptr(depth2), _ptr(raydirs)
-    prm.d_cam_ori = _ptr(cam_ori)
+    if cam_by_value is None:
+        prm.d_cam_ori = _ptr(cam_ori)
+    else:
+        prm.d_cam_ori, prm.cam_ori_value = None, (ctypes.c_float * 3)(*cam_by_value)
     prm.voxel_dims = (ctypes.c_float * 3)(*[float(v) for v in voxel_dims])
     prm.d_global_enc = _ptr(genc)
     prm.sample_depth, prm.dists_scale = float(sample_depth), float(dists_scale)
@@ -249,28 +269,39 @@ class FusedPerPixelRenderer:
         self.P, self.voxel_dims, self.lut = P, [float(v) for v in voxel_dims], label_lut
         self.pls, self.precision, self.preblend = per_level_scale, precision, preblend
         self.base_res, self.log2_T, self.L = base_res, log2_T, L
-        self._pack_key = self._pack = self._t3_key = self._t3 = self._sky_key = self._sky_pack = None
+        self.invalidate()
+        self.lut_dev = None
         self.sky_impl = 'native'     # 'native' = sdb_sky_forward (tcgen05), 'torch' = cuBLAS cross-check
         self.early_stop = None       # None = module default EARLY_STOP_T, 0 = off
 
+    # Cache keys hold a REFERENCE to the keyed tensor (so its address cannot be recycled for another tensor while the
+    # entry lives) and compare identity + torch's version counter.  A fresh style code per call -- what the reference's
+    # style_net produces -- is a new object and repacks.  Edits that bypass the version counter (`.data`) need invalidate().
+    @staticmethod
+    def _same(entry, t, extra):
+        return entry is not None and entry[0] is t and entry[1] == t._version and entry[2] == extra
+
+    def invalidate(self):
+        self._pack_key = self._pack = self._t3_key = self._t3 = self._sky_key = self._sky_pack = None
+
     def pack_for(self, z):
-        key = (z.data_ptr(), z._version, self.precision)
-        if self._pack_key != key:
-            self._pack, self._pack_key = pack_mlp(self.P, z, self.precision), key
+        if not self._same(self._pack_key, z, self.precision):
+            self._pack, self._pack_key = pack_mlp(self.P, z, self.precision), (z, z._version, self.precision)
         return self._pack
 
     def sky_pack_for(self, z):
-        key = (z.data_ptr(), z._version, self.precision)
-        if self._sky_key != key:
-            self._sky_pack, self._sky_key = pack_sky_mlp(self.P, z, self.precision), key
+        if not self._same(self._sky_key, z, self.precision):
+            self._sky_pack, self._sky_key = pack_sky_mlp(self.P, z, self.precision), (z, z._version, self.precision)
         return self._sky_pack
 
     def table3_for(self, global_enc):
+        """Pre-blended table of this scene code.  Keyed on the scene-code tensor OBJECT (+ version) and on the table's
+        storage + version: no device->host read of the code on the frame path."""
         emb = self.P['hash_encoder.embeddings']
-        key = (emb.data_ptr(), emb._version, tuple(global_enc.reshape(-1).tolist()))
-        if self._t3_key != key:
+        extra = (emb.data_ptr(), emb._version)
+        if not self._same(self._t3_key, global_enc, extra):
             self._t3 = preblend_table(emb, global_enc, self.log2_T, self.pls, self.base_res, self.L)
-            self._t3_key = key
+            self._t3_key = (global_enc, global_enc._version, extra)
         return self._t3
 
     def forward(self, voxel_id, depth2, raydirs, cam_ori, z, global_enc, num_samples=24, sample_depth=3.0,
@@ -285,12 +316,14 @@ class FusedPerPixelRenderer:
         if sky_avg is None:
             sky_avg = sky.mean(dim=(1, 2))                       # scenedreamer.py:395 / :597
         pack = self.pack_for(z)
+        if self.lut_dev is None or self.lut_dev.device != voxel_id.device:
+            self.lut_dev = self.lut.to(voxel_id.device, torch.int32).contiguous()      # once, not one H2D per frame
         kw = {}
         if self.preblend and N == 1:
             kw['table3'] = self.table3_for(global_enc)
         else:
             kw['table'] = self.P['hash_encoder.embeddings']
-        out = render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, self.voxel_dims, self.lut, pack, sky,
+        out = render_rays_forward(voxel_id, depth2, raydirs, cam_ori, global_enc, self.voxel_dims, self.lut_dev, pack, sky,
                                   sky_avg, num_samples=num_samples, sample_depth=sample_depth, dists_scale=dists_scale,
                                   uniforms=uniforms, precision=self.precision, per_level_scale=self.pls,
                                   base_res=self.base_res, log2_T=self.log2_T, L=self.L, want_samples=want_samples,
@@ -305,22 +338,29 @@ class FusedPerPixelRenderer:
 # The training record and the backward workspace are several GB each (3.9 + 4.0 KB per sample).  Asking torch's caching
 # allocator for them every step makes it split and re-grow its multi-GB blocks (a 7.4 GB request right after a 6.9 GB
 # one was carved out of the cached 7.4 GB block ends in cudaMalloc) -- measured as 10-40 ms of jitter per step.  They are
-# therefore recycled through this exact-size pool: taken in forward / backward, handed back when backward is done.
+# therefore recycled through this small pool: ONE parked buffer per (device, role); a buffer of another size replaces the
+# parked one (a crop-size change does not accumulate multi-GB entries), further buffers of a multi-view batch go back to
+# torch's allocator.  Reuse is stream-ordered: forward and backward of a step run on the same (current) stream.
 _scratch_pool = {}
 
 
-def _take_scratch(nbytes, dev):
-    lst = _scratch_pool.get((int(nbytes), str(dev)))
-    if lst:
-        return lst.pop()
+def _take_scratch(nbytes, dev, role):
+    key = (str(dev), role)
+    t = _scratch_pool.pop(key, None)
+    if t is not None and t.numel() == int(nbytes):
+        return t
+    del t                                                    # wrong size: release it before asking for the new one
     return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
 
 
-def _give_scratch(t):
+def _give_scratch(t, role):
     if t is not None:
-        lst = _scratch_pool.setdefault((int(t.numel()), str(t.device)), [])
-        if len(lst) < 2:
-            lst.append(t)
+        _scratch_pool[(str(t.device), role)] = t             # replaces (and thereby frees) a parked buffer of another size
+
+
+def clear_scratch():
+    """Hand the parked training record / backward workspace (several GB) back to torch's allocator."""
+    _scratch_pool.clear()
 
 
 class _RenderGrads(ctypes.Structure):
@@ -404,7 +444,7 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             wts = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev)
             rdp = torch.empty(N, H, W, S, 1, dtype=torch.float32, device=dev)
             ws = torch.empty(int(L.sdb_render_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
-            record = _take_scratch(L.sdb_render_train_record_bytes(N, H, W, S), dev)
+            record = _take_scratch(L.sdb_render_train_record_bytes(N, H, W, S), dev, 'record')
             prm, keep = _RenderParams(), []
             _fill_render_params(prm, keep, voxel_id, depth2, raydirs, cam_ori, genc_, cfg['voxel_dims'], lut, pack, sky_, sky_avg_,
                                 table3, S, cfg['sample_depth'], cfg['dists_scale'], cfg.get('uniforms'), prec,
@@ -423,6 +463,9 @@ class _FusedRenderTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_net_out, *_unused):
         L = _lib.lib()
+        if ctx.record is None:
+            raise RuntimeError('fused render: the training record of this pass was released by its first backward '
+                               '(retain_graph / double backward are not supported on the fused path)')
         cfg, prm = ctx.cfg, ctx.prm
         embeddings_, w1_, wh_, wsig_, wout_ = ctx.saved
         dev = embeddings_.device
@@ -440,7 +483,7 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             g_wout = torch.empty(64, 272, dtype=torch.float32, device=dev)
             g_sky = torch.zeros(N, H, W, 64, dtype=torch.float32, device=dev)
             g_sky_avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
-            wsb = _take_scratch(L.sdb_render_backward_workspace_bytes(N, H, W, S, int(cfg['L']), int(cfg['log2_T'])), dev)
+            wsb = _take_scratch(L.sdb_render_backward_workspace_bytes(N, H, W, S, int(cfg['L']), int(cfg['log2_T'])), dev, 'bwd')
             gr = _RenderGrads()
             gr.d_grad_net_out, gr.d_bwd_pack, gr.bwd_pack_stride = _ptr(g), _ptr(bpack), 0
             gr.d_table = _ptr(embeddings_)
@@ -450,8 +493,8 @@ class _FusedRenderTrainFn(torch.autograd.Function):
             _lib.check(L.sdb_render_rays_backward(ctypes.byref(prm), _ptr(ctx.record), ctypes.byref(gr), _stream(dev)),
                        'sdb_render_rays_backward')
         # stream-ordered reuse: the next forward / backward run on the same stream after these kernels
-        _give_scratch(wsb)
-        _give_scratch(ctx.record)
+        _give_scratch(wsb, 'bwd')
+        _give_scratch(ctx.record, 'record')
         ctx.record = None
         s_fcma, s_wsig, s_bsig, s_sky, s_skyavg, s_genc = ctx.shapes
         n_lab = s_fcma[1]
@@ -486,7 +529,7 @@ class _SkyTrainFn(torch.autograd.Function):
             sky = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
             avg = torch.empty(N, 64, dtype=torch.float32, device=dev)
             ws = torch.empty(int(L.sdb_sky_workspace_bytes(N, H, W)), dtype=torch.uint8, device=dev)
-            record = _take_scratch(L.sdb_sky_train_record_bytes(N, H, W), dev)
+            record = _take_scratch(L.sdb_sky_train_record_bytes(N, H, W), dev, 'sky_record')
             _lib.check(L.sdb_sky_train_forward(_ptr(rd), N, H, W, _ptr(pack), _ptr(sky), _ptr(avg), _ptr(ws), _ptr(record),
                                                _stream(dev)), 'sdb_sky_train_forward')
         ctx.dims, ctx.record, ctx.saved = (N, H, W), record, (wh_, wout_)
@@ -496,6 +539,8 @@ class _SkyTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_sky):
         L = _lib.lib()
+        if ctx.record is None:
+            raise RuntimeError('fused sky branch: the training record was released by the first backward')
         N, H, W = ctx.dims
         wh_, wout_ = ctx.saved
         dev = wh_.device
@@ -506,11 +551,11 @@ class _SkyTrainFn(torch.autograd.Function):
             g_w1ext = torch.empty(256, 48, dtype=torch.float32, device=dev)
             g_wh = torch.empty(4, 256, 272, dtype=torch.float32, device=dev)
             g_wout = torch.empty(64, 272, dtype=torch.float32, device=dev)
-            wsb = _take_scratch(L.sdb_sky_backward_workspace_bytes(N, H, W), dev)
+            wsb = _take_scratch(L.sdb_sky_backward_workspace_bytes(N, H, W), dev, 'sky_bwd')
             _lib.check(L.sdb_sky_backward(N, H, W, _ptr(ctx.record), _ptr(g), _ptr(bpack), _ptr(g_w1ext), _ptr(g_wh), _ptr(g_wout),
                                           _ptr(wsb), _stream(dev)), 'sdb_sky_backward')
-        _give_scratch(wsb)
-        _give_scratch(ctx.record)
+        _give_scratch(wsb, 'sky_bwd')
+        _give_scratch(ctx.record, 'sky_record')
         ctx.record = None
         return (None, g_w1ext[:, :33].contiguous(), g_w1ext[:, 47].reshape(ctx.shapes[0]), g_wh[:, :, :256].contiguous(),
                 g_wh[:, :, 256].contiguous(), g_wout[:, :256].contiguous(), g_wout[:, 256].contiguous())

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     of, os_, ou = oracle.camera_frame([-45.25, 204.8, -409.6], [1, 0, 0])
     assert list(f) == of.tolist() and list(s) == os_.tolist() and list(u) == ou.tolist()
     assert L.sdb_mlp_pack_bytes(2) > L.sdb_mlp_pack_bytes(0) > 700000
-    assert L.sdb_render_workspace_bytes(1, 570, 990) == (72 * 62 + 4) * 4
+    assert L.sdb_render_workspace_bytes(1, 570, 990) == (72 * 62 + 8) * 4      # counters, tile list, by-value camera slot
 
 
 def test_render_params_struct_matches_header():
@@ -59,12 +59,21 @@ def test_render_params_struct_matches_header():
 
 @pytest.fixture()
 def dropin_path():
+    """dropin/ first on the path, then the reference's own Python (staged copy or /root/reference): the `gridencoder`
+    package is the REFERENCE's, running on dropin/_gridencoder.py (gridencoder/grid.py:9-12 imports it by name)."""
+    from oracle import refgen
+    ref = refgen.reference_python_root()
+    mods = ('voxlib', '_gridencoder', 'gridencoder', 'gridencoder.grid')
     sys.path.insert(0, DROPIN)
-    for m in ('voxlib', '_gridencoder', 'gridencoder', 'gridencoder.grid'):
+    if ref is not None:
+        sys.path.insert(1, ref)
+    for m in mods:
         sys.modules.pop(m, None)
-    yield
+    yield ref
     sys.path.remove(DROPIN)
-    for m in ('voxlib', '_gridencoder', 'gridencoder', 'gridencoder.grid'):
+    if ref is not None:
+        sys.path.remove(ref)
+    for m in mods:
         sys.modules.pop(m, None)
 
 
@@ -91,10 +100,19 @@ def test_voxlib_and_gridencoder_module_surface(dropin_path):
     with pytest.raises(RuntimeError):
         voxlib.positional_encoding(torch.zeros(3, 3), 2, -1, True)
     with pytest.raises(RuntimeError):
-        voxlib.sp_trilinear_worldcoord(None, None, None, False, -1)
+        voxlib.sp_trilinear_worldcoord(torch.zeros(4, 2), torch.zeros(2, 2, 2, dtype=torch.int32), torch.zeros(3, 3), False, -1)
+    # import-time stand-ins of the two StyleGAN2 extensions imaginaire.layers hard-imports
+    import bias_act_cuda
+    import upfirdn2d_cuda
+    with pytest.raises(RuntimeError):
+        upfirdn2d_cuda.upfirdn2d(None)
+    with pytest.raises(RuntimeError):
+        bias_act_cuda.bias_act(None)
 
 
 def test_gridencoder_module_state(dropin_path, golden_ops):
+    if dropin_path is None:
+        pytest.skip('reference Python not available (oracle/_ref/py, /root/reference)')
     from gridencoder import GridEncoder
     from gridencoder.grid import VarGridEncoder
     ge = GridEncoder(input_dim=5, num_levels=16, level_dim=8, base_resolution=16, log2_hashmap_size=19,

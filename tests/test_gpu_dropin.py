@@ -18,10 +18,19 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 
 @pytest.fixture(scope='module')
 def gridencoder_pkg():
+    """The REFERENCE's own `gridencoder` package (staged copy, unmodified) on top of dropin/_gridencoder.py: its grid.py
+    does `import _gridencoder as _backend` (gridencoder/grid.py:9-12), so no copy of it lives in this repository."""
+    from oracle import refgen
+    ref = refgen.reference_python_root()
+    if ref is None:
+        pytest.skip('reference Python not staged (oracle/build_ref.py)')
     sys.path.insert(0, os.path.join(ROOT, 'dropin'))
+    sys.path.insert(1, ref)
     import gridencoder
+    assert gridencoder.grid._backend.__file__.startswith(os.path.join(ROOT, 'dropin'))
     yield gridencoder
     sys.path.remove(os.path.join(ROOT, 'dropin'))
+    sys.path.remove(ref)
 
 
 def device_level_scales(L, pls, base):
@@ -86,7 +95,13 @@ def test_patched_forward_perpix_matches_oracle(golden_ops):
     def sub(prefix):
         return Holder({k[len(prefix) + 1:]: v for k, v in P.items() if k.startswith(prefix + '.')})
 
-    gen = types.SimpleNamespace()
+    called = {}
+
+    class Gen:                                                # duck-typed stand-in; the real class: tests/test_gpu_generator.py
+        def _forward_perpix(self, *a):
+            called['ref'] = True
+
+    gen = Gen()
     gen.render_net, gen.sky_net, gen.hash_encoder = sub('render_net'), sub('sky_net'), sub('hash_encoder')
     gen.hash_encoder.per_level_scale, gen.hash_encoder.base_resolution = pls, 16
     gen.hash_encoder.log2_hashmap_size, gen.hash_encoder.num_levels = 19, 16
@@ -97,8 +112,6 @@ def test_patched_forward_perpix_matches_oracle(golden_ops):
     gen.sample_use_box_boundaries, gen.raw_noise_std = False, 0.0
     gen.pe_params, gen.pe_params_sky = [0, 0, 0, False], [5, True]
     gen.coarse_deterministic_sampling, gen.num_samples, gen.sample_depth, gen.dists_scale = True, 24, 3, 0.25
-    called = {}
-    gen._forward_perpix = lambda *a: called.setdefault('ref', True)
     integration.patch_generator(gen)
     g = torch.Generator().manual_seed(8888)
     z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)

@@ -32,6 +32,7 @@ class _FakeTensor:
         self.shape = t.shape
         self.is_cuda = True
         self.device = 'cuda:0'
+        self._base = None
 
     def __getitem__(self, idx):
         return _FakeTensor(self.t[idx])
@@ -44,18 +45,28 @@ class _FakeTensor:
 
 
 def _fake_generator(n_views, monkeypatch, calls):
-    gen = types.SimpleNamespace()
+    class Gen:                                               # stands in for imaginaire.generators.scenedreamer.Generator
+        def _forward_perpix(self, *a):
+            calls.append('reference')
+            return ('ref',)
+
+        def forward(self, *a):
+            return 'fwd'
+
+    integration.install(Gen)
+    assert Gen._forward_perpix is integration.fused_forward_perpix and Gen().forward() == 'fwd'
+    gen = Gen()
     lin = torch.nn.Linear(4, 4)
     gen.render_net, gen.sky_net, gen.hash_encoder = lin, torch.nn.Linear(2, 2), torch.nn.Linear(2, 2)
     gen.hash_encoder.per_level_scale, gen.hash_encoder.base_resolution = 1.38, 16
     gen.hash_encoder.log2_hashmap_size, gen.hash_encoder.num_levels = 19, 16
     gen.voxel = types.SimpleNamespace(voxel_t=torch.zeros(4, 8, 8))
+    gen.label_trans = types.SimpleNamespace(mcid2rdid_lut=torch.zeros(4, dtype=torch.long), ignore_id=0, dirt_id=3)
     gen.clip_feat_map, gen.keep_sky_out, gen.keep_sky_out_avgpool, gen.sky_global_avgpool = True, True, True, True
     gen.sample_use_box_boundaries, gen.raw_noise_std = False, 0.0
     gen.pe_params, gen.pe_params_sky = [0, 0, 0, False], [5, True]
     gen.coarse_deterministic_sampling, gen.num_samples, gen.sample_depth, gen.dists_scale = True, 4, 3, 0.25
-    st = types.SimpleNamespace(lut=torch.zeros(4, dtype=torch.int32))
-    st.reference_forward = lambda *a: calls.append('reference') or ('ref',)
+    st = integration._state(gen)
 
     class R:
         def forward(self, *a, **k):
@@ -63,8 +74,10 @@ def _fake_generator(n_views, monkeypatch, calls):
             n = a[0].shape[0]
             z = torch.zeros(n, 2, 2)
             return dict(net_out=torch.zeros(n, 2, 2, 64), total_weight=z, weights=z, rand_depth=z, sky=torch.zeros(n, 2, 2, 64))
-    st.get = lambda g: R()
-    gen._sdb200 = st
+
+        def invalidate(self):
+            calls.append('invalidate')
+    st.get_renderer = lambda g: R()
 
     def fake_train(P, vid, *a, **k):
         calls.append('train')
@@ -104,7 +117,64 @@ def test_hook_dispatch_rules(monkeypatch):
     assert calls == ['reference']
     calls.clear()
     gen.raw_noise_std = 0.0
-    for q in list(gen.render_net.parameters()) + list(gen.hash_encoder.parameters()):
+    for q in list(gen.render_net.parameters()) + list(gen.hash_encoder.parameters()) + list(gen.sky_net.parameters()):
         q.requires_grad_(False)
     f(gen, None, vid, dep, rd, ori, z, genc)                        # nothing to differentiate: inference kernel even with grad mode on
     assert calls == ['inference']
+
+
+def test_hook_gates_and_epochs(monkeypatch):
+    calls = []
+    gen, vid, dep, rd = _fake_generator(1, monkeypatch, calls)
+    ori, z, genc = torch.zeros(1, 3), torch.zeros(1, 4), torch.zeros(1, 2)
+    f = integration.fused_forward_perpix
+    with torch.no_grad():
+        f(gen, None, vid, dep, rd, ori, None, genc)                  # style_dims == 0: no style code -> reference composition
+        assert calls == ['reference']
+        calls.clear()
+        gen.pe_params = [0, 0, 0, True]                              # view direction fed to the MLP: not covered
+        f(gen, None, vid, dep, rd, ori, z, genc)
+        assert calls == ['reference']
+        calls.clear()
+        gen.pe_params = [0, 0, 0, False]
+        monkeypatch.setenv('SDB200_FUSED', '0')                      # switch: the reference's own composition
+        f(gen, None, vid, dep, rd, ori, z, genc)
+        assert calls == ['reference']
+        monkeypatch.delenv('SDB200_FUSED')
+    calls.clear()
+    for q in list(gen.render_net.parameters()) + list(gen.hash_encoder.parameters()):
+        q.requires_grad_(False)
+    f(gen, None, vid, dep, rd, ori, z, genc)                         # only sky_net trains: still the differentiable path
+    assert calls == ['train']
+    # every public entry starts a new epoch
+    st = integration._state(gen)
+    e = st.epoch
+    assert gen.forward() == 'fwd' and st.epoch == e + 1
+    # wrappers: WrappedModel / DDP (.module), ModelAverage (.averaged_model), nested
+    inner = types.SimpleNamespace(module=types.SimpleNamespace(averaged_model=types.SimpleNamespace(module=gen)))
+    assert integration._unwrap(inner) is gen
+    with pytest.raises(TypeError):
+        integration.patch_generator(types.SimpleNamespace(module=object()))
+    integration.invalidate(inner)
+    assert st.epoch == e + 2
+
+
+def test_renderer_caches_key_on_identity_not_address(monkeypatch):
+    """a new style tensor that happens to reuse the freed tensor's address must repack."""
+    built = []
+    monkeypatch.setattr(render, 'pack_mlp', lambda P, z, prec: built.append(float(z[0, 0])) or ('pack', len(built)))
+    r = render.FusedPerPixelRenderer({}, (4, 8, 8), torch.zeros(4, dtype=torch.int32), 1.38)
+    ptrs = set()
+    for k in range(4):
+        z = torch.full((1, 256), float(k))
+        ptrs.add(z.data_ptr())
+        assert r.pack_for(z) == ('pack', k + 1)
+        assert r.pack_for(z) == ('pack', k + 1)                      # same object, same version: cached
+        del z
+    assert built == [0.0, 1.0, 2.0, 3.0]
+    z = torch.zeros(1, 256)
+    p1 = r.pack_for(z)
+    z.add_(1.0)                                                      # in-place edit bumps the version counter
+    assert r.pack_for(z) != p1
+    r.invalidate()
+    assert r.pack_for(z) != ('pack', len(built) - 1)
