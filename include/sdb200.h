@@ -5,8 +5,8 @@
  * Conventions
  *   - every pointer named d_* is a DEVICE pointer owned by the caller; nothing is allocated,
  *     freed or retained by the library (no ownership transfer, re-entrant; the only process-wide
- *     state is one cuBLAS handle per device, created by the first sdb_*_backward call, and the
- *     optional diagnostics pointer);
+ *     state is a launch counter and the optional diagnostics pointer; the library links against
+ *     the CUDA runtime only -- no cuBLAS / cuDNN);
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *   - every entry point returns 0 on success, a positive cudaError_t on a CUDA failure, or a
  *     negative SDB_E* code for an argument error; no exceptions cross the ABI.  The Python
@@ -227,7 +227,8 @@ int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W,
  *      -> dZ of every layer (bf16 record) and dL/d features;
  *   3. table backward through the pre-blended 3-D table (vector red.add), un-blend to the raw 5-D
  *      table, and the scene-code gradient;
- *   4. weight gradients: bf16 GEMMs dZ^T * A over all samples (cuBLAS, fp32 accumulate/output).
+ *   4. weight gradients: dZ^T * A over all samples on the tensor cores (hand-written tcgen05 kernel: the
+ *      bf16 records are MMA-ready tiles, fp32 accumulators in TMEM; csrc/wgrad.cu).
  * The same sdb_render_params as the forward call must be passed (same rays, uniforms, packs).
  * The call reads the live-tile count back (one 4-byte D2H copy + stream synchronize).
  * ------------------------------------------------------------------------------------------ */
@@ -265,7 +266,7 @@ int sdb_render_rays_backward(const sdb_render_params *p, const void *d_record, c
  * that also records PE(raydir), the five hidden activations (bf16) and their LeakyReLU sign
  * words; sdb_sky_backward turns dL/d sky [R,64] (ray order; the contribution of the frame mean
  * already added by the caller) into the SKYMLP weight gradients (gancraft_base.py:150-169 under
- * torch.autograd): gradient chain on the tensor-core engine + bf16 GEMMs.
+ * torch.autograd): gradient chain + weight gradients on the tensor-core engine.
  *   d_grad_w1ext [256, 48]: cols 0..32 fc1.weight, col 47 the layer-0 bias (fc1.bias + fc_z_a(z));
  *   d_grad_wh [4][256, 272]: fc2..fc5 (cols 0..255 weight, col 256 bias); d_grad_wout [64, 272].
  *   backward pack: sdb_pack_sky_mlp_backward(wh [4][256,256], wout [64,256]).

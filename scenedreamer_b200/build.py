@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 LIB = os.path.join(HERE, 'libsdb200.so')
-SOURCES = ['api.cu', 'dda.cu', 'gridenc.cu', 'posenc.cu', 'tc_selftest.cu', 'render_fused.cu', 'render_train.cu']
+SOURCES = ['api.cu', 'dda.cu', 'gridenc.cu', 'posenc.cu', 'tc_selftest.cu', 'render_fused.cu', 'render_train.cu', 'wgrad.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '--expt-relaxed-constexpr']
 
@@ -61,11 +61,9 @@ def build(force=False, verbose=False):
         return obj
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(cc, srcs))
-    # cuBLAS serves the plain weight-gradient GEMMs of render_train.cu; the rpath covers processes that have not
-    # already loaded a libcublas.so.12 (torch brings its own)
+    # no library dependency besides the CUDA runtime: every kernel on the path, the weight-gradient GEMMs included, is ours
     tmp = LIB + '.tmp.%d' % os.getpid()                       # link aside, then rename: nobody dlopens a half-written file
-    cmd = [nvcc, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-lcublas',
-                                                '-Xlinker', '-rpath=/usr/local/cuda/lib64']
+    cmd = [nvcc, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

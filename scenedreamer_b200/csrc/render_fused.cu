@@ -386,13 +386,15 @@ mlp_kernel(const Params p)
                         // the training record is written AFTER the chunk has been handed to the MMA issuer (off the critical path)
                         if constexpr (TRAIN || BWD) {
                             // forward: A_{l+1}[slot][128*half + c0 ..], backward: dZ_{6-l}[slot][...]
-                            uint16_t *dst = TRAIN
-                                ? p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + half * 128 + c0
-                                : p.tr.dz + ((long long)(NACT - 1 - l) * p.tr.slot_cap + slot) * kHidden + half * 128 + c0;
+                            // (tiled record: a warp's 32 rows of one 8-column chunk are 512 contiguous bytes)
+                            uint16_t *arr = TRAIN ? p.tr.act + (long long)l * p.tr.slot_cap * kActCols
+                                                  : p.tr.dz + (long long)(NACT - 1 - l) * p.tr.slot_cap * kHidden;
+                            constexpr int nch = (TRAIN ? kActCols : kHidden) / 8;
+                            const int ch0 = (half * 128 + c0) >> 3;
 #pragma unroll
-                            for (int q = 0; q < 2; q++)
-                                st_global_v8(dst + 16 * q, make_uint4(rec[8 * q], rec[8 * q + 1], rec[8 * q + 2], rec[8 * q + 3]),
-                                             make_uint4(rec[8 * q + 4], rec[8 * q + 5], rec[8 * q + 6], rec[8 * q + 7]));
+                            for (int q = 0; q < 4; q++)
+                                *reinterpret_cast<uint4 *>(rec_chunk(arr, slot, nch, ch0 + q)) =
+                                    make_uint4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
                         }
                         if constexpr (TRAIN) p.tr.mask[((step_id * kNumAct + l) * kRows + row) * 8 + half * 4 + (c0 >> 5)] = mword;
                     }
@@ -400,9 +402,11 @@ mlp_kernel(const Params p)
                     tc05::mbar_arrive(&bars[B_EPIDONE + (g & 1u)]);        // accumulator buffer (g & 1) is free again
                     if (MODE == kRender && l == 3) sSig[half * kRows + row] = sig_part;
                     if constexpr (TRAIN) {   // the constant-1 column that turns the weight-gradient GEMM's column 256 into the bias gradient
-                        if (half == 0)
-                            st_global_v8(p.tr.act + ((long long)l * p.tr.slot_cap + slot) * kActCols + kHidden,
-                                         make_uint4(0x3F80u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
+                        if (half == 0) {
+                            uint16_t *arr = p.tr.act + (long long)l * p.tr.slot_cap * kActCols;
+                            *reinterpret_cast<uint4 *>(rec_chunk(arr, slot, kActCols / 8, kHidden / 8)) = make_uint4(0x3F80u, 0u, 0u, 0u);
+                            *reinterpret_cast<uint4 *>(rec_chunk(arr, slot, kActCols / 8, kHidden / 8 + 1)) = make_uint4(0u, 0u, 0u, 0u);
+                        }
                     }
                 }
                 // ---- colour layer ----
@@ -422,14 +426,12 @@ mlp_kernel(const Params p)
                         const uint32_t word = c0 == 0 ? mw.x : (c0 == 32 ? mw.y : (c0 == 64 ? mw.z : mw.w));
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = ((word >> j) & 1u) ? v[j] : 0.2f * v[j];
-                        uint16_t *dst = p.tr.dz + slot * kHidden + half * 128 + c0;
+                        const int ch0 = (half * 128 + c0) >> 3;
 #pragma unroll
-                        for (int q = 0; q < 2; q++)
-                            st_global_v8(dst + 16 * q,
-                                         make_uint4(tc05::pack2<true>(v[16 * q], v[16 * q + 1]), tc05::pack2<true>(v[16 * q + 2], v[16 * q + 3]),
-                                                    tc05::pack2<true>(v[16 * q + 4], v[16 * q + 5]), tc05::pack2<true>(v[16 * q + 6], v[16 * q + 7])),
-                                         make_uint4(tc05::pack2<true>(v[16 * q + 8], v[16 * q + 9]), tc05::pack2<true>(v[16 * q + 10], v[16 * q + 11]),
-                                                    tc05::pack2<true>(v[16 * q + 12], v[16 * q + 13]), tc05::pack2<true>(v[16 * q + 14], v[16 * q + 15])));
+                        for (int q = 0; q < 4; q++)
+                            *reinterpret_cast<uint4 *>(rec_chunk(p.tr.dz, slot, kHidden / 8, ch0 + q)) =
+                                make_uint4(tc05::pack2<true>(v[8 * q], v[8 * q + 1]), tc05::pack2<true>(v[8 * q + 2], v[8 * q + 3]),
+                                           tc05::pack2<true>(v[8 * q + 4], v[8 * q + 5]), tc05::pack2<true>(v[8 * q + 6], v[8 * q + 7]));
                     }
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
@@ -761,14 +763,12 @@ mlp_kernel(const Params p)
                         split8<PREC>(v8, ch[c], cl[c]);
                     }
                     if constexpr (TRAIN) {   // bf16 copy of the layer-0 operand: X0[slot][48] (fc1 weight / bias gradient)
-                        uint16_t *dst = p.tr.x0 + ((long long)work * kRows + row) * kSkyK0;
+                        const long long slot0 = (long long)work * kRows + row;
 #pragma unroll
-                        for (int q = 0; q < 3; q++)
-                            st_global_v8(dst + 16 * q,
-                                         make_uint4(tc05::pack2<true>(pe[16 * q], pe[16 * q + 1]), tc05::pack2<true>(pe[16 * q + 2], pe[16 * q + 3]),
-                                                    tc05::pack2<true>(pe[16 * q + 4], pe[16 * q + 5]), tc05::pack2<true>(pe[16 * q + 6], pe[16 * q + 7])),
-                                         make_uint4(tc05::pack2<true>(pe[16 * q + 8], pe[16 * q + 9]), tc05::pack2<true>(pe[16 * q + 10], pe[16 * q + 11]),
-                                                    tc05::pack2<true>(pe[16 * q + 12], pe[16 * q + 13]), tc05::pack2<true>(pe[16 * q + 14], pe[16 * q + 15])));
+                        for (int q = 0; q < kSkyK0 / 8; q++)
+                            *reinterpret_cast<uint4 *>(rec_chunk(p.tr.x0, slot0, kSkyK0 / 8, q)) =
+                                make_uint4(tc05::pack2<true>(pe[8 * q], pe[8 * q + 1]), tc05::pack2<true>(pe[8 * q + 2], pe[8 * q + 3]),
+                                           tc05::pack2<true>(pe[8 * q + 4], pe[8 * q + 5]), tc05::pack2<true>(pe[8 * q + 6], pe[8 * q + 7]));
                     }
                 }
                 if (gt == 0) SDB_MARK(4, 3, n, it);
@@ -799,7 +799,7 @@ mlp_kernel(const Params p)
                         const float v8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                         split8<PREC>(v8, gh[q], gl[q]);
                         if constexpr (SKYBWD)     // bf16 copy in slot order: operand of the fc_out_c weight-gradient GEMM
-                            *reinterpret_cast<uint4 *>(p.tr.dc16 + slot * kOutC + half * 32 + 8 * q) =
+                            *reinterpret_cast<uint4 *>(rec_chunk(p.tr.dc16, slot, kOutC / 8, half * 4 + q)) =
                                 make_uint4(tc05::pack2<true>(a.x, a.y), tc05::pack2<true>(a.z, a.w), tc05::pack2<true>(b.x, b.y),
                                            tc05::pack2<true>(b.z, b.w));
                     }
@@ -898,7 +898,7 @@ mlp_kernel(const Params p)
                         split8<PREC>(res, fh[i], fl[i]);
                         if constexpr (TRAIN) {   // bf16 copy of the features: X0[slot][8*level ..] (operand of the fc_1 weight gradient)
                             const long long slot = ((long long)work * S + s) * kRows + row;
-                            *reinterpret_cast<uint4 *>(p.tr.x0 + slot * kX0Cols + level * 8) =
+                            *reinterpret_cast<uint4 *>(rec_chunk(p.tr.x0, slot, kX0Cols / 8, level)) =
                                 make_uint4(tc05::pack2<true>(res[0], res[1]), tc05::pack2<true>(res[2], res[3]),
                                            tc05::pack2<true>(res[4], res[5]), tc05::pack2<true>(res[6], res[7]));
                         }
@@ -922,7 +922,7 @@ mlp_kernel(const Params p)
                         const int k = (int)label - 8 * half;
                         if (k >= 0 && k < 8) ob[k >> 1] = 0x3F80u << (16 * (k & 1));
                         if (half == 1) ob[3] |= 0x3F80u << 16;
-                        *reinterpret_cast<uint4 *>(p.tr.x0 + slot * kX0Cols + kFeat + 8 * half) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                        *reinterpret_cast<uint4 *>(rec_chunk(p.tr.x0, slot, kX0Cols / 8, kFeat / 8 + half)) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
                     }
                     if (gt == 0) SDB_MARK(4, 3, n, it);
                     if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);

@@ -16,12 +16,13 @@
 //   3. table3_backward_kernel     : scatter into the PRE-BLENDED 3-D table (8 corners instead of 32, vector
 //                                   red.add), then the transpose of the pre-blend (the same gather kernel:
 //                                   XOR-indexing is an involution) and the scene-code gradient;
-//   4. weight gradients           : plain bf16 GEMMs dZ^T * A over all samples through cuBLAS (fp32 out).
-#include <cublas_v2.h>
+//   4. weight gradients           : dZ^T * A over all samples on the tensor cores (wgrad.cu): the bf16 records are
+//                                   MMA-ready tiles, bulk-copied into shared memory, fp32 accumulators in TMEM.
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "rf_common.cuh"
+#include "wgrad.cuh"
 
 namespace rf {
 
@@ -61,8 +62,7 @@ static void bind_record(Params &p, uint8_t *rec, const RecordLayout &r) {
     p.tr.c = reinterpret_cast<float *>(rec + r.c);
 }
 
-constexpr size_t kCublasWsBytes = (size_t)256 << 20;   // split-K partials of the [256 x 272] x K=10^6 weight-gradient GEMMs
-struct BwdLayout { size_t dc32, dc16, dsig32, dsig16, dz, dx0, dt3, cublas, total; };
+struct BwdLayout { size_t dc32, dc16, dsig32, dsig16, dz, dx0, dt3, total; };
 static BwdLayout bwd_layout(long long n_tiles, int S, int L, int log2_T) {
     const size_t cap = (size_t)n_tiles * S * kRows;
     BwdLayout b{};
@@ -74,7 +74,6 @@ static BwdLayout bwd_layout(long long n_tiles, int S, int L, int log2_T) {
     b.dz = o; o = align_up(o + (size_t)kNumAct * cap * kHidden * 2);
     b.dx0 = o; o = align_up(o + cap * kFeat * 4);
     b.dt3 = o; o = align_up(o + ((size_t)L << log2_T) * 8 * 4);
-    b.cublas = o; o = align_up(o + kCublasWsBytes);
     b.total = o;
     return b;
 }
@@ -157,7 +156,7 @@ composite_backward_kernel(const Params p, const float *__restrict__ g_out, float
             const float ws = __shfl_sync(full, s < 32 ? w0 : w1, s & 31);
             const float dcx = in_clamp(c.x) ? ws * g.x : 0.0f, dcy = in_clamp(c.y) ? ws * g.y : 0.0f;
             *reinterpret_cast<float2 *>(dc32 + slot * kOutC + 2 * lane) = make_float2(dcx, dcy);
-            *reinterpret_cast<uint32_t *>(dc16 + slot * kOutC + 2 * lane) = tc05::pack2<true>(dcx, dcy);
+            *reinterpret_cast<uint32_t *>(rec_chunk(dc16, slot, kOutC / 8, lane >> 2) + 2 * (lane & 3)) = tc05::pack2<true>(dcx, dcy);
             if (s == lane) dw0 = dw;
             if (s == lane + 32) dw1 = dw;
         }
@@ -344,32 +343,17 @@ genc_backward_kernel(const float *__restrict__ table, const float *__restrict__ 
     }
 }
 
-// ---- 4. weight gradients through cuBLAS ----------------------------------------------------------------
-// One handle per device, created on first use (the only process-global state of the library besides the
-// diagnostics pointer; creation is not thread-safe -- the reference's callers are single-threaded per process).
-static cublasHandle_t g_cublas[64] = {};
-// `ws` / `ws_bytes`: caller-owned scratch handed to cuBLAS for this call sequence.  Without it cuBLAS falls back to
-// allocating the split-K workspace itself for every GEMM whose partials exceed its small default pool -- measured here as
-// 11-18 ms of allocator stalls per backward for 1.6 ms of GEMM kernels.
-static int cublas_for_stream(cudaStream_t st, void *ws, size_t ws_bytes, cublasHandle_t *out) {
-    int dev = 0;
-    SDB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return SDB_EUNSUPPORTED;
-    if (!g_cublas[dev] && cublasCreate(&g_cublas[dev]) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorInitializationError;
-    if (cublasSetStream(g_cublas[dev], st) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
-    if (getenv("SDB_CUBLAS_OWN_WS") == nullptr || atoi(getenv("SDB_CUBLAS_OWN_WS")) != 0)      // diagnostics: 0 = cuBLAS' default pool
-        if (cublasSetWorkspace(g_cublas[dev], ws, ws_bytes) != CUBLAS_STATUS_SUCCESS) return (int)cudaErrorUnknown;
-    *out = g_cublas[dev];
-    return SDB_OK;
-}
-// C [n_out, k_in] (row-major fp32) = dZ^T [n_out, M] * A [M, k_in]; A, dZ row-major bf16 with row strides lda, ldz
-static int wgrad(cublasHandle_t h, const uint16_t *A, int lda, int k_in, const uint16_t *dZ, int ldz, int n_out, long long M,
-                 float *C) {
-    const float one = 1.0f, zero = 0.0f;
-    const cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, k_in, n_out, (int)M, &one, A, CUDA_R_16BF, lda, dZ,
-                                          CUDA_R_16BF, ldz, &zero, C, CUDA_R_32F, k_in, CUBLAS_COMPUTE_32F,
-                                          CUBLAS_GEMM_DEFAULT_TENSOR_OP);
-    return s == CUBLAS_STATUS_SUCCESS ? SDB_OK : (int)cudaErrorUnknown;
+// ---- 4. weight gradients: job lists for wgrad.cu ------------------------------------------------------------------
+// One job per 128-row M-tile of a layer's output.  A = the layer's input record, Z = the gradient at its pre-activation.
+static void add_jobs(WgJob *jobs, int &n, const uint16_t *A, int a_cols, const uint16_t *Z, int z_cols, float *out, int n_out) {
+    for (int r0 = 0; r0 < z_cols; r0 += 128) {
+        WgJob &j = jobs[n++];
+        j = WgJob{};
+        j.A = A; j.Z = Z; j.out = out;
+        j.a_chunks = a_cols / 8;
+        j.z_chunks_total = z_cols / 8; j.z_chunk0 = r0 / 8; j.z_chunks = (z_cols - r0 < 128 ? z_cols - r0 : 128) / 8;
+        j.ld_out = a_cols; j.row0 = r0; j.rows = (n_out - r0 < 128 ? n_out - r0 : 128);
+    }
 }
 
 }  // namespace rf
@@ -464,13 +448,6 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
     SDB_CUDA(cudaStreamSynchronize(st));
     if (n_live < 0 || n_live > p.n_tiles) return SDB_EINVAL;
     const long long n_slots = (long long)n_live * p.S * kRows;
-    // The GEMMs below reduce over the slot dimension.  cuBLAS plans every NEW problem size on the host (measured: ~1.5 ms per
-    // GEMM, 12 ms per backward, whenever the live-tile count differs from the previous call -- and the plans do not stick
-    // when a few sizes alternate), so that dimension is made a constant of the frame geometry: the GEMMs always run over
-    // the buffers' full capacity and the rows of both operands beyond the live slots are zero-filled (one memset per
-    // array, a few GB at HBM speed ~ 0.8 ms for a 256x256 view) -- 8 plans per resolution, made once.
-    const int n_live_pad = p.n_tiles;
-    const long long n_slots_pad = (long long)n_live_pad * p.S * kRows;
     const size_t table_bytes = ((size_t)sp->L << p.log2_T) * 8 * 4;
 
     SDB_CUDA(cudaMemsetAsync(g->d_grad_sky_avg, 0, (size_t)p.n_img * kOutC * 4, st));
@@ -524,33 +501,22 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         SDB_CHECK_LAUNCH();
     }
     mark();
-    // 4. weight gradients (bf16 x bf16 -> fp32 GEMMs over all recorded samples)
+    // 4. weight gradients on the tensor cores (every live item, nothing else: no padding rows to zero)
     {
-        const long long cap0 = p.tr.slot_cap;
-        const size_t pad = (size_t)(n_slots_pad - n_slots);
-        if (pad > 0) {
-            SDB_CUDA(cudaMemsetAsync(p.tr.x0 + (size_t)n_slots * kX0Cols, 0, pad * kX0Cols * 2, st));
-            SDB_CUDA(cudaMemsetAsync(dc16 + (size_t)n_slots * kOutC, 0, pad * kOutC * 2, st));
-            SDB_CUDA(cudaMemsetAsync(dsig16 + (size_t)n_slots * 8, 0, pad * 8 * 2, st));
-            for (int k = 0; k < kNumAct; k++) {
-                SDB_CUDA(cudaMemsetAsync(p.tr.act + ((size_t)k * cap0 + n_slots) * kActCols, 0, pad * kActCols * 2, st));
-                SDB_CUDA(cudaMemsetAsync(dz + ((size_t)k * cap0 + n_slots) * kHidden, 0, pad * kHidden * 2, st));
-            }
-        }
-        cublasHandle_t h;
-        int rc = cublas_for_stream(st, ws + bl.cublas, kCublasWsBytes, &h);
-        if (rc != SDB_OK) return rc;
+        SDB_CUDA(cudaMemsetAsync(g->d_grad_w1ext, 0, (size_t)kHidden * kX0Cols * 4, st));
+        SDB_CUDA(cudaMemsetAsync(g->d_grad_wh, 0, (size_t)5 * kHidden * kActCols * 4, st));
+        SDB_CUDA(cudaMemsetAsync(g->d_grad_wsig, 0, (size_t)8 * kActCols * 4, st));
+        SDB_CUDA(cudaMemsetAsync(g->d_grad_wout, 0, (size_t)kOutC * kActCols * 4, st));
         const long long cap = p.tr.slot_cap;
-        rc = wgrad(h, p.tr.x0, kX0Cols, kX0Cols, dz, kHidden, kHidden, n_slots_pad, g->d_grad_w1ext);                       // fc_1 | fc_m_a | bias
-        if (rc != SDB_OK) return rc;
-        for (int k = 0; k < 5; k++) {                                                                                   // fc_2 .. fc_6
-            rc = wgrad(h, p.tr.act + (size_t)k * cap * kActCols, kActCols, kActCols, dz + (size_t)(k + 1) * cap * kHidden, kHidden,
-                       kHidden, n_slots_pad, g->d_grad_wh + (size_t)k * kHidden * kActCols);
-            if (rc != SDB_OK) return rc;
-        }
-        rc = wgrad(h, p.tr.act + (size_t)5 * cap * kActCols, kActCols, kActCols, dc16, kOutC, kOutC, n_slots_pad, g->d_grad_wout);   // fc_out_c
-        if (rc != SDB_OK) return rc;
-        rc = wgrad(h, p.tr.act + (size_t)3 * cap * kActCols, kActCols, kActCols, dsig16, 8, 8, n_slots_pad, g->d_grad_wsig);         // fc_sigma
+        WgJob jobs[kWgMaxJobs];
+        int nj = 0;
+        add_jobs(jobs, nj, p.tr.x0, kX0Cols, dz, kHidden, g->d_grad_w1ext, kHidden);                                  // fc_1 | fc_m_a | bias
+        for (int k = 0; k < 5; k++)                                                                                    // fc_2 .. fc_6
+            add_jobs(jobs, nj, p.tr.act + (size_t)k * cap * kActCols, kActCols, dz + (size_t)(k + 1) * cap * kHidden, kHidden,
+                     g->d_grad_wh + (size_t)k * kHidden * kActCols, kHidden);
+        add_jobs(jobs, nj, p.tr.act + (size_t)5 * cap * kActCols, kActCols, dc16, kOutC, g->d_grad_wout, kOutC);       // fc_out_c
+        add_jobs(jobs, nj, p.tr.act + (size_t)3 * cap * kActCols, kActCols, dsig16, 8, g->d_grad_wsig, 8);             // fc_sigma
+        const int rc = launch_wgrad(jobs, nj, (long long)n_live * p.S, st);
         if (rc != SDB_OK) return rc;
     }
     mark();
@@ -605,15 +571,15 @@ extern "C" int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void 
         const int rc = launch_sky_bwd_chain(p, grid, st);
         if (rc != SDB_OK) return rc;
     }
-    cublasHandle_t h;
-    int rc = cublas_for_stream(st, ws + bl.cublas, kCublasWsBytes, &h);
-    if (rc != SDB_OK) return rc;
-    rc = wgrad(h, p.tr.x0, kSkyK0, kSkyK0, p.tr.dz, kHidden, kHidden, cap, d_grad_w1ext);                                       // fc1 | bias
-    if (rc != SDB_OK) return rc;
-    for (int k = 0; k < 4; k++) {                                                                                               // fc2 .. fc5
-        rc = wgrad(h, p.tr.act + (size_t)k * cap * kActCols, kActCols, kActCols, p.tr.dz + (size_t)(k + 1) * cap * kHidden, kHidden,
-                   kHidden, cap, d_grad_wh + (size_t)k * kHidden * kActCols);
-        if (rc != SDB_OK) return rc;
-    }
-    return wgrad(h, p.tr.act + (size_t)4 * cap * kActCols, kActCols, kActCols, p.tr.dc16, kOutC, kOutC, cap, d_grad_wout);      // fc_out_c
+    SDB_CUDA(cudaMemsetAsync(d_grad_w1ext, 0, (size_t)kHidden * kSkyK0 * 4, st));
+    SDB_CUDA(cudaMemsetAsync(d_grad_wh, 0, (size_t)4 * kHidden * kActCols * 4, st));
+    SDB_CUDA(cudaMemsetAsync(d_grad_wout, 0, (size_t)kOutC * kActCols * 4, st));
+    WgJob jobs[kWgMaxJobs];
+    int nj = 0;
+    add_jobs(jobs, nj, p.tr.x0, kSkyK0, p.tr.dz, kHidden, d_grad_w1ext, kHidden);                                              // fc1 | bias
+    for (int k = 0; k < 4; k++)                                                                                               // fc2 .. fc5
+        add_jobs(jobs, nj, p.tr.act + (size_t)k * cap * kActCols, kActCols, p.tr.dz + (size_t)(k + 1) * cap * kHidden, kHidden,
+                 d_grad_wh + (size_t)k * kHidden * kActCols, kHidden);
+    add_jobs(jobs, nj, p.tr.act + (size_t)4 * cap * kActCols, kActCols, p.tr.dc16, kOutC, d_grad_wout, kOutC);                // fc_out_c
+    return launch_wgrad(jobs, nj, p.n_tiles, st);
 }

@@ -155,11 +155,21 @@ static_assert(B_COUNT <= kBarSlots, "barrier table");
 constexpr int kX0Cols = kRenderK0;           // 144: features | one-hot label | 1
 constexpr int kActCols = kHidden + 16;       // 272: activations | 1 | 0 x 15 (the 1 makes the wgrad GEMM emit the bias grad; 544 B rows stay 32 B aligned)
 constexpr int kNumAct = 6;
+// The bf16 arrays of the record (x0, act, dz, dc16) are kept as MMA-READY TILES, not row-major: an array of C columns is
+//   [work item = slot / 128][chunk = column / 8][row = slot % 128][8 columns]      (16 B per (row, chunk), 2 KB per chunk)
+// so that (a) a warp of 32 consecutive rows writes 512 contiguous bytes per store instruction and (b) one item of an
+// array is a contiguous range that the weight-gradient kernel (wgrad.cu) bulk-copies into shared memory, where it is a
+// canonical MN-major tcgen05 operand whose reduction dimension is the samples.
+__host__ __device__ __forceinline__ uint16_t *rec_chunk(uint16_t *base, long long slot, int n_chunks, int chunk) {
+    return base + ((((slot >> 7) * n_chunks + chunk) << 10) + ((slot & 127) << 3));
+}
+static_assert(kRows == 128, "rec_chunk assumes 128-row work items");
+
 struct TrainBuf {
     long long slot_cap;        // slots the buffers were sized for (n_tiles * S * 128)
     float4 *x3;                // [slots] (x, y, z in [0,1], w = +1 inside / -1 skip in the table backward)
-    uint16_t *x0;              // [slots][144] bf16 (render) / [slots][48] bf16 (sky: PE(raydir) | 0 | 1)
-    uint16_t *act;             // [6][slot_cap][272] bf16: A1..A6
+    uint16_t *x0;              // tiled [slots x 144] bf16 (render) / [slots x 48] bf16 (sky: PE(raydir) | 0 | 1)
+    uint16_t *act;             // [6] x tiled [slot_cap x 272] bf16: A1..A6
     uint32_t *mask;            // [steps][6][128][8]: bit j of word q = (A[., 32q + j] > 0)
     float *sig, *nds;          // [slots] sigma (pre-relu), new_dists * dists_scale
     float *c;                  // [slots][64] colour head output (pre-clamp)
@@ -167,9 +177,9 @@ struct TrainBuf {
     int32_t *tile_work;        // [n_tiles]: position in the live list or -1
     // backward chain
     const float *dc;           // [slots][64] fp32 (render) / [R][64] fp32 in RAY order (sky: dL/dsky)
-    uint16_t *dc16;            // sky only: [slots][64] bf16 copy of dL/dsky written by the chain's operand producer
+    uint16_t *dc16;            // sky only: tiled [slots x 64] bf16 copy of dL/dsky written by the chain's operand producer
     const float *dsig;         // [slots]
-    uint16_t *dz;              // [6][slot_cap][256] bf16: dZ1..dZ6
+    uint16_t *dz;              // [6] x tiled [slot_cap x 256] bf16: dZ1..dZ6
     float *dx0;                // [slots][128]
 };
 
@@ -290,14 +300,13 @@ static inline SkyRecordLayout sky_record_layout(long long n_tiles) {
     r.total = o;
     return r;
 }
-struct SkyBwdLayout { size_t dc16, dz, cublas, total; };
+struct SkyBwdLayout { size_t dc16, dz, total; };
 static inline SkyBwdLayout sky_bwd_layout(long long n_tiles) {
     const size_t cap = (size_t)n_tiles * kRows;
     SkyBwdLayout b{};
     size_t o = 0;
     b.dc16 = o; o = rf_align_up(o + cap * kOutC * 2);
     b.dz = o; o = rf_align_up(o + (size_t)Net<kSky>::NACT * cap * kHidden * 2);
-    b.cublas = o; o = rf_align_up(o + ((size_t)256 << 20));          // cuBLAS split-K scratch (kCublasWsBytes)
     b.total = o;
     return b;
 }

@@ -4,8 +4,7 @@ Mirrors the role of Generator._forward_perpix (imaginaire/generators/scenedreame
 of the tile loop in inference_givenstyle (:600-628): given the ray/voxel intersection buffers, the
 style code and the scene code it returns the per-pixel feature map `net_out` (+ depth, opacity).
 All heavy work happens in the CUDA library; torch is used to allocate tensors, to fold the style
-modulation into the weights (tiny [256x256] elementwise products, once per style code) and --
-for now -- to run the per-RAY sky MLP (3% of the FLOPs) through cuBLAS.
+modulation into the weights (tiny [256x256] elementwise products, once per style code).
 """
 import ctypes
 

@@ -91,14 +91,19 @@ def main():
 
     def rv(off, nbytes, dtype):
         return record[off:off + nbytes].view(dtype)
+
+    def untile(t, cols):
+        """bf16 records are MMA-ready tiles [item][chunk of 8 columns][128 rows][8] (rf_common.cuh: rec_chunk) -> [slots, cols]"""
+        items = t.numel() // (128 * cols)
+        return t.reshape(items, cols // 8, 128, 8).permute(0, 2, 1, 3).reshape(items * 128, cols)
     n_live = int(rv(lay[0], 4, torch.int32)[0])
     nsl = n_live * S * 128
     print('tiles %d live %d slots %d' % (ntiles, n_live, nsl))
     tile_list = rv(lay[1], ntiles * 4, torch.int32)[:n_live].long()
     rayflags = rv(lay[3], ntiles * 128 * 4, torch.int32)[:n_live * 128]
     x3 = rv(lay[4], cap * 16, torch.float32).reshape(cap, 4)[:nsl]
-    x0 = rv(lay[5], cap * 288, torch.bfloat16).reshape(cap, 144)[:nsl].float()
-    act = rv(lay[6], 6 * cap * 544, torch.bfloat16).reshape(6, cap, 272)[:, :nsl].float()
+    x0 = untile(rv(lay[5], cap * 288, torch.bfloat16), 144)[:nsl].float()
+    act = torch.stack([untile(a_, 272) for a_ in rv(lay[6], 6 * cap * 544, torch.bfloat16).reshape(6, cap * 272)])[:, :nsl].float()
     mask = rv(lay[7], steps * 6 * 128 * 8 * 4, torch.int32).reshape(steps, 6, 128, 8)[:n_live * S]
     sig = rv(lay[8], cap * 4, torch.float32)[:nsl]
     nds = rv(lay[9], cap * 4, torch.float32)[:nsl]
@@ -171,10 +176,10 @@ def main():
     def wv(off, nbytes, dtype):
         return wsb[off:off + nbytes].view(dtype)
     dc32 = wv(lay[11], cap * 256, torch.float32).reshape(cap, 64)[:nsl]
-    dc16 = wv(lay[12], cap * 128, torch.bfloat16).reshape(cap, 64)[:nsl].float()
+    dc16 = untile(wv(lay[12], cap * 128, torch.bfloat16), 64)[:nsl].float()
     dsig32 = wv(lay[13], cap * 4, torch.float32)[:nsl]
     dsig16 = wv(lay[14], cap * 16, torch.bfloat16).reshape(cap, 8)[:nsl].float()
-    dz = wv(lay[15], 6 * cap * 512, torch.bfloat16).reshape(6, cap, 256)[:, :nsl].float()
+    dz = torch.stack([untile(d_, 256) for d_ in wv(lay[15], 6 * cap * 512, torch.bfloat16).reshape(6, cap * 256)])[:, :nsl].float()
     dx0 = wv(lay[16], cap * 512, torch.float32).reshape(cap, 128)[:nsl]
 
     print('--- compositing backward (torch autograd on the recorded sigma / c) ---')
