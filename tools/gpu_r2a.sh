@@ -2,10 +2,12 @@
 # round 2, call A: full GPU test suite (incl. the real reference Generator), smoke, default bench with all legs
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
+python -m scenedreamer_b200.build > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }   # no-op when the shipped .so matches the sources
 export OMP_WAIT_POLICY=PASSIVE GOMP_SPINCOUNT=0
 timeout 1500 python -m pytest tests -m gpu -q -s -x 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
 tail -8 gpurun_out/pytest_gpu.log
 grep -E "FULL C2|timeline ms|hook stats|C2 window|C4 window" gpurun_out/pytest_gpu.log
+timeout 300 python tools/ray_stats.py --frames 4 > gpurun_out/ray_stats.log 2>&1; cat gpurun_out/ray_stats.log | cut -c1-400
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 timeout 1500 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -3 gpurun_out/bench.err
