@@ -39,6 +39,7 @@ def sp_trilinear_worldcoord(in_feature, corner_lut_t, in_worldcoord, ign_zero, c
     return _ops.sp_trilinear_worldcoord(in_feature, corner_lut_t, in_worldcoord, ign_zero, channel_pos)
 
 
-def sp_trilinear_worldcoord_backward(out_feature_grad, corner_lut_t, in_worldcoord, ign_zero, channel_pos):
+def sp_trilinear_worldcoord_backward(out_feature_grad, in_feature, corner_lut_t, in_worldcoord, ign_zero, need_coord_grad):
     """voxlib.cpp:17."""
-    return _ops.sp_trilinear_worldcoord_backward(out_feature_grad, corner_lut_t, in_worldcoord, ign_zero, channel_pos)
+    return _ops.sp_trilinear_worldcoord_backward(out_feature_grad, in_feature, corner_lut_t, in_worldcoord, ign_zero,
+                                                 need_coord_grad)

@@ -107,6 +107,24 @@ int sdb_positional_encoding_backward(const float *d_out_grad, const float *d_out
                                      void *stream);
 
 /* --------------------------------------------------------------------------------------------
+ * voxlib surface: sparse tri-linear interpolation at world coordinates (GANcraft block features;
+ * SceneDreamer never calls it, gancraft_base.py:442 does).  Replace
+ *   voxlib.sp_trilinear_worldcoord / sp_trilinear_worldcoord_backward
+ *   (voxlib.cpp:15,17,27-28; sp_trilinear_worldcoord_kernel.cu:48-338, host :351-437, :453-520).
+ *   d_feature [M, C] fp32 (row i = feature of corner id i, or id i+1 with ign_zero);
+ *   d_corner_lut int32 volume, element (a,b,c) at a*strides[0] + b*strides[1] + c*strides[2];
+ *   d_worldcoord [E, 3] fp32 contiguous; d_out [E, C]; d_out_grad [E, C]; d_feature_grad [M, C]
+ *   (zeroed by the call, then accumulated with atomics like the reference).
+ * ------------------------------------------------------------------------------------------ */
+int sdb_sp_trilinear_worldcoord(const float *d_feature, int64_t M, int32_t C, const int32_t *d_corner_lut,
+                                const int64_t lut_dims[3], const int64_t lut_strides[3],
+                                const float *d_worldcoord, int64_t E, int ign_zero, float *d_out, void *stream);
+int sdb_sp_trilinear_worldcoord_backward(const float *d_out_grad, int64_t M, int32_t C,
+                                         const int32_t *d_corner_lut, const int64_t lut_dims[3],
+                                         const int64_t lut_strides[3], const float *d_worldcoord, int64_t E,
+                                         int ign_zero, float *d_feature_grad, void *stream);
+
+/* --------------------------------------------------------------------------------------------
  * a2-a5, a8, a10-a12. Fused per-pixel render: sampling -> labels -> hash-grid features ->
  * style-modulated sigma/colour MLP (tcgen05 tensor cores) -> front-to-back compositing + sky
  * blend.  Replaces the body of Generator._forward_perpix and the tile loop around it

@@ -398,6 +398,59 @@ def make_params(seed=0, stress=False, style_dim=128, interm=256, hidden=256, fea
 
 
 # ----------------------------------------------------------------------------------------------
+# voxlib.sp_trilinear_worldcoord (surface parity; never reached by SceneDreamer).
+# imaginaire/model_utils/gancraft/voxlib/sp_trilinear_worldcoord_kernel.cu:48-198 (forward), :205-338 (backward)
+# ----------------------------------------------------------------------------------------------
+def sp_trilinear_corners(corner_lut, worldcoord, ign_zero):
+    """-> (idx int64 [E, 8] with -1 = nothing, w float32 [E, 8]); corner j: bit2 = x+1, bit1 = y+1, bit0 = z+1 (:90-105)."""
+    wc = _f32(worldcoord).reshape(-1, 3)
+    fl = torch.floor(wc)
+    loc = wc - fl
+    one = torch.tensor(1.0, dtype=torch.float32)
+    ws, ids = [], []
+    dims = torch.tensor(corner_lut.shape)
+    v0 = torch.minimum(torch.maximum(fl.nan_to_num(0.0).to(torch.int64), torch.zeros(3, dtype=torch.int64)), dims - 1)
+    v1 = torch.minimum(torch.maximum(fl.nan_to_num(0.0).to(torch.int64) + 1, torch.zeros(3, dtype=torch.int64)), dims - 1)
+    for j in range(8):
+        b = ((j >> 2) & 1, (j >> 1) & 1, j & 1)
+        f = [loc[:, d] if b[d] else one - loc[:, d] for d in range(3)]
+        ws.append((f[0] * f[1]) * f[2])                                   # fp32, left to right like the reference
+        c = [v1[:, d] if b[d] else v0[:, d] for d in range(3)]
+        ids.append(corner_lut[c[0], c[1], c[2]].to(torch.int64))
+    idx = torch.stack(ids, 1)
+    idx[torch.isnan(wc).any(1)] = -1                                      # "hard boundary check": NaN selects nothing (:108-111)
+    if ign_zero:
+        idx = idx - 1
+    return idx, torch.stack(ws, 1)
+
+
+def sp_trilinear_worldcoord(in_feature, corner_lut, worldcoord, ign_zero=False):
+    """out[e, c] = sum_j fmaf(feature[idx_j][c], w_j, acc), j = 0..7 (:186-191) -- sequential fp32 FMAs."""
+    idx, w = sp_trilinear_corners(corner_lut.cpu(), worldcoord.cpu(), ign_zero)
+    feat = _f32(in_feature).double()
+    E, C = idx.shape[0], feat.shape[1]
+    acc = torch.zeros(E, C, dtype=torch.float32)
+    for j in range(8):
+        ok = idx[:, j] >= 0
+        rows = feat[idx[:, j].clamp(min=0)]
+        upd = (rows * w[:, j:j + 1].double() + acc.double()).to(torch.float32)      # one rounding per fma
+        acc = torch.where(ok[:, None], upd, acc)
+    return acc.reshape(tuple(worldcoord.shape[:-1]) + (C,))
+
+
+def sp_trilinear_worldcoord_backward(out_grad, in_feature, corner_lut, worldcoord, ign_zero=False):
+    """feature_grad[idx_j][c] += g[c] * w_j (:323-329), accumulated here in float64."""
+    idx, w = sp_trilinear_corners(corner_lut.cpu(), worldcoord.cpu(), ign_zero)
+    C = in_feature.shape[1]
+    g = _f32(out_grad).reshape(-1, C)
+    grad = torch.zeros(in_feature.shape[0], C, dtype=torch.float64)
+    for j in range(8):
+        ok = idx[:, j] >= 0
+        grad.index_add_(0, idx[ok, j], (g[ok] * w[ok, j:j + 1]).double())
+    return grad.to(torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------
 # a3-a5, a8-a11: the whole per-pixel stage.  imaginaire/generators/scenedreamer.py:285-428
 # ----------------------------------------------------------------------------------------------
 def forward_perpix(P, voxel_id, depth2, raydirs, cam_ori_t, z, global_enc, voxel_dims, mc2reduced_lut,

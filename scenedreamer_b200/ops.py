@@ -140,12 +140,60 @@ def positional_encoding_backward(out_feature_grad, out_feature, ndegrees, dim, i
     return in_grad
 
 
-def sp_trilinear_worldcoord(*args, **kwargs):
-    raise RuntimeError('sp_trilinear_worldcoord is not part of the SceneDreamer render path '
-                       '(only gancraft_base.py:442 calls it) and is not implemented by scenedreamer_b200')
+def _sp_args(in_feature, corner_lut_t, in_worldcoord):
+    _check_input(in_feature, 'in_feature', torch.float32)           # CHECK_CONTIGUOUS(in_feature) in the reference
+    _check_cuda(corner_lut_t, 'in_corner_lut')
+    _check_cuda(in_worldcoord, 'in_worldcoord')
+    if in_feature.dim() != 2 or corner_lut_t.dim() != 3 or corner_lut_t.dtype != torch.int32:
+        raise RuntimeError('sp_trilinear_worldcoord: in_feature must be [M, C] float32 and in_corner_lut a 3-D int32 tensor')
+    if in_worldcoord.dtype != torch.float32 or in_worldcoord.shape[-1] != 3 or in_worldcoord.dim() > 8:
+        raise RuntimeError('sp_trilinear_worldcoord: in_worldcoord must be float32 [..., 3] with at most 8 dimensions')
+    dims = (ctypes.c_int64 * 3)(*corner_lut_t.shape)
+    strides = (ctypes.c_int64 * 3)(*corner_lut_t.stride())         # any strides, like the reference (:401-406)
+    wc = in_worldcoord.contiguous().reshape(-1, 3)
+    return dims, strides, wc
 
 
-sp_trilinear_worldcoord_backward = sp_trilinear_worldcoord
+def sp_trilinear_worldcoord(in_feature, corner_lut_t, in_worldcoord, ign_zero, channel_pos):
+    """-> out_feature float32 [..., C] (voxlib.cpp:15).  channel_pos: -1 keeps the channels last in memory, e.g. -3 lays
+    the result out channel-first ([.., C, H, W] in memory) while the returned view still has C last, like the
+    reference's transposed allocation (sp_trilinear_worldcoord_kernel.cu:410-424)."""
+    dims, strides, wc = _sp_args(in_feature, corner_lut_t, in_worldcoord)
+    E, C = wc.shape[0], in_feature.shape[1]
+    out = torch.empty(E, C, dtype=torch.float32, device=in_feature.device)
+    with torch.cuda.device(in_feature.device):
+        code = _lib.lib().sdb_sp_trilinear_worldcoord(_ptr(in_feature), int(in_feature.shape[0]), int(C), _ptr(corner_lut_t), dims,
+                                                      strides, _ptr(wc), int(E), int(bool(ign_zero)), _ptr(out),
+                                                      _stream(in_feature))
+    _lib.check(code, 'sp_trilinear_worldcoord')
+    out = out.reshape(tuple(in_worldcoord.shape[:-1]) + (C,))
+    nd = in_worldcoord.dim()
+    cp = channel_pos + nd if channel_pos < 0 else channel_pos
+    if not 0 <= cp < nd:
+        raise RuntimeError('sp_trilinear_worldcoord: channel_pos out of range')
+    if cp != nd - 1:
+        out = out.movedim(-1, cp).contiguous().movedim(cp, -1)
+    return out
+
+
+def sp_trilinear_worldcoord_backward(out_feature_grad, in_feature, corner_lut_t, in_worldcoord, ign_zero, need_coord_grad):
+    """-> [in_feature_grad float32 [M, C]] (voxlib.cpp:17); coordinates get no gradient (the reference asserts
+    need_coord_grad == false, sp_trilinear_worldcoord_kernel.cu:454)."""
+    if need_coord_grad:
+        raise RuntimeError('sp_trilinear_worldcoord_backward: need_coord_grad is not supported (nor by the reference)')
+    _check_cuda(out_feature_grad, 'out_feature_grad')
+    dims, strides, wc = _sp_args(in_feature, corner_lut_t, in_worldcoord)
+    E, C = wc.shape[0], in_feature.shape[1]
+    if out_feature_grad.dtype != torch.float32 or tuple(out_feature_grad.shape) != tuple(in_worldcoord.shape[:-1]) + (C,):
+        raise RuntimeError('sp_trilinear_worldcoord_backward: out_feature_grad must be float32 [..., C]')
+    g = out_feature_grad.contiguous().reshape(E, C)
+    grad = torch.empty_like(in_feature)
+    with torch.cuda.device(in_feature.device):
+        code = _lib.lib().sdb_sp_trilinear_worldcoord_backward(_ptr(g), int(in_feature.shape[0]), int(C), _ptr(corner_lut_t), dims,
+                                                               strides, _ptr(wc), int(E), int(bool(ign_zero)), _ptr(grad),
+                                                               _stream(in_feature))
+    _lib.check(code, 'sp_trilinear_worldcoord_backward')
+    return [grad]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -292,3 +292,46 @@ def test_tcgen05_mn_major_operands_from_activation_tiles(G):
     torch.cuda.synchronize()
     ref = x.bfloat16().float().t() @ y.bfloat16().float()
     assert float((c - ref).abs().max()) <= 1e-3
+
+
+def _sp_case(seed, ign_zero, strided_lut):
+    g = torch.Generator().manual_seed(seed)
+    X, Y, Z, M, C = 9, 12, 10, 300, 40
+    lut = torch.randint(0, M + (1 if ign_zero else 0), (X, Y, Z), generator=g, dtype=torch.int32)
+    if strided_lut:
+        lut = lut.permute(2, 0, 1).contiguous().permute(1, 2, 0)            # same values, non-contiguous strides
+    feat = torch.randn(M, C, generator=g)
+    wc = torch.rand(3, 50, 7, 3, generator=g) * torch.tensor([X + 2.0, Y + 2.0, Z + 2.0]) - 1.0      # some outside: clamped corners
+    wc[0, 0, 0] = float('nan')
+    wc[1, 3, 2, 1] = float('nan')
+    wc[2, 5, 1] = torch.tensor([4.0, 7.0, 3.0])                            # exactly on a lattice point
+    return lut, feat, wc
+
+
+@pytest.mark.parametrize('ign_zero,strided', [(False, False), (True, False), (True, True)])
+def test_sp_trilinear_worldcoord_vs_oracle_and_reference(ign_zero, strided):
+    """voxlib.sp_trilinear_worldcoord[_backward] (surface parity): forward bit-exact against the CPU oracle and the
+    reference's own CUDA extension, backward (atomics) to 1e-5."""
+    lut, feat, wc = _sp_case(3, ign_zero, strided)
+    out = ops.sp_trilinear_worldcoord(feat.to(DEV), lut.to(DEV) if not strided else lut.to(DEV), wc.to(DEV), ign_zero, -1)
+    ref = oracle.sp_trilinear_worldcoord(feat, lut, wc, ign_zero)
+    assert out.shape == wc.shape[:-1] + (feat.shape[1],)
+    assert torch.equal(out.cpu(), ref)
+    assert float(out[0, 0, 0].abs().max()) == 0.0                           # NaN coordinate: nothing selected
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    gf, = ops.sp_trilinear_worldcoord_backward(go.to(DEV), feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, False)
+    gref = oracle.sp_trilinear_worldcoord_backward(go, feat, lut, wc, ign_zero)
+    np.testing.assert_allclose(gf.cpu().numpy(), gref.numpy(), rtol=1e-5, atol=1e-5)
+    # channel-first memory layout, channels still the last LOGICAL dim (reference :410-424)
+    out_cf = ops.sp_trilinear_worldcoord(feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, -3)
+    assert torch.equal(out_cf, out) and out_cf.stride(-1) == wc.shape[1] * wc.shape[2]
+    rv = load_ref('ref_voxlib')
+    if rv is not None:
+        r_out = rv.sp_trilinear_worldcoord(feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, -1)
+        assert torch.equal(r_out, out)
+        r_cf = rv.sp_trilinear_worldcoord(feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, -3)
+        assert torch.equal(r_cf, out_cf) and r_cf.stride() == out_cf.stride()
+        r_g, = rv.sp_trilinear_worldcoord_backward(go.to(DEV), feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, False)
+        np.testing.assert_allclose(gf.cpu().numpy(), r_g.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        ops.sp_trilinear_worldcoord_backward(go.to(DEV), feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, True)
