@@ -13,12 +13,18 @@ tc_selftest_kernel(const float *__restrict__ a, const float *__restrict__ b, flo
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;
-    uint8_t *sB = smem + 128 * K * 2;
+    uint8_t *sB = smem + 130 * K * 2;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sB + N * K * 2);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
 
     const int KC = K / 8;
+    // variant 2 (layout of the convolution kernel, rendercnn.cu): A holds 130 rows per 8-column chunk -- a pixel row with a
+    // one-pixel halo on either side -- and the operand starts ONE ROW (16 B) into it: a tap of a 3x3 convolution is the same
+    // buffer read through a shifted start address.  Row r of `a` sits at buffer row r + 1; rows 0 and 129 are zero.
+    if (variant == 2)
+        for (int i = tid; i < 130 * KC; i += 128) *reinterpret_cast<uint4 *>(sA + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
     for (int i = tid; i < 128 * KC; i += 128) {
         const int r = i / KC, kc = i % KC;
         const float *src = a + (size_t)r * K + kc * 8;
@@ -27,7 +33,7 @@ tc_selftest_kernel(const float *__restrict__ a, const float *__restrict__ b, flo
         v.y = tc05::pack2<BF16>(src[2], src[3]);
         v.z = tc05::pack2<BF16>(src[4], src[5]);
         v.w = tc05::pack2<BF16>(src[6], src[7]);
-        *reinterpret_cast<uint4 *>(sA + tc05::chunk_off(128, r, kc)) = v;
+        *reinterpret_cast<uint4 *>(sA + (variant == 2 ? (uint32_t)(kc * 130 + r + 1) * 16u : tc05::chunk_off(128, r, kc))) = v;
     }
     for (int i = tid; i < N * KC; i += 128) {
         const int r = i / KC, kc = i % KC;
@@ -57,7 +63,10 @@ tc_selftest_kernel(const float *__restrict__ a, const float *__restrict__ b, flo
         const uint32_t lboA = 128 * 16, lboB = N * 16, sbo = 128;
         for (int kk = 0; kk < K / 16; kk++) {
             uint64_t da, db;
-            if (variant == 0) {
+            if (variant == 2) {
+                da = tc05::make_smem_desc(tc05::smem_u32(sA) + 16 + kk * 2 * 130 * 16, 130 * 16, sbo);
+                db = tc05::make_smem_desc(tc05::smem_u32(sB) + kk * 2 * lboB, lboB, sbo);
+            } else if (variant == 0) {
                 da = tc05::make_smem_desc(tc05::smem_u32(sA) + kk * 2 * lboA, lboA, sbo);
                 db = tc05::make_smem_desc(tc05::smem_u32(sB) + kk * 2 * lboB, lboB, sbo);
             } else {  // LBO / SBO meaning swapped (diagnostic)
@@ -91,7 +100,7 @@ extern "C" int sdb_tc_selftest(const float *d_a, const float *d_b, float *d_c, i
 {
     if (!d_a || !d_b || !d_c) return SDB_EINVAL;
     if (N < 16 || N > 256 || N % 16 || K < 16 || K > 256 || K % 16) return SDB_EINVAL;
-    const size_t smem = (size_t)128 * K * 2 + (size_t)N * K * 2 + 64;
+    const size_t smem = (size_t)130 * K * 2 + (size_t)N * K * 2 + 64;
     if (use_bf16) {
         SDB_CUDA(cudaFuncSetAttribute(tc_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_selftest_kernel<true><<<1, 128, smem, (cudaStream_t)stream>>>(d_a, d_b, d_c, N, K, variant);

@@ -335,3 +335,17 @@ def test_sp_trilinear_worldcoord_vs_oracle_and_reference(ign_zero, strided):
         np.testing.assert_allclose(gf.cpu().numpy(), r_g.cpu().numpy(), rtol=1e-5, atol=1e-5)
     with pytest.raises(RuntimeError):
         ops.sp_trilinear_worldcoord_backward(go.to(DEV), feat.to(DEV), lut.to(DEV), wc.to(DEV), ign_zero, True)
+
+
+def test_tc_operand_with_shifted_start_row():
+    """tcgen05 K-major operand read through a start address shifted by one 16-byte row inside a 130-row (haloed) buffer:
+    what a 3x3 convolution tap of the RenderCNN kernel is.  Must equal the plain operand bit for bit."""
+    g = torch.Generator().manual_seed(11)
+    for N, K in ((256, 32), (64, 64)):
+        a = torch.randn(128, K, generator=g).to(DEV)
+        b = torch.randn(N, K, generator=g).to(DEV)
+        c0 = ops.tc_selftest(a, b, variant=0)
+        c2 = ops.tc_selftest(a, b, variant=2)
+        torch.cuda.synchronize()
+        assert torch.equal(c0, c2)
+        assert float((c0 - a.half().float() @ b.half().float().t()).abs().max()) <= 1e-3
