@@ -299,6 +299,30 @@ int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void *d_record, 
                      const void *d_bwd_pack, float *d_grad_w1ext, float *d_grad_wh, float *d_grad_wout,
                      void *d_workspace, void *stream);
 
+/* --------------------------------------------------------------------------------------------
+ * f1. RenderCNN + tanh on the tensor cores: per-pixel feature map -> image.
+ * Replaces Base3DGenerator._forward_global = RenderCNN.forward + tanh
+ *   (imaginaire/generators/gancraft_base.py:172-225, :588-603) for the WHOLE padded frame at once
+ *   (the reference's tile loop, scenedreamer.py:600-628, computes the same function tile by tile).
+ *   pack: sdb_cnn_pack() from the reference's `denoiser.*` tensors (device fp32, their shapes):
+ *         conv1 [256,64,1,1]+[256]; conv2a, conv3a [256,256,3,3]+[256]; conv2b, conv3b [256,256,3,3];
+ *         conv4a, conv4b [256,256,1,1]+[256]; conv4 [3,256,1,1]+[3];
+ *   d_mod [4][256] = fc_z_cond(z) for ONE style code (the four `adapt` chunks, gancraft_base.py:208-209);
+ *   d_net_out [H][W][64] fp32 (the fused kernel's net_out) -> d_rgb [3][H][W] = tanh(raw), d_rgb_raw
+ *   [3][H][W] or NULL;  precision 2 = fp16 hi/lo split x3 (fp32-grade, parity), 0 = one fp16 pass;
+ *   d_workspace: sdb_cnn_workspace_bytes() bytes; workspace_ready = 0 on the first call for a given
+ *   (workspace, H, W, precision) -- the call then clears the zero borders -- and 1 afterwards.
+ * ------------------------------------------------------------------------------------------ */
+int64_t sdb_cnn_pack_bytes(int32_t precision);
+int sdb_cnn_pack(const float *d_w1, const float *d_b1, const float *d_w2a, const float *d_b2a, const float *d_w2b,
+                 const float *d_w3a, const float *d_b3a, const float *d_w3b, const float *d_w4a, const float *d_b4a,
+                 const float *d_w4b, const float *d_b4b, const float *d_w4, const float *d_b4, int32_t precision,
+                 void *d_pack, void *stream);
+int64_t sdb_cnn_workspace_bytes(int32_t H, int32_t W, int32_t precision);
+int sdb_cnn_forward(const float *d_net_out, int32_t H, int32_t W, const void *d_pack, const float *d_mod,
+                    int32_t precision, float *d_rgb, float *d_rgb_raw, void *d_workspace, int32_t workspace_ready,
+                    void *stream);
+
 /* Kernels this library has launched in this process so far (every launch is counted; memsets and
  * library GEMMs are not).  bench.py reads it around its timed region for `gpu_launches`.          */
 int64_t sdb_launch_count(void);

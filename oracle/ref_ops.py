@@ -398,6 +398,52 @@ def make_params(seed=0, stress=False, style_dim=128, interm=256, hidden=256, fea
 
 
 # ----------------------------------------------------------------------------------------------
+# f1: RenderCNN + tanh.  imaginaire/generators/gancraft_base.py:172-225 (RenderCNN), :588-603 (_forward_global)
+# ----------------------------------------------------------------------------------------------
+def make_cnn_params(seed=0, in_ch=64, hidden=256, style=256, gain=1.4):
+    """Synthetic `denoiser.*` weights with the reference's state-dict names / shapes; gains keep activations O(1)."""
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+
+    def conv(name, o, i, k, bias=True):
+        P['denoiser.%s.weight' % name] = torch.randn(o, i, k, k, generator=g) * (gain / np.sqrt(i * k * k))
+        if bias:
+            P['denoiser.%s.bias' % name] = torch.randn(o, generator=g) * 0.1
+    conv('conv1', hidden, in_ch, 1)
+    conv('conv2a', hidden, hidden, 3)
+    conv('conv2b', hidden, hidden, 3, bias=False)
+    conv('conv3a', hidden, hidden, 3)
+    conv('conv3b', hidden, hidden, 3, bias=False)
+    conv('conv4a', hidden, hidden, 1)
+    conv('conv4b', hidden, hidden, 1)
+    conv('conv4', 3, hidden, 1)
+    P['denoiser.conv4.weight'] *= 0.2                          # raw image O(1): tanh not saturated
+    P['denoiser.fc_z_cond.weight'] = torch.randn(4 * hidden, style, generator=g) * (0.5 / np.sqrt(style))
+    P['denoiser.fc_z_cond.bias'] = torch.randn(4 * hidden, generator=g) * 0.1
+    return P
+
+
+def render_cnn(net_out, z, P, prefix='denoiser.', dtype=torch.float32):
+    """net_out [N,H,W,C] (as _forward_perpix returns it), z [N,256] -> (tanh image, raw image) [N,3,H,W].
+    Restates RenderCNN.forward (gancraft_base.py:201-225) + the permute / tanh of _forward_global (:598-601)."""
+    import torch.nn.functional as F
+    W = lambda n: P[prefix + n].to(net_out.device, dtype)
+    x = net_out.to(dtype).permute(0, 3, 1, 2).contiguous()
+    adapt = torch.chunk(F.linear(z.to(net_out.device, dtype), W('fc_z_cond.weight'), W('fc_z_cond.bias')), 4, dim=-1)
+    act = lambda t: F.leaky_relu(t, 0.2)
+    mod = lambda t, w, b: t * (w[..., None, None] + 1) + b[..., None, None]
+    y = act(F.conv2d(x, W('conv1.weight'), W('conv1.bias')))
+    y = y + F.conv2d(act(F.conv2d(y, W('conv2a.weight'), W('conv2a.bias'), padding=1)), W('conv2b.weight'), None, padding=1)
+    y = act(mod(y, adapt[0], adapt[1]))
+    y = y + F.conv2d(act(F.conv2d(y, W('conv3a.weight'), W('conv3a.bias'), padding=1)), W('conv3b.weight'), None, padding=1)
+    y = act(mod(y, adapt[2], adapt[3]))
+    y = y + F.conv2d(act(F.conv2d(y, W('conv4a.weight'), W('conv4a.bias'))), W('conv4b.weight'), W('conv4b.bias'))
+    y = act(y)
+    raw = F.conv2d(y, W('conv4.weight'), W('conv4.bias'))
+    return torch.tanh(raw), raw
+
+
+# ----------------------------------------------------------------------------------------------
 # voxlib.sp_trilinear_worldcoord (surface parity; never reached by SceneDreamer).
 # imaginaire/model_utils/gancraft/voxlib/sp_trilinear_worldcoord_kernel.cu:48-198 (forward), :205-338 (backward)
 # ----------------------------------------------------------------------------------------------

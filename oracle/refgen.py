@@ -106,6 +106,7 @@ def build_generator(scene_size=1024, device='cuda', weights_seed=0, stress=True,
                 p.copy_(torch.randn(p.shape, generator=g) * (1.4 / np.sqrt(fan_in)))
             elif name.endswith('bias'):
                 p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+        gen.denoiser.conv4.weight.mul_(0.2)                    # raw image O(1): tanh not saturated
     gen = gen.to(device).eval()
     for p in gen.parameters():
         p.requires_grad = False

@@ -70,45 +70,53 @@ wgrad_kernel(const WgParams prm)
     const uint32_t a_bytes = (uint32_t)jb.a_chunks * kChunkBytes, z_bytes = (uint32_t)jb.z_chunks * kChunkBytes;
 
     if (my_items > 0) {
-        if (warp == 0 && lane == 0) {
-            // ---- loader: one bulk copy per operand and item ----
-            for (long long n = 0; n < my_items; n++) {
-                const int s = (int)(n % kWgStages);
-                if (n >= kWgStages) tc05::mbar_wait_backoff(&bars[kWgStages + s], (uint32_t)((n / kWgStages - 1) & 1), 64);
-                const long long item = split + n * jb.nsplit;
-                uint8_t *sA = smem + s * kWgStageBytes, *sZ = sA + kWgABytes;
-                tc05::mbar_arrive_expect_tx(&bars[s], a_bytes + z_bytes);
-                tc05::bulk_g2s(sA, reinterpret_cast<const uint8_t *>(jb.A) + (size_t)item * a_bytes, a_bytes, &bars[s]);
-                tc05::bulk_g2s(sZ, reinterpret_cast<const uint8_t *>(jb.Z) + ((size_t)item * jb.z_chunks_total + jb.z_chunk0) * kChunkBytes,
-                               z_bytes, &bars[s]);
-            }
-        } else if (warp == 1 && lane == 0) {
-            // ---- MMA issuer: D[128 x N] += Zpart^T [128 x 128 samples] * A [128 samples x N], 16 samples per instruction ----
-            const int N = jb.a_chunks * 8;
-            const int n_main = N > 256 ? 256 : N;                   // k_in = 272 = 256 + 16: two instructions per 16 samples
-            const uint32_t idesc_main = tc05::make_idesc(128, n_main, true) | (1u << 15) | (1u << 16);     // A and B MN-major
-            const uint32_t idesc_tail = tc05::make_idesc(128, N - n_main > 0 ? N - n_main : 16, true) | (1u << 15) | (1u << 16);
-            for (long long n = 0; n < my_items; n++) {
-                const int s = (int)(n % kWgStages);
-                tc05::mbar_wait(&bars[s], (uint32_t)((n / kWgStages) & 1));
-                tc05::fence_after_thread_sync();
-                const uint32_t sA = tc05::smem_u32(smem + s * kWgStageBytes), sZ = sA + kWgABytes;
-#pragma unroll 1
-                for (int kk = 0; kk < kRows / 16; kk++) {
-                    const uint32_t acc = (n > 0 || kk > 0) ? 1u : 0u;
-                    const uint64_t dz = tc05::make_smem_desc(sZ + kk * 256, 128, kChunkBytes);
-                    tc05::mma_f16_ss(tmem, dz, tc05::make_smem_desc(sA + kk * 256, 128, kChunkBytes), idesc_main, acc);
-                    if (N > 256)
-                        tc05::mma_f16_ss(tmem + 256, dz, tc05::make_smem_desc(sA + 32 * kChunkBytes + kk * 256, 128, kChunkBytes),
-                                         idesc_tail, acc);
+        // role lanes run their loops inside `if (lane == 0)`; the other 31 lanes of those warps park at __syncwarp (a hardware
+        // barrier), they do not spin next to the working lane
+        if (warp == 0) {
+            if (lane == 0) {
+                // ---- loader: one bulk copy per operand and item ----
+                for (long long n = 0; n < my_items; n++) {
+                    const int s = (int)(n % kWgStages);
+                    if (n >= kWgStages) tc05::mbar_wait_backoff(&bars[kWgStages + s], (uint32_t)((n / kWgStages - 1) & 1), 32);
+                    const long long item = split + n * jb.nsplit;
+                    uint8_t *sA = smem + s * kWgStageBytes, *sZ = sA + kWgABytes;
+                    tc05::mbar_arrive_expect_tx(&bars[s], a_bytes + z_bytes);
+                    tc05::bulk_g2s(sA, reinterpret_cast<const uint8_t *>(jb.A) + (size_t)item * a_bytes, a_bytes, &bars[s]);
+                    tc05::bulk_g2s(sZ, reinterpret_cast<const uint8_t *>(jb.Z) + ((size_t)item * jb.z_chunks_total + jb.z_chunk0) * kChunkBytes,
+                                   z_bytes, &bars[s]);
                 }
-                tc05::mma_commit(&bars[kWgStages + s]);            // the stage is free once these MMAs have read it
             }
-            tc05::mma_commit(&bars[2 * kWgStages]);
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                // ---- MMA issuer: D[128 x N] += Zpart^T [128 x 128 samples] * A [128 samples x N], 16 samples per instruction ----
+                const int N = jb.a_chunks * 8;
+                const int n_main = N > 256 ? 256 : N;                   // k_in = 272 = 256 + 16: two instructions per 16 samples
+                const uint32_t idesc_main = tc05::make_idesc(128, n_main, true) | (1u << 15) | (1u << 16);     // A and B MN-major
+                const uint32_t idesc_tail = tc05::make_idesc(128, N - n_main > 0 ? N - n_main : 16, true) | (1u << 15) | (1u << 16);
+                for (long long n = 0; n < my_items; n++) {
+                    const int s = (int)(n % kWgStages);
+                    tc05::mbar_wait(&bars[s], (uint32_t)((n / kWgStages) & 1));
+                    tc05::fence_after_thread_sync();
+                    const uint32_t sA = tc05::smem_u32(smem + s * kWgStageBytes), sZ = sA + kWgABytes;
+#pragma unroll 1
+                    for (int kk = 0; kk < kRows / 16; kk++) {
+                        const uint32_t acc = (n > 0 || kk > 0) ? 1u : 0u;
+                        const uint64_t dz = tc05::make_smem_desc(sZ + kk * 256, 128, kChunkBytes);
+                        tc05::mma_f16_ss(tmem, dz, tc05::make_smem_desc(sA + kk * 256, 128, kChunkBytes), idesc_main, acc);
+                        if (N > 256)
+                            tc05::mma_f16_ss(tmem + 256, dz, tc05::make_smem_desc(sA + 32 * kChunkBytes + kk * 256, 128, kChunkBytes),
+                                             idesc_tail, acc);
+                    }
+                    tc05::mma_commit(&bars[kWgStages + s]);            // the stage is free once these MMAs have read it
+                }
+                tc05::mma_commit(&bars[2 * kWgStages]);
+            }
+            __syncwarp();
         }
         // ---- accumulators -> gradient (thread = output row) ----
         tc05::mbar_wait_backoff(&bars[2 * kWgStages], 0, 128);
-        __syncwarp();                                               // lanes 0 of warps 0 / 1 rejoin their warps
+        __syncwarp();
         tc05::fence_after_thread_sync();
         const int N = jb.a_chunks * 8;
         const int row = warp * 32 + lane;

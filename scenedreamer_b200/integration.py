@@ -36,7 +36,7 @@ import sys
 
 import torch
 
-from . import render
+from . import render, rendercnn
 
 TARGET_MODULE = 'imaginaire.generators.scenedreamer'
 PUBLIC_ENTRIES = ('forward', 'inference_givenstyle', 'inference_givenstyle_depth')
@@ -76,8 +76,10 @@ class _FusedState:
         self.precision = precision
         self.epoch = 0
         self.renderer, self.renderer_key = None, None
+        self.cnn, self.cnn_key, self.cnn_precision = None, None, rendercnn.PRECISION_FP16X3
         self.frame = _FrameCache()
-        self.stats = {'fused_calls': 0, 'frame_launches': 0, 'tile_hits': 0, 'train_calls': 0, 'reference_calls': 0}
+        self.stats = {'fused_calls': 0, 'frame_launches': 0, 'tile_hits': 0, 'train_calls': 0, 'reference_calls': 0,
+                      'cnn_frame_launches': 0, 'cnn_tile_hits': 0, 'cnn_calls': 0, 'cnn_reference_calls': 0}
 
     @property
     def lut(self):
@@ -92,6 +94,20 @@ class _FusedState:
         self.frame.clear()
         if self.renderer is not None:
             self.renderer.invalidate()
+        self.cnn, self.cnn_key = None, None
+
+    def get_cnn(self, gen):
+        """Tensor-core RenderCNN engine over the generator's own `denoiser.*` tensors, or None if the module is not
+        SceneDreamer's RenderCNN (64 -> 256 -> 3)."""
+        den = getattr(gen, 'denoiser', None)
+        if den is None:
+            return None
+        P = {'denoiser.' + k: v for k, v in den.state_dict().items()}
+        key = (self.epoch, tuple((k, v.data_ptr(), v._version) for k, v in P.items()))
+        if self.cnn_key != key:
+            self.cnn = rendercnn.RenderCNNEngine(P, self.cnn_precision) if rendercnn.supported(P) else None
+            self.cnn_key = key
+        return self.cnn
 
     def get_renderer(self, gen):
         mods = (('render_net', gen.render_net), ('sky_net', gen.sky_net), ('hash_encoder', gen.hash_encoder))
@@ -253,13 +269,13 @@ def fused_forward_perpix(self, blk_feats, voxel_id, depth2, raydirs, cam_ori_t, 
         return _tuple12(out, sky_mask, sky_only_mask)
     st.stats['fused_calls'] += 1
     r = st.get_renderer(self)
-    sky_avg = getattr(self, 'sky_avg', None)
-    if sky_avg is not None:
-        sky_avg = sky_avg.reshape(-1, 64)
+    sky_attr = getattr(self, 'sky_avg', None)                  # set once per frame by inference_givenstyle (scenedreamer.py:592-598)
+    sky_avg = sky_attr.reshape(-1, 64) if sky_attr is not None else None
     win = _frame_window(voxel_id, depth2, raydirs) if (N == 1 and uniforms is None) else None
     if win is not None:
         bases, h0, w0, h, w = win
-        keyt = list(bases) + [z, global_enc] + ([sky_avg] if sky_avg is not None else [])
+        # keyed on the tensor OBJECTS the tile loop hands over unchanged from tile to tile (a reshape would be a new object)
+        keyt = list(bases) + [z, global_enc] + ([sky_attr] if sky_attr is not None else [])
         full, key = st.frame.lookup(keyt, st.epoch, (self.num_samples, float(self.sample_depth), float(self.dists_scale)))
         if full is None:
             st.stats['frame_launches'] += 1
@@ -273,6 +289,44 @@ def fused_forward_perpix(self, blk_feats, voxel_id, depth2, raydirs, cam_ori_t, 
     out = r.forward(voxel_id.contiguous(), depth2.contiguous(), raydirs.contiguous(), cam_ori_t, z, global_enc,
                     uniforms=uniforms, sky_avg=sky_avg, want_samples=True, **kw)
     return _tuple12(out, sky_mask, sky_only_mask)
+
+
+def fused_forward_global(self, net_out, z):
+    """Replacement body of Base3DGenerator._forward_global (gancraft_base.py:588-603): RenderCNN + tanh on the tensor
+    cores.  When `net_out` is a tile of the frame the fused per-pixel launch produced (the unmodified tile loop of
+    inference_givenstyle), the CNN runs ONCE on the whole padded frame and every tile gets its window: the receptive
+    radius is 4 px, the loop crops pad/2 = 15 px from every tile side.  Calls that need gradients
+    through the CNN (gen_update) keep the reference's cuDNN composition."""
+    st = _state(self)
+    reference = type(self)._sdb200_reference_forward_global
+    needs_grad = torch.is_grad_enabled() and (net_out.requires_grad or (z is not None and z.requires_grad) or
+                                              any(q.requires_grad for q in self.denoiser.parameters()))
+    eng = None
+    if enabled() and os.environ.get('SDB200_CNN', '1') != '0' and not needs_grad and z is not None and net_out.is_cuda and \
+            net_out.dim() == 4 and net_out.shape[-1] == 64 and net_out.dtype == torch.float32:
+        eng = st.get_cnn(self)
+    if eng is None:
+        st.stats['cnn_reference_calls'] += 1
+        return reference(self, net_out, z)
+    full = st.frame.out
+    if full is not None and net_out.shape[0] == 1 and z.shape[0] == 1:
+        base = full['net_out']
+        if net_out._base is base and net_out.stride() == base.stride():
+            HB, WB = base.shape[1], base.shape[2]
+            off = net_out.storage_offset() - base.storage_offset()
+            h0, rem = divmod(off, WB * 64)
+            w0, rem = divmod(rem, 64)
+            h, w = net_out.shape[1], net_out.shape[2]
+            if rem == 0 and off >= 0 and h0 + h <= HB and w0 + w <= WB:
+                if full.get('rgb_z') is not z:
+                    st.stats['cnn_frame_launches'] += 1
+                    full['rgb'], full['rgb_raw'] = eng.forward(base, z)
+                    full['rgb_z'] = z
+                else:
+                    st.stats['cnn_tile_hits'] += 1
+                return full['rgb'][:, :, h0:h0 + h, w0:w0 + w], full['rgb_raw'][:, :, h0:h0 + h, w0:w0 + w]
+    st.stats['cnn_calls'] += 1
+    return eng.forward(net_out, z)
 
 
 def _epoch_entry(name, fn):
@@ -296,6 +350,9 @@ def install(generator_cls, precision=DEFAULT_PRECISION):
     generator_cls._sdb200_reference_forward_perpix = generator_cls._forward_perpix
     generator_cls._sdb200_precision = precision
     generator_cls._forward_perpix = fused_forward_perpix
+    if hasattr(generator_cls, '_forward_global') and hasattr(generator_cls, '_forward_perpix_sub'):
+        generator_cls._sdb200_reference_forward_global = generator_cls._forward_global
+        generator_cls._forward_global = fused_forward_global
     for name in PUBLIC_ENTRIES:
         fn = generator_cls.__dict__.get(name)
         if fn is not None:
@@ -309,6 +366,11 @@ def uninstall(generator_cls):
         return
     generator_cls._forward_perpix = ref
     del generator_cls._sdb200_reference_forward_perpix
+    if '_sdb200_reference_forward_global' in generator_cls.__dict__:
+        g = generator_cls._sdb200_reference_forward_global
+        if '_forward_global' in generator_cls.__dict__:
+            del generator_cls._forward_global                  # the method is inherited from Base3DGenerator
+        del generator_cls._sdb200_reference_forward_global
     for name in PUBLIC_ENTRIES:
         fn = generator_cls.__dict__.get(name)
         if fn is not None and hasattr(fn, '_sdb200_wrapped'):

@@ -59,6 +59,7 @@ def test_reference_generator_zero_edit_full_frame(fused_generator, tmp_path):
     st = gen._sdb200.stats
     print('hook stats', st)
     assert st['frame_launches'] == 1 and st['tile_hits'] == 39 and st['reference_calls'] == 0 and st['train_calls'] == 0
+    assert st['cnn_frame_launches'] == 1 and st['cnn_tile_hits'] == 39 and st['cnn_reference_calls'] == 0       # RenderCNN: once per frame too
     f = r['frames'][0]
     net, dep, rgb = f['net_out'].cpu().numpy(), f['depth'].cpu().numpy(), f['rgb'].cpu().numpy()
     assert net.shape == (540, 960, 64) and ref['net_out'].shape == net.shape
@@ -76,8 +77,8 @@ def test_reference_generator_zero_edit_full_frame(fused_generator, tmp_path):
           % (r['perpix_ms'][0], r['cnn_ms'][0], float(ref['perpix_ms'][0]), float(ref['cnn_ms'][0])))
     assert 0.3 < live < 0.95
     assert e_net <= 1e-3, e_net
-    # RenderCNN + tanh on both sides is the reference's own cuDNN path (TF32 convolutions by default): identical code on
-    # inputs that differ by e_net; its Lipschitz gain on this weight set is O(10)
+    # RenderCNN + tanh: ours is fp32-grade (fp16x3 on the tensor cores, tests/test_gpu_cnn.py pins it to 1e-4 of float64); the
+    # reference arm runs cuDNN with its default TF32 convolutions, whose own distance to fp32 is of the order of 1e-3..1e-2
     assert e_rgb <= 2e-2, e_rgb
     # depth: north_star asks 1e-3 max-abs.  The float64 referee (reference's fp32 features -> LightningMLP, volume rendering and
     # the sum in float64) is the arbiter: the fused result must be within 1e-3 of it, or no further from it than the
@@ -86,7 +87,7 @@ def test_reference_generator_zero_edit_full_frame(fused_generator, tmp_path):
     # a second frame of the same call re-uses packs / table (same epoch), a new call starts a new epoch
     ep = gen._sdb200.epoch
     refgen.run_inference(gen, style, str(tmp_path / 'fused_out'), frames=2, keep=False)
-    assert gen._sdb200.epoch == ep + 1 and gen._sdb200.stats['frame_launches'] == 3
+    assert gen._sdb200.epoch == ep + 1 and gen._sdb200.stats['frame_launches'] == 3 and gen._sdb200.stats['cnn_frame_launches'] == 3
 
 
 def test_two_styles_through_one_generator(fused_generator, tmp_path):
