@@ -107,6 +107,7 @@ def build_workload(device, seed=3407, scene=SCENE, pattern=0):
     z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
     genc = torch.tanh(torch.randn(1, 2, generator=g))
     lut = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_python_ops.npz'))['mc2reduced_lut']
+    P.update(oracle.make_cnn_params(seed=1))                       # denoiser.* (RenderCNN), reference state-dict names
     return world, poses, P, z, genc, lut
 
 
@@ -125,8 +126,9 @@ def cpu_frame_sample(world, pose, P, z, genc, lut, crop=64):
     offsets, pls = oracle.grid_offsets()
     t0 = time.perf_counter()
     vid, dep, rd = oracle.ray_voxel_intersection_perspective(world.voxel_t, o, d, u, f, cc, [crop, crop], 6)
-    oracle.forward_perpix(P, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0), z, genc,
-                          list(world.voxel_t.shape), torch.from_numpy(lut), offsets, pls, num_samples=SPP)
+    r = oracle.forward_perpix(P, vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0), z, genc,
+                              list(world.voxel_t.shape), torch.from_numpy(lut), offsets, pls, num_samples=SPP)
+    oracle.render_cnn(r['net_out'], z, P)                          # RenderCNN + tanh on the same crop (gancraft_base.py:588-603)
     return time.perf_counter() - t0, crop * crop * SPP
 
 
@@ -155,8 +157,8 @@ def run_reference_arm(args):
         'config': {'workload': 'C2: single 540x960 frame, scene_size=1024, num_samples=24, cam_mode=0 (CPU: %dx%d-ray '
                                'centre crop per step)' % (crop, crop)},
         'cpu_baseline': {'value': val, 'unit': 'Msamples/s', 'cores': CPU_THREADS, 'host_cpus': os.cpu_count(), 'kind': 'port',
-                         'sample': '%dx%d-ray centre crop of the C2 frame per step (oracle/: C DDA + hash encode with '
-                                   'OpenMP, torch fp32 MLP), %d steps' % (crop, crop, args.steps),
+                         'sample': '%dx%d-ray centre crop of the C2 frame per step: raycast + per-pixel path + RenderCNN (oracle/: C DDA + '
+                                   'hash encode with OpenMP, torch fp32 MLP / conv2d), %d steps' % (crop, crop, args.steps),
                          'omp_threads': oracle.num_threads()},
         'e2e': {'value': val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -215,6 +217,15 @@ class FrameRenderer:
         self.r = render.FusedPerPixelRenderer(self.P, world.voxel_t.shape, render.reduced_label_lut(lut), pls,
                                               precision=precision, preblend=True)
         self.z, self.genc = z.to(device), genc.to(device)
+        from scenedreamer_b200 import rendercnn
+        self.cnn = rendercnn.RenderCNNEngine(self.P)
+
+    def image(self, out, pad):
+        """f1: per-pixel features of the padded frame -> RGB [3, H - pad, W - pad] (RenderCNN + tanh on the whole frame, then
+        the crop of pad/2 the reference applies to every tile, scenedreamer.py:621-622)."""
+        rgb, _ = self.cnn.forward(out['net_out'], self.z, want_raw=False)
+        c = pad // 2
+        return rgb[0, :, c:rgb.shape[2] - c, c:rgb.shape[3] - c] if c else rgb[0]
 
     def set_early_stop(self, T):
         self.r.early_stop = T
@@ -279,7 +290,10 @@ def run_gpu_arm(args):
         dist.all_gather_into_tensor(allp, part.reshape(1, 65))
         return (allp[:, :64].sum(0) / allp[:, 64].sum()).reshape(1, 64)
 
-    def one_step(k, ev=None, kev=None, cev=None, want_host=True):
+    host_rgb = torch.empty(3, out_hw[0], out_hw[1], dtype=torch.float32).pin_memory()
+    e2e_image = not strong                    # the user-facing result of a frame is the IMAGE: RenderCNN + tanh (f1) on top of the path
+
+    def one_step(k, ev=None, kev=None, cev=None, want_host=True, to_image=False):
         idx = (k if strong else (k * world_size + rank)) % len(cams)
         cam = cams[idx]
         if ev is not None:
@@ -287,25 +301,31 @@ def run_gpu_arm(args):
         pose = pose_pinned[idx]                                      # this step's inputs, pinned host memory, passed by value
         out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev, rows=rows,
                        sky_sum_hook=sky_hook if (strong and world_size > 1) else None)
-        maps = torch.stack([out['depth'][0], out['total_weight'][0]])
+        if to_image:
+            maps = fr.image(out, PAD)                                # [3, 540, 960] RGB
+        else:
+            maps = torch.stack([out['depth'][0], out['total_weight'][0]])
         if strong and band_h < band_cap:                             # equal-size bands for the gather (the last band may be shorter)
             maps = torch.nn.functional.pad(maps, (0, 0, 0, band_cap - band_h))
         if world_size > 1:
             if cev is not None:
                 cev[0].record()
-            allm = sharding.gather_frames(maps.unsqueeze(0))         # THE collective of the path: finished maps of every rank
+            allm = sharding.gather_frames(maps.unsqueeze(0))         # THE collective of the path: finished frames of every rank
             if cev is not None:
                 cev[1].record()
             if strong:                                               # bands -> one frame [2, rows, W]
                 maps = allm.permute(1, 0, 2, 3).reshape(2, -1, res[1])
-        if want_host:
-            host_out[:, :maps.shape[1]].copy_(maps, non_blocking=True)   # D2H of the step's result
+        if want_host:                                                # D2H of the step's result
+            if to_image:
+                host_rgb.copy_(maps, non_blocking=True)
+            else:
+                host_out[:, :maps.shape[1]].copy_(maps, non_blocking=True)
         if ev is not None:
             ev[1].record()
         return out
 
     for w in range(max(args.warmup, 3)):
-        one_step(w)
+        one_step(w, to_image=e2e_image)
         flush.zero_()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
@@ -321,7 +341,7 @@ def run_gpu_arm(args):
     launches0 = int(L.sdb_launch_count())
     t_begin = time.perf_counter()
     for k in range(args.steps):
-        one_step(k, evs[k], kevs[k], cevs[k])
+        one_step(k, evs[k], kevs[k], cevs[k], to_image=e2e_image)
         torch.cuda.synchronize()                                     # the caller READS the step's result on the host
         flush.zero_()                                                # L2 flush between timed iterations
     torch.cuda.synchronize()
@@ -383,6 +403,18 @@ def run_gpu_arm(args):
         steps_exec = float(np.mean([int(w[1]) for w in wss]))         # tile-steps executed (after early termination)
         mma_eq = {'fp16': (9 + 5 * 17 + 17 * 0.25), 'bf16x3': (27 + 5 * 50 + 50 * 0.25), 'fp16x3': (27 + 5 * 50 + 50 * 0.25)}[args.precision]
         exec_tflops = steps_exec * mma_eq * (2.0 * 128 * 256 * 16) / kern_s / 1e12
+        cnn_ms = None
+        if e2e_image:
+            o_ = fr.frame(cams[0])
+            ts_ = []
+            for _ in range(5):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                fr.image(o_, PAD)
+                b_.record()
+                torch.cuda.synchronize()
+                ts_.append(a_.elapsed_time(b_))
+            cnn_ms = float(np.median(ts_))
         band_frac = band_h / float(res[0])
         alg_tflops = samples_per_frame * band_frac * FLOP_PER_SAMPLE / kern_s / 1e12
         traffic = None
@@ -424,9 +456,13 @@ def run_gpu_arm(args):
                                              % render.EARLY_STOP_T),
                        'host_affinity': 'each rank pinned to the CPUs of its GPU (NVML affinity), %s CPUs for rank 0' % pinned_cpus},
             'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
-                    'd2h_bytes_per_step': int(host_out.numel() * 4), 'ms_per_step': tot_ms / args.steps,
-                    'note': 'per step: pose from pinned host memory (by value in the launch arguments) -> DDA -> sky -> fused render -> '
-                            'depth+opacity maps to pinned host, host waits for them'},
+                    'd2h_bytes_per_step': int((host_rgb if e2e_image else host_out).numel() * 4), 'ms_per_step': tot_ms / args.steps,
+                    'result': 'RGB image [3,%d,%d] fp32' % out_hw if e2e_image else 'depth + opacity maps',
+                    'note': ('per step: pose from pinned host memory (by value in the launch arguments) -> DDA -> sky -> fused render -> '
+                             'RenderCNN + tanh on the whole padded frame (tcgen05 implicit GEMM, fp16x3) -> crop -> RGB to pinned host, host '
+                             'waits for it.  `value` is the per-pixel path alone (SURVEY 8(d): a1-a12), e2e goes on to the image, so the two '
+                             'differ by the RenderCNN time (`rendercnn_ms`)') if e2e_image else
+                            'per step: pose (by value) -> DDA -> sky -> fused render of this rank\'s row band -> band maps gathered -> host'},
             'gpu_launches': launches,
             'gpu_launches_note': 'counted by the library (sdb_launch_count) over the timed region on rank 0: per step dda_perspective, '
                                  'mlp_kernel<sky>, sky_mean, set_cam, prepass, mlp_kernel<render> (all ours)',
@@ -448,7 +484,8 @@ def run_gpu_arm(args):
             'cpu_baseline': cpu, 'clocks': clocks, 'wall_s': t_wall,
             'per_rank_ms': {'columns': ['e2e_step', 'dda_sky', 'fused_kernel_window', 'collective_incl_wait', 'e2e_step_max', 'cpus_in_affinity'],
                             'rows': table},
-            'collective': {'op': 'all_gather_into_tensor(depth+opacity maps)', 'bytes_per_rank': int(2 * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
+            'rendercnn_ms': cnn_ms,
+            'collective': {'op': 'all_gather_into_tensor(%s)' % ('RGB frames in the e2e loop, depth+opacity maps in the device-only loops' if e2e_image else 'row bands of depth+opacity maps'), 'bytes_per_rank': int(2 * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
                            'ms_per_step_incl_wait_for_slowest_rank': float(np.mean(coll_ms))} if world_size > 1 else None,
         }
         line.update(extras)

@@ -53,7 +53,8 @@ def test_c2_frame_window_parity_and_properties(golden_ops):
     derr = float((out['depth'][0][sl].cpu() - ref['depth_map'][0].squeeze(-1)).abs().max())
     print('C2 window (%d:%d, %d:%d) max err net_out %.3e depth %.3e, live fraction %.2f' % (y0, y0 + 48, x0, x0 + 64, err, derr, live))
     # depth = sum_s w*t with t of several hundred voxels in this scene: ulp(512) = 6e-5, so 1e-3 ABSOLUTE is at
-    # the fp32 rounding level of the 24-term sum; the bar is 1e-3 absolute or 1e-5 relative, whichever is larger
+    # the fp32 rounding level (the reference's own fp32 evaluation is 1.2e-3 away from a float64 referee on this frame:
+    # tests/test_gpu_generator.py); the bar is 1e-3 absolute or 1e-5 relative, whichever is larger
     dmax = float(ref['depth_map'].abs().max())
     assert err <= 1e-3 and derr <= max(1e-3, 1e-5 * dmax), (err, derr, dmax)
     wl = float((vid[sl][..., 0, 0] != 0).float().mean())
