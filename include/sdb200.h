@@ -323,6 +323,17 @@ int sdb_cnn_forward(const float *d_net_out, int32_t H, int32_t W, const void *d_
                     int32_t precision, float *d_rgb, float *d_rgb_raw, void *d_workspace, int32_t workspace_ready,
                     void *stream);
 
+/* --------------------------------------------------------------------------------------------
+ * f2. The Adam step of the hash table in one pass over (param, grad, exp_avg,
+ * exp_avg_sq) -- torch.optim.Adam's arithmetic and state (imaginaire/utils/trainer.py:297-323,
+ * configs/scenedreamer_train.yaml:36-61: betas (0, 0.999), eps 1e-7, no weight decay / amsgrad).
+ * n elements (multiple of 4, 16-byte aligned arrays); step = count AFTER the increment (>= 1).
+ * With beta1 == 0 entries whose gradient is exactly 0 only decay exp_avg_sq (param / exp_avg are
+ * not read) -- identical to the dense formula.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int64_t step, void *stream);
+
 /* Kernels this library has launched in this process so far (every launch is counted; memsets and
  * library GEMMs are not).  bench.py reads it around its timed region for `gpu_launches`.          */
 int64_t sdb_launch_count(void);

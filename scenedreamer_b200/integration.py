@@ -36,7 +36,7 @@ import sys
 
 import torch
 
-from . import render, rendercnn
+from . import optim, render, rendercnn
 
 TARGET_MODULE = 'imaginaire.generators.scenedreamer'
 PUBLIC_ENTRIES = ('forward', 'inference_givenstyle', 'inference_givenstyle_depth')
@@ -137,6 +137,10 @@ def _state(gen):
 
 def _live_params(gen):
     """Parameters (not detached) under the reference's state-dict names, for the autograd path."""
+    if os.environ.get('SDB200_ADAM', '1') != '0':
+        emb = getattr(gen.hash_encoder, 'embeddings', None)
+        if emb is not None and not getattr(emb, '_sdb200_table', False):
+            optim.tag_table(emb)                                # its Adam step is taken over by the one-pass kernel (optim.py)
     P = {}
     for prefix, mod in (('render_net', gen.render_net), ('sky_net', gen.sky_net), ('hash_encoder', gen.hash_encoder)):
         for k, v in mod.named_parameters():
@@ -350,6 +354,8 @@ def install(generator_cls, precision=DEFAULT_PRECISION):
     generator_cls._sdb200_reference_forward_perpix = generator_cls._forward_perpix
     generator_cls._sdb200_precision = precision
     generator_cls._forward_perpix = fused_forward_perpix
+    if os.environ.get('SDB200_ADAM', '1') != '0':
+        optim.install_step_hook()                               # f2: the hash table's Adam step in one pass (optim.py)
     if hasattr(generator_cls, '_forward_global') and hasattr(generator_cls, '_forward_perpix_sub'):
         generator_cls._sdb200_reference_forward_global = generator_cls._forward_global
         generator_cls._forward_global = fused_forward_global

@@ -145,3 +145,64 @@ def test_train_sky_torch_crosscheck(scene, golden_ops, sky_impl):
         rel = float((a - b).norm() / (b.norm() + 1e-30))
         print('sky %-28s native vs %s rel-L2 %.3e' % (k, sky_impl, rel))
         assert rel <= 1e-2, k
+
+
+@pytest.mark.parametrize('betas', [(0.0, 0.999), (0.9, 0.999)])
+def test_fused_adam_step_matches_torch_adam(betas):
+    """f2: sdb_adam_step == torch.optim.Adam (reference: trainer.py:297-323, scenedreamer_train.yaml:36-61) over several
+    steps with the sparse gradients a hash table sees (most rows exactly zero); parameters AND optimizer state."""
+    from scenedreamer_b200 import optim
+    g = torch.Generator().manual_seed(0)
+    rows = 50000
+    p0 = (torch.rand(rows, 8, generator=g) * 2e-4 - 1e-4).to(DEV)
+    pa = torch.nn.Parameter(p0.clone())
+    ref = torch.optim.Adam([pa], lr=1e-4, eps=1e-7, betas=betas)
+    pb = p0.clone()
+    m, v = torch.zeros_like(pb), torch.zeros_like(pb)
+    for t in range(1, 7):
+        grad = torch.zeros(rows, 8, device=DEV)
+        idx = torch.randint(0, rows, (rows // 20,), generator=g).to(DEV)
+        grad[idx] = torch.randn(idx.numel(), 8, generator=g).to(DEV) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))
+        pa.grad = grad.clone()
+        ref.step()
+        optim.adam_step_(pb, grad, m, v, t, 1e-4, betas[0], betas[1], 1e-7)
+    st = ref.state[pa]
+    np.testing.assert_allclose(pb.cpu().numpy(), pa.detach().cpu().numpy(), rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(m.cpu().numpy(), st['exp_avg'].cpu().numpy(), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(v.cpu().numpy(), st['exp_avg_sq'].cpu().numpy(), rtol=2e-6, atol=1e-30)
+
+
+def test_adam_step_hook_takes_over_tagged_table_only():
+    """Zero-edit route of f2: a plain torch.optim.Adam over (table, other); the tagged table is stepped by the fused kernel
+    with the optimizer's own hyper-parameters and state, everything else by torch -- same result as untouched torch Adam."""
+    from scenedreamer_b200 import optim
+    g = torch.Generator().manual_seed(1)
+    t0, o0 = torch.randn(4096, 8, generator=g).to(DEV), torch.randn(33, generator=g).to(DEV)
+    table, other = torch.nn.Parameter(t0.clone()), torch.nn.Parameter(o0.clone())
+    table_r, other_r = torch.nn.Parameter(t0.clone()), torch.nn.Parameter(o0.clone())
+    kw = dict(lr=1e-3, eps=1e-7, betas=(0.0, 0.999))
+    opt = torch.optim.Adam([{'params': [table], 'lr': 5e-4}, {'params': [other]}], **kw)
+    opt_r = torch.optim.Adam([{'params': [table_r], 'lr': 5e-4}, {'params': [other_r]}], **kw)
+    optim.tag_table(table)
+    optim.install_step_hook()
+    before = optim.stats['fused_steps']
+    try:
+        for _ in range(3):
+            gt = torch.zeros_like(t0)
+            gt[::7] = torch.randn(gt[::7].shape, generator=g).to(DEV)
+            go = torch.randn(33, generator=g).to(DEV)
+            table.grad, other.grad = gt.clone(), go.clone()
+            table_r.grad, other_r.grad = gt.clone(), go.clone()
+            opt.step()
+            assert table.grad is None                                  # cleared by the hook: torch skipped it
+            optim.remove_step_hook()
+            opt_r.step()
+            optim.install_step_hook()
+    finally:
+        optim.remove_step_hook()
+    assert optim.stats['fused_steps'] == before + 3
+    np.testing.assert_allclose(table.detach().cpu().numpy(), table_r.detach().cpu().numpy(), rtol=2e-6, atol=1e-9)
+    assert torch.equal(other, other_r)
+    assert float(opt.state[table]['step']) == 3.0 and set(opt.state[table]) == {'step', 'exp_avg', 'exp_avg_sq'}
+    sd = opt.state_dict()                                              # interchangeable with a plain Adam
+    opt_r.load_state_dict(sd)
