@@ -248,7 +248,8 @@ int sdb_sky_forward(const float *d_raydirs, int32_t n_img, int32_t H, int32_t W,
  *   4. weight gradients: dZ^T * A over all samples on the tensor cores (hand-written tcgen05 kernel: the
  *      bf16 records are MMA-ready tiles, fp32 accumulators in TMEM; csrc/wgrad.cu).
  * The same sdb_render_params as the forward call must be passed (same rays, uniforms, packs).
- * The call reads the live-tile count back (one 4-byte D2H copy + stream synchronize).
+ * The call is fully asynchronous: the live-tile count of the recorded pass stays on the device (record
+ * header), every kernel is launched over the record's capacity and reads it there.
  * ------------------------------------------------------------------------------------------ */
 int64_t sdb_render_train_record_bytes(int32_t n_img, int32_t H, int32_t W, int32_t S);
 int sdb_render_rays_train_forward(const sdb_render_params *p, void *d_record, void *stream);
@@ -333,6 +334,17 @@ int sdb_cnn_forward(const float *d_net_out, int32_t H, int32_t W, const void *d_
  * ------------------------------------------------------------------------------------------ */
 int sdb_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int64_t step, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * f4. Rejection statistics of the training camera sampler, one pass on the
+ * device (Generator._get_batch, imaginaire/generators/scenedreamer.py:127-142):
+ *   d_stats[0] = mean of the non-NaN first-hit entry depths depth2[0, :, :, 0]
+ *   d_stats[1] = -sum_k p_k log(p_k + 1e-10), p_k = share of rays whose first voxel id is k (n_bins = 680)
+ * d_voxel_id [H*W, M] int32, d_depth2 [2][H*W][M]; d_workspace: sdb_pose_stats_workspace_bytes().
+ * ------------------------------------------------------------------------------------------ */
+int64_t sdb_pose_stats_workspace_bytes(int32_t n_bins);
+int sdb_pose_stats(const int32_t *d_voxel_id, const float *d_depth2, int32_t H, int32_t W, int32_t M, int32_t n_bins,
+                   float *d_stats, void *d_workspace, void *stream);
 
 /* Kernels this library has launched in this process so far (every launch is counted; memsets and
  * library GEMMs are not).  bench.py reads it around its timed region for `gpu_launches`.          */

@@ -218,8 +218,10 @@ __device__ __forceinline__ void red_add8(float *dst, const float (&v)[8]) {
 }
 
 __global__ void __launch_bounds__(256)
-table3_backward_kernel(const Params p, long long n_slots, const float *__restrict__ dx0, float *__restrict__ dt3, int agg_levels)
+table3_backward_kernel(const Params p, const float *__restrict__ dx0, float *__restrict__ dt3, int agg_levels)
 {
+    // the number of live slots is read on the device: the host never waits for the forward pass to size a launch
+    const long long n_slots = (long long)__ldg(p.n_live) * p.S * kRows;
     const long long slot = blockIdx.x * 256ll + threadIdx.x;
     const int level = blockIdx.y, lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
@@ -442,12 +444,10 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
     const bool timing0 = getenv("SDB_TIMING") != nullptr;
     cudaEvent_t tev0 = nullptr;
     if (timing0) { cudaEventCreate(&tev0); cudaEventRecord(tev0, st); }
-    // number of live ray tiles of the recorded forward pass (sizes the GEMMs and the grids below)
-    int32_t n_live = 0;
-    SDB_CUDA(cudaMemcpyAsync(&n_live, rec + rl.hdr, 4, cudaMemcpyDeviceToHost, st));
-    SDB_CUDA(cudaStreamSynchronize(st));
-    if (n_live < 0 || n_live > p.n_tiles) return SDB_EINVAL;
-    const long long n_slots = (long long)n_live * p.S * kRows;
+    // The number of live ray tiles of the recorded pass stays ON THE DEVICE (record header): every kernel below is launched over
+    // the record's capacity and reads it there, so this call never synchronises -- the host can queue the whole backward (and the
+    // torch ops behind it) while the forward kernel is still running, which is what makes the step time independent of host speed.
+    const long long cap_items = (long long)p.n_tiles * p.S;
     const size_t table_bytes = ((size_t)sp->L << p.log2_T) * 8 * 4;
 
     SDB_CUDA(cudaMemsetAsync(g->d_grad_sky_avg, 0, (size_t)p.n_img * kOutC * 4, st));
@@ -464,14 +464,6 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
     composite_backward_kernel<<<p.n_tiles, 256, 0, st>>>(p, g->d_grad_net_out, g->d_grad_sky, g->d_grad_sky_avg, dc32, dc16,
                                                          dsig32, dsig16);
     SDB_CHECK_LAUNCH();
-    if (n_live == 0) {
-        SDB_CUDA(cudaMemsetAsync(g->d_grad_table, 0, table_bytes, st));
-        SDB_CUDA(cudaMemsetAsync(g->d_grad_w1ext, 0, (size_t)kHidden * kX0Cols * 4, st));
-        SDB_CUDA(cudaMemsetAsync(g->d_grad_wh, 0, (size_t)5 * kHidden * kActCols * 4, st));
-        SDB_CUDA(cudaMemsetAsync(g->d_grad_wsig, 0, (size_t)8 * kActCols * 4, st));
-        SDB_CUDA(cudaMemsetAsync(g->d_grad_wout, 0, (size_t)kOutC * kActCols * 4, st));
-        return SDB_OK;
-    }
     mark();
     // 2. data-gradient chain on the tensor-core engine: one work item per (live tile, sample step) -- the slot index
     //    (work * 1 + 0) * 128 + row of such an item IS the record's (tile * S + step) * 128 + row
@@ -479,19 +471,18 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         Params pc = p;
         pc.work_mult = p.S;
         pc.S = 1;
-        const long long items = (long long)n_live * p.S;
-        const int grid = items < sdb_num_sms() ? (int)items : sdb_num_sms();
+        const int grid = cap_items < sdb_num_sms() ? (int)cap_items : sdb_num_sms();      // work items beyond n_live * S do not exist: CTAs find none
         const int rc = launch_bwd_chain(pc, grid, st);
         if (rc != SDB_OK) return rc;
     }
     mark();
     // 3. table gradient: scatter into the pre-blended table, transpose of the pre-blend, scene code
     {
-        dim3 grid((unsigned)((n_slots + 255) / 256), kLevels);
+        dim3 grid((unsigned)((cap_items * kRows + 255) / 256), kLevels);
         // SDB_TABLE_AGG_LEVELS: tuning knob (levels 0..n-1 use the warp-aggregated scatter); default from profiles/
         int agg_levels = 12;
         if (const char *e = getenv("SDB_TABLE_AGG_LEVELS")) agg_levels = atoi(e);
-        table3_backward_kernel<<<grid, 256, 0, st>>>(p, n_slots, dx0, dt3, agg_levels);
+        table3_backward_kernel<<<grid, 256, 0, st>>>(p, dx0, dt3, agg_levels);
         SDB_CHECK_LAUNCH();
         int rc = sdb_preblend_table(dt3, g->d_grad_table, sp->L, p.log2_T, p.level_S, p.base_res, p.genc, stream);
         if (rc != SDB_OK) return rc;
@@ -516,7 +507,7 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
                      g->d_grad_wh + (size_t)k * kHidden * kActCols, kHidden);
         add_jobs(jobs, nj, p.tr.act + (size_t)5 * cap * kActCols, kActCols, dc16, kOutC, g->d_grad_wout, kOutC);       // fc_out_c
         add_jobs(jobs, nj, p.tr.act + (size_t)3 * cap * kActCols, kActCols, dsig16, 8, g->d_grad_wsig, 8);             // fc_sigma
-        const int rc = launch_wgrad(jobs, nj, (long long)n_live * p.S, st);
+        const int rc = launch_wgrad(jobs, nj, p.n_live, p.S, cap_items, st);
         if (rc != SDB_OK) return rc;
     }
     mark();
@@ -526,6 +517,8 @@ extern "C" int sdb_render_rays_backward(const sdb_render_params *sp, const void 
         for (int i = 0; i + 1 < ntev; i++) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
         float pre = 0.0f;
         if (tev0) { cudaEventElapsedTime(&pre, tev0, tev[0]); cudaEventDestroy(tev0); }
+        int32_t n_live = 0;
+        cudaMemcpy(&n_live, rec + rl.hdr, 4, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[sdb timing] backward: prologue %.3f ms, compositing %.3f ms, chain %.3f ms, table %.3f ms, weight GEMMs %.3f ms (n_live %d)\n",
                 pre, ms[0], ms[1], ms[2], ms[3], n_live);
         for (int i = 0; i < ntev; i++) cudaEventDestroy(tev[i]);
@@ -581,5 +574,5 @@ extern "C" int sdb_sky_backward(int32_t n_img, int32_t H, int32_t W, const void 
         add_jobs(jobs, nj, p.tr.act + (size_t)k * cap * kActCols, kActCols, p.tr.dz + (size_t)(k + 1) * cap * kHidden, kHidden,
                  d_grad_wh + (size_t)k * kHidden * kActCols, kHidden);
     add_jobs(jobs, nj, p.tr.act + (size_t)4 * cap * kActCols, kActCols, p.tr.dc16, kOutC, d_grad_wout, kOutC);                // fc_out_c
-    return launch_wgrad(jobs, nj, p.n_tiles, st);
+    return launch_wgrad(jobs, nj, nullptr, 1, p.n_tiles, st);
 }

@@ -32,7 +32,9 @@ constexpr uint32_t kWgSmem = kWgStages * kWgStageBytes + 256;
 struct WgParams {
     WgJob job[kWgMaxJobs];
     int n_jobs;
-    long long n_items;
+    const int32_t *n_live;       // device: live ray tiles of the recorded pass (nullptr: every item up to cap_items exists)
+    int items_per_live;
+    long long cap_items;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -48,7 +50,7 @@ wgrad_kernel(const WgParams prm)
     while (j < prm.n_jobs && split >= prm.job[j].nsplit) { split -= prm.job[j].nsplit; j++; }
     if (j >= prm.n_jobs) return;
     const WgJob jb = prm.job[j];
-    const long long n_items = prm.n_items;
+    const long long n_items = prm.n_live ? (long long)__ldg(prm.n_live) * prm.items_per_live : prm.cap_items;
     const long long my_items = split < n_items ? (n_items - split + jb.nsplit - 1) / jb.nsplit : 0;
 
     // dZ chunks the job does not own stay zero for the whole kernel (M-tiles narrower than 128 rows: fc_out_c, fc_sigma)
@@ -138,13 +140,16 @@ wgrad_kernel(const WgParams prm)
 }  // namespace
 
 // Splits: CTAs are handed out in proportion to the bytes a job streams per item, one CTA per SM over the whole list.
-int launch_wgrad(WgJob *jobs, int n_jobs, long long n_items, cudaStream_t st)
+int launch_wgrad(WgJob *jobs, int n_jobs, const int32_t *d_n_live, int items_per_live, long long cap_items, cudaStream_t st)
 {
     if (n_jobs < 1 || n_jobs > kWgMaxJobs) return SDB_EINVAL;
-    if (n_items <= 0) return SDB_OK;
+    if (cap_items <= 0) return SDB_OK;
+    const long long n_items = cap_items;
     WgParams prm{};
     prm.n_jobs = n_jobs;
-    prm.n_items = n_items;
+    prm.n_live = d_n_live;
+    prm.items_per_live = items_per_live;
+    prm.cap_items = cap_items;
     double total = 0.0;
     for (int i = 0; i < n_jobs; i++) {
         const WgJob &jb = jobs[i];

@@ -21,6 +21,8 @@ struct WgJob {
 };
 
 // dW += over the first n_items work items (128 samples each); `out` buffers must have been zeroed on the stream.
-int launch_wgrad(WgJob *jobs, int n_jobs, long long n_items, cudaStream_t st);
+// n_items = *d_n_live * items_per_live read ON THE DEVICE (no host round trip), or cap_items when d_n_live is null;
+// cap_items (the record's capacity) only sizes the split of the jobs over the CTAs.
+int launch_wgrad(WgJob *jobs, int n_jobs, const int32_t *d_n_live, int items_per_live, long long cap_items, cudaStream_t st);
 
 }  // namespace rf

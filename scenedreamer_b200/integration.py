@@ -75,7 +75,7 @@ class _FusedState:
         self._lut = None
         self.precision = precision
         self.epoch = 0
-        self.renderer, self.renderer_key = None, None
+        self.renderer, self.renderer_key, self.renderer_epoch, self.cnn_epoch = None, None, -1, -1
         self.cnn, self.cnn_key, self.cnn_precision = None, None, rendercnn.PRECISION_FP16X3
         self.frame = _FrameCache()
         self.stats = {'fused_calls': 0, 'frame_launches': 0, 'tile_hits': 0, 'train_calls': 0, 'reference_calls': 0,
@@ -99,6 +99,9 @@ class _FusedState:
     def get_cnn(self, gen):
         """Tensor-core RenderCNN engine over the generator's own `denoiser.*` tensors, or None if the module is not
         SceneDreamer's RenderCNN (64 -> 256 -> 3)."""
+        if self.cnn_epoch == self.epoch and self.cnn_key is not None:
+            return self.cnn
+        self.cnn_epoch = self.epoch
         den = getattr(gen, 'denoiser', None)
         if den is None:
             return None
@@ -110,6 +113,11 @@ class _FusedState:
         return self.cnn
 
     def get_renderer(self, gen):
+        # inside an epoch (one public call of the generator) the weights cannot change behind torch's back: the state-dict scan
+        # below is done once per epoch, not once per tile of the reference's tile loop (40 scans x ~0.3 ms per frame)
+        if self.renderer is not None and self.renderer_epoch == self.epoch and not torch.is_grad_enabled():
+            return self.renderer
+        self.renderer_epoch = self.epoch
         mods = (('render_net', gen.render_net), ('sky_net', gen.sky_net), ('hash_encoder', gen.hash_encoder))
         P = {}
         for prefix, mod in mods:
@@ -333,6 +341,66 @@ def fused_forward_global(self, net_out, z):
     return eng.forward(net_out, z)
 
 
+SAMPLER_SPECULATION = 4          # candidate poses judged per synchronisation
+
+
+def fused_get_batch(self, batch_size, device):
+    """Replacement body of Generator._get_batch (scenedreamer.py:80-155): the training camera sampler.
+
+    The reference draws a pose, raycasts it, and reads two statistics back to the host (mean first-hit depth, entropy of the
+    first-hit labels: two blocking round trips per candidate) before deciding whether to keep it.  Here SAMPLER_SPECULATION
+    candidates are drawn with the reference's OWN pose functions in the reference's order, raycast back to back, judged on
+    the device by one small kernel each (ops.pose_stats) and read back with ONE synchronisation; the first accepted one wins
+    and the host RNGs (torch, numpy) are rewound to their state right after that candidate was drawn.  The accepted poses,
+    their order and the RNG streams afterwards are therefore exactly the reference's."""
+    reference = type(self)._sdb200_reference_get_batch
+    if not enabled() or os.environ.get('SDB200_SAMPLER', '1') == '0' or self.camera_sampler_type not in ('random', 'traditional') or \
+            not torch.device(device).type == 'cuda':
+        return reference(self, batch_size, device)
+    import numpy as np
+    from . import ops
+    smod = sys.modules[type(self).__module__]
+    camctl, mc_utils = smod.camctl, smod.mc_utils
+    with torch.no_grad():
+        if hasattr(self.voxel, 'sample_world'):
+            self.voxel.sample_world(device)
+        ids, deps, dirs, oris = [], [], [], []
+        for _ in range(batch_size):
+            picked = None
+            while picked is None:
+                cands = []
+                for _k in range(SAMPLER_SPECULATION):
+                    cam_res = self.cam_res                                           # scenedreamer.py:97-122, verbatim order of draws
+                    cam_c = [(cam_res[0] - 1) / 2, (cam_res[1] - 1) / 2]
+                    if self.camera_sampler_type == 'traditional' and torch.rand(1).item() > 0.5:
+                        cam_ori_t, cam_dir_t, cam_up_t, cam_f = camctl.rand_camera_pose_tour(self.voxel)
+                        cam_f = cam_f * (cam_res[1] - 1)
+                    else:
+                        cam_ori_t, cam_dir_t, cam_up_t = camctl.rand_camera_pose_thridperson2(self.voxel)
+                        cam_f = 0.5 / np.tan(np.deg2rad(73 / 2) * (np.random.rand(1) * 0.5 + 0.5)) * (cam_res[1] - 1)
+                    cam_res_crop = [self.crop_size[0] + self.pad, self.crop_size[1] + self.pad]
+                    cam_c = mc_utils.rand_crop(cam_c, cam_res, cam_res_crop)
+                    rng = (torch.get_rng_state(), np.random.get_state())
+                    out = smod.voxlib.ray_voxel_intersection_perspective(self.voxel.voxel_t, cam_ori_t, cam_dir_t, cam_up_t, cam_f, cam_c,
+                                                                         cam_res_crop, self.num_blocks_early_stop)
+                    cands.append((out, cam_ori_t, rng, ops.pose_stats(out[0], out[1])))
+                stats = torch.stack([c[3] for c in cands]).cpu()                     # the ONE synchronisation of this round
+                for (out, ori, rng, _s), (avg_depth, entropy) in zip(cands, stats.tolist()):
+                    if self.camera_rej_avg_depth > 0 and avg_depth < self.camera_rej_avg_depth:
+                        continue
+                    if self.camera_min_entropy > 0 and entropy < self.camera_min_entropy:
+                        continue
+                    picked = (out, ori)
+                    torch.set_rng_state(rng[0])                                      # forget the candidates drawn after the winner
+                    np.random.set_state(rng[1])
+                    break
+            ids.append(picked[0][0])
+            deps.append(picked[0][1])
+            dirs.append(picked[0][2])
+            oris.append(picked[1])
+        return torch.stack(ids, 0), torch.stack(deps, 0), torch.stack(dirs, 0), torch.stack(oris, 0).to(device), None
+
+
 def _epoch_entry(name, fn):
     @functools.wraps(fn)
     def entry(self, *a, **k):
@@ -356,6 +424,9 @@ def install(generator_cls, precision=DEFAULT_PRECISION):
     generator_cls._forward_perpix = fused_forward_perpix
     if os.environ.get('SDB200_ADAM', '1') != '0':
         optim.install_step_hook()                               # f2: the hash table's Adam step in one pass (optim.py)
+    if '_get_batch' in generator_cls.__dict__ and hasattr(generator_cls, 'sample_camera'):
+        generator_cls._sdb200_reference_get_batch = generator_cls._get_batch
+        generator_cls._get_batch = fused_get_batch
     if hasattr(generator_cls, '_forward_global') and hasattr(generator_cls, '_forward_perpix_sub'):
         generator_cls._sdb200_reference_forward_global = generator_cls._forward_global
         generator_cls._forward_global = fused_forward_global
@@ -372,6 +443,9 @@ def uninstall(generator_cls):
         return
     generator_cls._forward_perpix = ref
     del generator_cls._sdb200_reference_forward_perpix
+    if '_sdb200_reference_get_batch' in generator_cls.__dict__:
+        generator_cls._get_batch = generator_cls._sdb200_reference_get_batch
+        del generator_cls._sdb200_reference_get_batch
     if '_sdb200_reference_forward_global' in generator_cls.__dict__:
         g = generator_cls._sdb200_reference_forward_global
         if '_forward_global' in generator_cls.__dict__:

@@ -241,6 +241,25 @@ def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, 
 
 
 # ------------------------------------------------------------------------------------------------
+# f4: rejection statistics of the camera sampler
+# ------------------------------------------------------------------------------------------------
+def pose_stats(voxel_id, depth2, n_bins=680, out=None):
+    """voxel_id [H,W,M,1] int32, depth2 [2,H,W,M,1] (a raycast result) -> float32 [2] on the device:
+    (mean non-NaN first-hit depth, entropy of the first-hit voxel ids) -- scenedreamer.py:127-142, no host round trip."""
+    _check_input(voxel_id, 'voxel_id', torch.int32)
+    _check_input(depth2, 'depth2', torch.float32)
+    H, W, M = voxel_id.shape[:3]
+    L = _lib.lib()
+    dev = voxel_id.device
+    stats = out if out is not None else torch.empty(2, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(L.sdb_pose_stats_workspace_bytes(int(n_bins))), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        code = L.sdb_pose_stats(_ptr(voxel_id), _ptr(depth2), int(H), int(W), int(M), int(n_bins), _ptr(stats), _ptr(ws), _stream(voxel_id))
+    _lib.check(code, 'pose_stats')
+    return stats
+
+
+# ------------------------------------------------------------------------------------------------
 # diagnostics
 # ------------------------------------------------------------------------------------------------
 def tc_selftest(a, b, bf16=False, variant=0):

@@ -349,3 +349,21 @@ def test_tc_operand_with_shifted_start_row():
         torch.cuda.synchronize()
         assert torch.equal(c0, c2)
         assert float((c0 - a.half().float() @ b.half().float().t()).abs().max()) <= 1e-3
+
+
+def test_pose_stats_match_torch(world):
+    """f4: the camera sampler's rejection statistics (scenedreamer.py:127-142) from one device pass vs the reference's torch ops."""
+    vox = world.voxel_t.to(DEV)
+    for k in (0, 3):
+        o, d, u, f, c, res = synth.frame_camera(world, synth.eval_camera_poses(world, maxstep=8, pattern=0)[k], (60, 90), 6)
+        vid, dep, _ = ops.ray_voxel_intersection_perspective(vox, o, d, u, f, c, res, 6)
+        st = ops.pose_stats(vid, dep).cpu()
+        depth_map = dep[0, :, :, 0, :]
+        avg = torch.mean(depth_map[~torch.isnan(depth_map)])
+        cnt = torch.bincount(torch.flatten(vid[:, :, 0, 0]), weights=None, minlength=680).float() / (vid.size(0) * vid.size(1))
+        ent = -torch.sum(cnt * torch.log(cnt + 1e-10))
+        assert abs(float(st[0]) - float(avg)) <= 1e-5 * abs(float(avg)) and abs(float(st[1]) - float(ent)) <= 1e-5
+    empty = torch.zeros(8, 8, 6, 1, dtype=torch.int32, device=DEV)
+    nan = torch.full((2, 8, 8, 6, 1), float('nan'), device=DEV)
+    st = ops.pose_stats(empty, nan).cpu()
+    assert torch.isnan(st[0]) and abs(float(st[1])) <= 1e-6          # nothing hit: mean of nothing, one label -> zero entropy
