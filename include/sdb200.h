@@ -328,12 +328,14 @@ int sdb_cnn_forward(const float *d_net_out, int32_t H, int32_t W, const void *d_
  * f2. The Adam step of the hash table in one pass over (param, grad, exp_avg,
  * exp_avg_sq) -- torch.optim.Adam's arithmetic and state (imaginaire/utils/trainer.py:297-323,
  * configs/scenedreamer_train.yaml:36-61: betas (0, 0.999), eps 1e-7, no weight decay / amsgrad).
- * n elements (multiple of 4, 16-byte aligned arrays); step = count AFTER the increment (>= 1).
+ * n elements (multiple of 4, 16-byte aligned arrays); step = count AFTER the increment (>= 1); the
+ * hyper-parameters are doubles (Python floats): 1 - beta, the bias corrections and lr / bc1 are formed
+ * in double and narrowed last, as torch does.
  * With beta1 == 0 entries whose gradient is exactly 0 only decay exp_avg_sq (param / exp_avg are
  * not read) -- identical to the dense formula.
  * ------------------------------------------------------------------------------------------ */
-int sdb_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, float lr,
-                  float beta1, float beta2, float eps, int64_t step, void *stream);
+int sdb_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, int64_t step, void *stream);
 
 /* --------------------------------------------------------------------------------------------
  * f4. Rejection statistics of the training camera sampler, one pass on the
@@ -345,6 +347,21 @@ int sdb_adam_step(float *d_param, const float *d_grad, float *d_exp_avg, float *
 int64_t sdb_pose_stats_workspace_bytes(int32_t n_bins);
 int sdb_pose_stats(const int32_t *d_voxel_id, const float *d_depth2, int32_t H, int32_t W, int32_t M, int32_t n_bins,
                    float *d_stats, void *d_workspace, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * f3. Voxel world of a scene from its bird's-eye-view maps, built in HBM.
+ * Replaces the CPU scatter passes, the per-tree Python loop and the 1-4 GB host->device copy of
+ * PCGVoxelGenerator.next_world (imaginaire/model_utils/pcg_gen.py:83-174).
+ *   sdb_world_build: d_hq / d_label int32 [X, Z] (quantised height index, block id per column);
+ *     tree instances d_inst int32 [n_inst, 4] = (h, x, z, model) in the reference's iteration order,
+ *     models concatenated in d_models with dims d_mdim [n_models, 3] and offsets d_moff int64;
+ *     -> d_world int32 [SH, X, Z] (scratch), d_heightmap int64 [X, Z], d_minmax int32[2] = {gnd, top}.
+ *   sdb_world_truncate: d_voxel_t [sky - gnd, X, Z] = world[gnd:sky] (tree keys decoded).
+ * ------------------------------------------------------------------------------------------ */
+int sdb_world_build(const int32_t *d_hq, const int32_t *d_label, int32_t X, int32_t Z, int32_t SH, const int32_t *d_inst,
+                    int32_t n_inst, const int32_t *d_models, const int32_t *d_mdim, const int64_t *d_moff,
+                    int32_t *d_world, int64_t *d_heightmap, int32_t *d_minmax, void *stream);
+int sdb_world_truncate(const int32_t *d_world, int32_t X, int32_t Z, int32_t gnd, int32_t sky, int32_t *d_voxel_t, void *stream);
 
 /* Kernels this library has launched in this process so far (every launch is counted; memsets and
  * library GEMMs are not).  bench.py reads it around its timed region for `gpu_launches`.          */

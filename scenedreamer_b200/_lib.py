@@ -62,9 +62,13 @@ SIGNATURES = {
     'sdb_cnn_pack': (c_int, [c_void_p] * 14 + [c_i32, c_void_p, c_void_p]),
     'sdb_cnn_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
     'sdb_cnn_forward': (c_int, [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_void_p]),
-    'sdb_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_void_p]),
+    'sdb_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                              ctypes.c_double, c_i64, c_void_p]),
     'sdb_pose_stats_workspace_bytes': (c_i64, [c_i32]),
     'sdb_pose_stats': (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
+    'sdb_world_build': (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    'sdb_world_truncate': (c_int, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p]),
     'sdb_launch_count': (c_i64, []),
     'sdb_debug_train_layout': (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_i64)]),
     'sdb_debug_set_progress_buffer': (None, [c_void_p]),

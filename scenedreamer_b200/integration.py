@@ -36,7 +36,7 @@ import sys
 
 import torch
 
-from . import optim, render, rendercnn
+from . import optim, render, rendercnn, worldgen
 
 TARGET_MODULE = 'imaginaire.generators.scenedreamer'
 PUBLIC_ENTRIES = ('forward', 'inference_givenstyle', 'inference_givenstyle_depth')
@@ -494,8 +494,7 @@ class _PatchingLoader(importlib.abc.Loader):
 
     def exec_module(self, module):
         self.inner.exec_module(module)
-        if enabled() and hasattr(module, 'Generator'):
-            install(module.Generator)
+        ensure_installed()
 
     def __getattr__(self, name):
         return getattr(self.inner, name)
@@ -531,6 +530,9 @@ def ensure_installed():
     if mod is not None and hasattr(mod, 'Generator'):
         if enabled():
             install(mod.Generator)
+            pcg = sys.modules.get('imaginaire.model_utils.pcg_gen')
+            if pcg is not None and hasattr(pcg, 'PCGVoxelGenerator') and os.environ.get('SDB200_WORLDGEN', '1') != '0':
+                worldgen.install(pcg.PCGVoxelGenerator)             # f3: the scene's voxel world is built on the device
         _installed = True
 
 
