@@ -17,7 +17,11 @@ namespace {
 // (1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative)
 __device__ __forceinline__ float adam_one(float &p, float g, float &m, float &v, float b1, float b2, float omb1, float omb2,
                                           float step_size, float bc2_sqrt, float eps) {
-    m = __fmaf_rn(b1, m, omb1 * g);                              // lerp(m, g, 1 - beta1)
+    // exp_avg.lerp_(grad, 1 - beta1) with ATen's formula: w < 0.5 ? m + w (g - m) : g - (g - m)(1 - w)
+    {
+        const float diff = g - m;
+        m = (fabsf(omb1) < 0.5f) ? __fmaf_rn(omb1, diff, m) : g - diff * (1.0f - omb1);
+    }
     v = __fmaf_rn(b2, v, (omb2 * g) * g);                        // mul_(beta2).addcmul_(g, g, value = 1 - beta2)
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);   // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
     p = __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);           // addcdiv_(m, denom, value = -step_size)
