@@ -66,9 +66,11 @@ def build_world(height_map, semantic_map, tree_map, tree_models, device, rng=ran
     label = np.asarray(BIOME2MC, dtype=np.int32)[sem.astype(np.int64)]
     with torch.cuda.device(dev):
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        d_hq = torch.from_numpy(hq.astype(np.int32)).to(dev)
-        d_label = torch.from_numpy(label).to(dev)
-        d_inst = torch.from_numpy(inst).to(dev) if len(inst) else None
+        # C-contiguous uploads: the maps may arrive Fortran-ordered (np.load keeps the order of the saved array), and a torch
+        # tensor made from such an array keeps transposed strides all the way to the device
+        d_hq = torch.from_numpy(np.ascontiguousarray(hq, dtype=np.int32)).to(dev)
+        d_label = torch.from_numpy(np.ascontiguousarray(label, dtype=np.int32)).to(dev)
+        d_inst = torch.from_numpy(np.ascontiguousarray(inst)).to(dev) if len(inst) else None
         d_models, d_mdim, d_moff = torch.from_numpy(flat).to(dev), torch.from_numpy(mdim).to(dev), torch.from_numpy(moff).to(dev)
         world = torch.empty(SAMPLE_HEIGHT, X, Z, dtype=torch.int32, device=dev)                       # scratch: 1 GB at 1024^2, 4.3 GB at 2048^2
         heightmap = torch.empty(X, Z, dtype=torch.int64, device=dev)
@@ -80,10 +82,10 @@ def build_world(height_map, semantic_map, tree_map, tree_models, device, rng=ran
         voxel_t = torch.empty(sky - gnd, X, Z, dtype=torch.int32, device=dev)
         _lib.check(L.sdb_world_truncate(_ptr(world), X, Z, gnd, sky, _ptr(voxel_t), st), 'sdb_world_truncate')
         del world
-        h16 = torch.from_numpy(hq.astype(np.int64)).to(dev) + PAD_NUM
+        h16 = torch.from_numpy(np.ascontiguousarray(hq, dtype=np.int64)).to(dev) + PAD_NUM
         current_height_map = (h16 / (SAMPLE_HEIGHT - 1))[None, None]                                  # :167
-        org_sem = torch.from_numpy(sem.copy()).to(dev)
-        org_sem[torch.from_numpy(trees != 255).to(dev)] = 10                                          # :100-101
+        org_sem = torch.from_numpy(np.ascontiguousarray(sem)).to(dev)
+        org_sem[torch.from_numpy(np.ascontiguousarray(trees != 255)).to(dev)] = 10                                          # :100-101
         current_semantic_map = F.one_hot(org_sem.to(torch.int64)).to(torch.float).permute(2, 0, 1)[None]   # :168
     return dict(voxel_t=voxel_t, heightmap=heightmap.cpu(), gnd_level=gnd, sky_level=sky, current_height_map=current_height_map,
                 current_semantic_map=current_semantic_map, total_size=(X, Z))
