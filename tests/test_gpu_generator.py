@@ -37,6 +37,8 @@ def fused_generator():
     refgen.setup('dropin')
     gen, _ = refgen.build_generator(1024, DEV)
     refgen.set_world(gen, refgen.synthetic_world(1024), DEV)
+    from scenedreamer_b200 import integration
+    integration.ensure_installed()          # what the first drop-in call of a run does (dropin/voxlib.py); idempotent
     return gen
 
 
