@@ -230,11 +230,8 @@ class FrameRenderer:
     def set_early_stop(self, T):
         self.r.early_stop = T
 
-    def frame(self, cam, events=None, rows=None, sky_sum_hook=None):
-        """cam = (ori, dir, up, f, c, res) with HOST tensors: the reference API takes the pose from the CPU
-        (scenedreamer.py:569-586); it rides in the kernel arguments of the DDA and of the fused kernel, nothing is
-        copied to the device per frame.  rows = (y0, y1): only that band of the padded frame (single-frame sharding);
-        sky_sum_hook(avg_band, n_rays_band) -> frame-global sky mean (the band means of all ranks combined)."""
+    def cast(self, cam, rows=None):
+        """a1 + a9 for the frame or for a band of rows (y0, y1) of it: -> (voxel_id, depth2, raydirs, sky, band sky mean, n rays)."""
         o, d, u, f, c, res = cam
         if rows is not None:
             y0, y1 = rows
@@ -242,14 +239,23 @@ class FrameRenderer:
         vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, res, 6)
         vid, dep, rd = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0)
         sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
-        if sky_sum_hook is not None:
-            sky_avg = sky_sum_hook(sky_avg, res[0] * res[1])
+        return vid, dep, rd, sky, sky_avg, res[0] * res[1]
+
+    def shade(self, cam, rays, sky_avg, events=None):
+        vid, dep, rd, sky = rays[:4]
         if events is not None:
             events[0].record()
-        out = self.r.forward(vid, dep, rd, o.unsqueeze(0), self.z, self.genc, num_samples=self.spp, sky=sky, sky_avg=sky_avg)
+        out = self.r.forward(vid, dep, rd, cam[0].unsqueeze(0), self.z, self.genc, num_samples=self.spp, sky=sky, sky_avg=sky_avg)
         if events is not None:
             events[1].record()
         return out
+
+    def frame(self, cam, events=None, rows=None):
+        """cam = (ori, dir, up, f, c, res) with HOST tensors: the reference API takes the pose from the CPU
+        (scenedreamer.py:569-586); it rides in the kernel arguments of the DDA and of the fused kernel, nothing is
+        copied to the device per frame.  rows = (y0, y1): only that band of the padded frame."""
+        rays = self.cast(cam, rows)
+        return self.shade(cam, rays, rays[4], events)
 
 
 def run_gpu_arm(args):
@@ -275,20 +281,47 @@ def run_gpu_arm(args):
     # pinned host copies of the per-frame inputs (camera pose) and of the per-frame result
     pose_pinned = [torch.stack([c[0], c[1], c[2]]).pin_memory() for c in cams]
     res = cams[0][5]
-    rows = sharding.tile_rows_for_rank(res[0], rank, world_size) if strong else None
-    band_h = (rows[1] - rows[0]) if strong else res[0]
-    band_cap = sharding.tile_rows_for_rank(res[0], 0, world_size)[1] if strong else res[0]      # tallest band (rank 0's)
-    host_out = torch.empty(2, (band_cap * world_size) if strong else res[0], res[1], dtype=torch.float32).pin_memory()
+    bands = [b for b in sharding.paired_bands(res[0], rank, world_size)] if strong else None     # two bands per rank (top + mirrored bottom)
+    rows = bands[0] if strong else None
+    band_h = sum(b[1] - b[0] for b in bands) if strong else res[0]
+    band_cap = sharding.tile_rows_for_rank(res[0], 0, 2 * world_size)[1] if strong else res[0]  # tallest band (band 0)
+    host_out = torch.empty(2, (2 * band_cap * world_size) if strong else res[0], res[1], dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     L = _lib.lib()
 
-    def sky_hook(avg_band, n_band):
-        # single-frame sharding: the frame-global sky mean (scenedreamer.py:592-598) needs every band: one 64-float
+    def global_sky_mean(parts):
+        # single-frame sharding: the frame-global sky mean (scenedreamer.py:592-598) needs every band: one 65-float
         # all-gather of the band sums, combined in rank order
-        part = torch.cat([avg_band.reshape(64) * float(n_band), torch.tensor([float(n_band)], device=dev)])
+        part = torch.zeros(65, device=dev)
+        for avg_band, n_band in parts:
+            part[:64] += avg_band.reshape(64) * float(n_band)
+            part[64] += float(n_band)
+        if world_size == 1:
+            return (part[:64] / part[64]).reshape(1, 64)
         allp = torch.empty(world_size, 65, device=dev)
         dist.all_gather_into_tensor(allp, part.reshape(1, 65))
         return (allp[:, :64].sum(0) / allp[:, 64].sum()).reshape(1, 64)
+
+    def strong_step(cam, kev):
+        """ONE frame over all ranks: this rank's two bands -> [2, 2 * band_cap, W] maps (bands padded to the tallest)."""
+        rays = [fr.cast(cam, b) for b in bands if b[1] > b[0]]
+        avg = global_sky_mean([(r[4], r[5]) for r in rays])
+        outs = []
+        if kev is not None:
+            kev[0].record()
+        for r in rays:
+            outs.append(fr.shade(cam, r, avg))
+        if kev is not None:
+            kev[1].record()
+        parts, i = [], 0
+        for b in bands:
+            h = b[1] - b[0]
+            m = torch.zeros(2, band_cap, res[1], device=dev)
+            if h > 0:
+                m[:, :h] = torch.stack([outs[i]['depth'][0], outs[i]['total_weight'][0]])
+                i += 1
+            parts.append(m)
+        return torch.cat(parts, 1), (outs[-1] if outs else None)
 
     host_rgb = torch.empty(3, out_hw[0], out_hw[1], dtype=torch.float32).pin_memory()
     e2e_image = not strong                    # the user-facing result of a frame is the IMAGE: RenderCNN + tanh (f1) on top of the path
@@ -299,22 +332,21 @@ def run_gpu_arm(args):
         if ev is not None:
             ev[0].record()
         pose = pose_pinned[idx]                                      # this step's inputs, pinned host memory, passed by value
-        out = fr.frame((pose[0], pose[1], pose[2], cam[3], cam[4], cam[5]), kev, rows=rows,
-                       sky_sum_hook=sky_hook if (strong and world_size > 1) else None)
-        if to_image:
-            maps = fr.image(out, PAD)                                # [3, 540, 960] RGB
+        camk = (pose[0], pose[1], pose[2], cam[3], cam[4], cam[5])
+        if strong:
+            maps, out = strong_step(camk, kev)
         else:
-            maps = torch.stack([out['depth'][0], out['total_weight'][0]])
-        if strong and band_h < band_cap:                             # equal-size bands for the gather (the last band may be shorter)
-            maps = torch.nn.functional.pad(maps, (0, 0, 0, band_cap - band_h))
+            out = fr.frame(camk, kev)
+            maps = fr.image(out, PAD) if to_image else torch.stack([out['depth'][0], out['total_weight'][0]])
         if world_size > 1:
             if cev is not None:
                 cev[0].record()
-            allm = sharding.gather_frames(maps.unsqueeze(0))         # THE collective of the path: finished frames of every rank
+            allm = sharding.gather_frames(maps.unsqueeze(0))         # THE collective of the path: finished frames / bands of every rank
             if cev is not None:
                 cev[1].record()
-            if strong:                                               # bands -> one frame [2, rows, W]
-                maps = allm.permute(1, 0, 2, 3).reshape(2, -1, res[1])
+            if strong:                                               # rank r holds bands r and 2N-1-r: back into frame order
+                a = allm.reshape(world_size, 2, 2, band_cap, res[1])
+                maps = torch.cat([a[:, :, 0], a[:, :, 1].flip(0)], 0).permute(1, 0, 2, 3).reshape(2, -1, res[1])
         if want_host:                                                # D2H of the step's result
             if to_image:
                 host_rgb.copy_(maps, non_blocking=True)
@@ -397,7 +429,7 @@ def run_gpu_arm(args):
         kern_s = tot_kern_ms * 1e-3 / args.steps
         # executed tensor work: live 16x8 ray tiles x steps x 128 rows, MMAs as issued (x3 split: 3 per product)
         # (rank 0 alone: no collective in here)
-        wss = [fr.frame(cams[(k if strong else k * world_size) % len(cams)], rows=rows)['workspace'][:8].view(torch.int32).cpu()
+        wss = [fr.frame(cams[(k if strong else k * world_size) % len(cams)], rows=rows)['workspace'][:8].view(torch.int32).cpu()   # (strong: first band only)
                for k in range(min(args.steps, 8))]
         live_tiles = float(np.mean([int(w[0]) for w in wss]))
         steps_exec = float(np.mean([int(w[1]) for w in wss]))         # tile-steps executed (after early termination)
@@ -447,7 +479,7 @@ def run_gpu_arm(args):
                       'fp16x3': 'f16x3 split (f32-grade), f32 accumulate'}[args.precision] + '; table/compositing f32',
             'data': 'synthetic',
             'config': {'workload': wl_name + ', pad %d (%dx%d rays cast+shaded, %d px credited); ' % (PAD, res[0], res[1], out_hw[0] * out_hw[1]) +
-                                   ('ONE frame per step split into row bands over the GPUs' if strong else 'one frame per GPU per step'),
+                                   ('ONE frame per step split into 2 row bands per GPU (band r and its mirror 2N-1-r)' if strong else 'one frame per GPU per step'),
                        'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
                        'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)',
                        'early_termination': ('off' if args.no_early_stop else
@@ -485,7 +517,7 @@ def run_gpu_arm(args):
             'per_rank_ms': {'columns': ['e2e_step', 'dda_sky', 'fused_kernel_window', 'collective_incl_wait', 'e2e_step_max', 'cpus_in_affinity'],
                             'rows': table},
             'rendercnn_ms': cnn_ms,
-            'collective': {'op': 'all_gather_into_tensor(%s)' % ('RGB frames in the e2e loop, depth+opacity maps in the device-only loops' if e2e_image else 'row bands of depth+opacity maps'), 'bytes_per_rank': int(2 * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
+            'collective': {'op': 'all_gather_into_tensor(%s)' % ('RGB frames in the e2e loop, depth+opacity maps in the device-only loops' if e2e_image else 'row bands of depth+opacity maps'), 'bytes_per_rank': int(2 * 2 * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
                            'ms_per_step_incl_wait_for_slowest_rank': float(np.mean(coll_ms))} if world_size > 1 else None,
         }
         line.update(extras)

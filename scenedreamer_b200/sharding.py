@@ -41,3 +41,13 @@ def tile_rows_for_rank(H, rank, world_size, tile_h=8):
     y0 = min(H, rank * per * tile_h)
     y1 = min(H, (rank + 1) * per * tile_h)
     return y0, y1
+
+
+def paired_bands(H, rank, world_size, tile_h=8):
+    """Single-frame sharding, balanced: the frame is cut into 2 * world_size contiguous bands of tile rows and rank r
+    shades band r AND band 2*world_size - 1 - r.  Cost per row grows roughly monotonically from the sky at the top of a
+    frame to the ground at its bottom, so pairing a band from the top with its mirror from the bottom evens the ranks out
+    (contiguous single bands left the sky-only top ranks idle: 0.1 ms against 3.3 ms of kernel time at 8 GPUs)."""
+    first = tile_rows_for_rank(H, rank, 2 * world_size, tile_h)
+    second = tile_rows_for_rank(H, 2 * world_size - 1 - rank, 2 * world_size, tile_h)
+    return [first, second]
