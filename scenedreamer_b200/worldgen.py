@@ -82,8 +82,9 @@ def build_world(height_map, semantic_map, tree_map, tree_models, device, rng=ran
         voxel_t = torch.empty(sky - gnd, X, Z, dtype=torch.int32, device=dev)
         _lib.check(L.sdb_world_truncate(_ptr(world), X, Z, gnd, sky, _ptr(voxel_t), st), 'sdb_world_truncate')
         del world
-        h16 = torch.from_numpy(np.ascontiguousarray(hq, dtype=np.int64)).to(dev) + PAD_NUM
-        current_height_map = (h16 / (SAMPLE_HEIGHT - 1))[None, None]                                  # :167
+        # O(X*Z) host arithmetic, uploaded: torch's CPU int64 / int division is what the reference's value is bit for bit
+        h16 = torch.from_numpy(np.ascontiguousarray(hq, dtype=np.int64)) + PAD_NUM
+        current_height_map = (h16 / (SAMPLE_HEIGHT - 1))[None, None].to(dev)                          # :167
         org_sem = torch.from_numpy(np.ascontiguousarray(sem)).to(dev)
         org_sem[torch.from_numpy(np.ascontiguousarray(trees != 255)).to(dev)] = 10                                          # :100-101
         current_semantic_map = F.one_hot(org_sem.to(torch.int64)).to(torch.float).permute(2, 0, 1)[None]   # :168
