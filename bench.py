@@ -431,8 +431,9 @@ def run_gpu_arm(args):
         # (rank 0 alone: no collective in here)
         wss = [fr.frame(cams[(k if strong else k * world_size) % len(cams)], rows=rows)['workspace'][:8].view(torch.int32).cpu()   # (strong: first band only)
                for k in range(min(args.steps, 8))]
-        live_tiles = float(np.mean([int(w[0]) for w in wss]))
-        steps_exec = float(np.mean([int(w[1]) for w in wss]))         # tile-steps executed (after early termination)
+        live_tiles = float(np.mean([int(w[0]) for w in wss]))         # live 16x8 tiles (tile kernel) or live RAYS (ray-slot kernel)
+        steps_exec = float(np.mean([int(w[1]) for w in wss]))         # steps of 128 rows executed (after early termination)
+        ray_slots = bool(int(wss[0][3]) == 1)
         mma_eq = {'fp16': (9 + 5 * 17 + 17 * 0.25), 'bf16x3': (27 + 5 * 50 + 50 * 0.25), 'fp16x3': (27 + 5 * 50 + 50 * 0.25)}[args.precision]
         exec_tflops = steps_exec * mma_eq * (2.0 * 128 * 256 * 16) / kern_s / 1e12
         cnn_ms = None
@@ -473,8 +474,9 @@ def run_gpu_arm(args):
             'value_exact_march_note': 'same measurement with early termination off (every sample of every live tile shaded)',
             'samples_credited_per_frame': samples_per_frame,
             'samples_shaded_per_frame': steps_exec * 128 / band_frac,
-            'samples_shaded_note': 'tile-steps executed x 128 rays (rank 0, mean over frames): sky-only 16x8 tiles are never shaded, '
-                                   'tiles stop once every live ray is opaque; padding rays and dead rays inside live tiles ARE shaded',
+            'samples_shaded_note': 'steps executed x 128 rows (rank 0, mean over frames).  Ray-slot kernel: only live rays occupy rows, a ray '
+                                   'leaves its row once it is opaque (one sample later) -- rows idle at the tail of a CTA are counted; tile kernel: '
+                                   'sky-only tiles are skipped, a tile stops once every live ray is opaque',
             'dtype': {'fp16': 'f16 (f32 accumulate)', 'bf16x3': 'bf16x3 split (f32-grade), f32 accumulate',
                       'fp16x3': 'f16x3 split (f32-grade), f32 accumulate'}[args.precision] + '; table/compositing f32',
             'data': 'synthetic',
@@ -507,8 +509,10 @@ def run_gpu_arm(args):
                          'executed_tflops': exec_tflops, 'executed_frac': exec_tflops / tf,
                          'executed_what': '16-bit MMA flops as issued: tile-steps executed x MMAs per step (the parity modes issue 3 MMAs '
                                           'per product) -- the tensor-pipe occupancy; one third of it is algorithmic work',
-                         'live_tiles_per_frame': live_tiles, 'tile_steps_executed_per_frame': steps_exec,
-                         'tile_steps_without_early_termination': live_tiles * spp,
+                         'kernel_variant': 'ray slots: every MMA row is a ray with its own cursor, refilled from a queue of live rays' if ray_slots
+                                           else '16x8 ray tiles marched in lock step',
+                         ('live_rays_per_frame' if ray_slots else 'live_tiles_per_frame'): live_tiles, 'tile_steps_executed_per_frame': steps_exec,
+                         'tile_steps_without_early_termination': (np.ceil(live_tiles / 128.0) if ray_slots else live_tiles) * spp,
                          'hbm': {'algorithmic_bytes_per_launch': samples_per_frame * BYTES_PER_SAMPLE,
                                  'algorithmic_GBps': samples_per_frame * band_frac * BYTES_PER_SAMPLE / kern_s / 1e9, 'peak_GBps': hbm,
                                  'note': 'SURVEY 8(d) prescribes 16,398 B/sample; the kernel does NOT move them (pre-blended table: 4x fewer '

@@ -37,6 +37,8 @@
 //   * training: the TRAIN variants additionally leave a per-sample record in HBM, and the same engine runs the
 //     data-gradient chains (MODE kBwd / kSkyBwd: transposed weights, LeakyReLU' from recorded sign words);
 //     render_train.cu holds the rest of the backward (compositing, table scatter, weight-gradient GEMMs).
+#include <stdlib.h>
+
 #include "rf_common.cuh"
 
 namespace rf {
@@ -161,10 +163,18 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo
 template <int PREC> __device__ __forceinline__ uint32_t one16() { return PREC == 1 ? 0x3F80u : 0x3C00u; }   // 1.0
 
 // ---- the kernel ------------------------------------------------------------------------------------
-template <int PREC, bool RAW5D, int MODE, bool TRAIN>
+// RAYQ (inference render only): the 128 MMA rows of the CTA are independent RAY SLOTS instead of the pixels of one 16x8 tile.
+// Every slot has its own (ray, sample step) cursor; when its ray is finished -- all S samples marched or, with early termination,
+// transmittance below the threshold -- the slot takes the next ray of a frame-wide queue of live rays (compacted by
+// prepass_rays_kernel, in tile order so that neighbouring slots stay spatially coherent).  Dead rays never occupy a row and a
+// tile no longer marches until its slowest ray is opaque: per C2 frame 4.4-4.7 M + ~0.5 M (one wasted step per terminated ray)
+// instead of 6.5-6.8 M samples are shaded (tools/ray_stats.py).  The CTA runs ONE open-ended "tile": the loop control of all four
+// roles is the early-termination mechanism below (stop_step decided by the epilogue two steps ahead).
+template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const Params p)
 {
+    static_assert(!RAYQ || (MODE == kRender && !TRAIN && !RAW5D), "ray slots: inference render over the pre-blended table");
     constexpr bool SKY = MODE == kSky, BWD = MODE == kBwd || MODE == kSkyBwd, SKYBWD = MODE == kSkyBwd;
     constexpr bool ONE_STEP = SKY || SKYBWD;     // per-RAY networks: every tile of the frame, one step per tile
     constexpr int NACT = Net<MODE>::NACT;
@@ -203,9 +213,16 @@ mlp_kernel(const Params p)
     // the render gradient chain has no dependency between the sample steps of a tile: there every (tile, step) is its own
     // work item (work_mult = S, one step each), which balances a few hundred tiles over 148 CTAs far better than whole tiles
     const int wmult = (MODE == kBwd && p.work_mult > 1) ? p.work_mult : 1;
-    const int n_work = ONE_STEP ? p.n_tiles : *p.n_live * wmult;
+    const int n_work = RAYQ ? (int)gridDim.x : (ONE_STEP ? p.n_tiles : *p.n_live * wmult);
     constexpr bool STATE = MODE == kRender;      // per-ray sampling state (gather -> epilogue hand-off) exists
     const int S = ONE_STEP ? 1 : p.S;
+    const int SL = RAYQ ? 0x3fffffff : S;        // steps of one work item: open-ended for ray slots (ended through sStop)
+    // ray-slot bookkeeping lives in the second state buffer (unused in this mode): per-step row info ring, done flags, cursors
+    uint4 *sInfo = reinterpret_cast<uint4 *>(sState + kStFloats * kRows);          // [4][128]: depth, interval, ray, code
+    int *sDone = reinterpret_cast<int *>(sInfo + 4 * kRows);                        // [2][128]: ray + 1 finished early at step (s & 1)
+    int2 *sCur = reinterpret_cast<int2 *>(sDone + 2 * kRows);                       // [128]: (ray, sample step) of every slot
+    volatile int *sExh = reinterpret_cast<volatile int *>(sCur + kRows);            // [4]: queue exhausted as of step (s & 3); [4] = seen
+    static_assert(4 * kRows * 16 + 2 * kRows * 4 + kRows * 8 + 32 <= kStFloats * kRows * 4, "ray-slot bookkeeping fits the second state buffer");
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -219,10 +236,15 @@ mlp_kernel(const Params p)
         tc05::mbar_init(&bars[B_EPIDONE], kEpiThreads);
         tc05::mbar_init(&bars[B_EPIDONE + 1], kEpiThreads);
         for (int i = 0; i < 2; i++) { tc05::mbar_init(&bars[B_STRDY + i], kRows); tc05::mbar_init(&bars[B_STFREE + i], kEpiThreads); }
+        tc05::mbar_init(&bars[B_COMP], kEpiThreads);
         tc05::fence_mbar_init();
     }
     if (warp == kLoaderWarp) tc05::tmem_alloc(tmem_slot, kTmemCols);
-    if (tid < 2) { sStop[tid] = kMaxS + 1; sVote[tid] = 0; }
+    if (tid < 2) { sStop[tid] = RAYQ ? 0x7fffffff : kMaxS + 1; sVote[tid] = 0; }
+    if constexpr (RAYQ) {
+        for (int i = tid; i < kRows; i += kThreads) { sCur[i] = make_int2(-1, 0); sDone[i] = 0; sDone[kRows + i] = 0; }
+        if (tid < 5) sExh[tid] = 0;
+    }
     // Work distribution over the persistent CTAs.  Static (work = blockIdx + it * grid) unless the launcher hands in a
     // counter: then the first tile is static and every further one is drawn from the counter by ONE thread of the
     // most-ahead role (gather thread 0) and published through a 4-deep shared ring; the other roles pick the it-th
@@ -231,7 +253,7 @@ mlp_kernel(const Params p)
     volatile int *sWork = reinterpret_cast<volatile int *>(smem + SM.sched);
     volatile int *sPub = sWork + 4;
     if (tid == 0) *sPub = 0;
-    const bool dyn = STATE && p.work_counter != nullptr;
+    const bool dyn = STATE && !RAYQ && p.work_counter != nullptr;
     auto fetch_work = [&](int it) -> int {
         if (!dyn) {
             const int w = (int)blockIdx.x + it * (int)gridDim.x;
@@ -268,7 +290,7 @@ mlp_kernel(const Params p)
         for (int it = 0;; it++) {
             const int work = fetch_work(it);
             if (work < 0) break;
-            const int tile = ONE_STEP ? work : p.tile_list[work / wmult];
+            const int tile = RAYQ ? 0 : (ONE_STEP ? work : p.tile_list[work / wmult]);
             const TileCoord tc = tile_coord(p, tile);
             const int buf = it & 1;
             const float *st = sState + buf * kStFloats * kRows;
@@ -286,7 +308,7 @@ mlp_kernel(const Params p)
             const long long ray = ((long long)tc.img * p.H + y) * p.W + x;
             uint32_t flags = in_img ? 4u : 0u, labs = 0;
             float dir0 = 0.0f, ori0 = 0.0f;
-            if (STATE) {
+            if (STATE && !RAYQ) {
                 tc05::mbar_wait(&bars[B_STRDY + buf], (it >> 1) & 1);
                 flags = __float_as_uint(st[kStFlags * kRows + row]);
                 labs = __float_as_uint(st[kStLab * kRows + row]);
@@ -302,10 +324,12 @@ mlp_kernel(const Params p)
             bool is_gnd = false;
 
             int s_done = S;           // steps actually executed for this tile
-            for (int s = 0; s < S; s++, n++) {
+            int skip_ray = -1;        // RAYQ: the ray this slot finished early at the previous step (its next sample is already in flight)
+            (void)skip_ray;
+            for (int s = 0; s < SL; s++, n++) {
                 if (ESTOP && s >= 2 && s >= sStop[buf]) { s_done = s; break; }
                 Sample sm{0.0f, 0.0f, 0};
-                if (STATE) {
+                if (STATE && !RAYQ) {
                     sm = sample_at(p, st, row, s, sFrac, ray);
                     is_gnd = is_gnd || (__fadd_rn(__fmul_rn(dir0, sm.depth), ori0) <= 1.0f);   // scenedreamer.py:354,380
                 }
@@ -459,6 +483,82 @@ mlp_kernel(const Params p)
                 if constexpr (SKY) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) outc[j] = c[j];
+                } else if constexpr (RAYQ) {
+                    // ---- compositing of ray slots (a10/a11): every row is its own ray at its own sample step ----
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const float sigma = (sSig[row] + sSig[kRows + row]) + sF[kFBsig];
+                    const uint4 info = sInfo[(s & 3) * kRows + row];            // published by the gather role for this step
+                    const int rq = (int)info.z;
+                    const uint32_t code = info.w;                                // bits 0-7 sample step, 8 first, 9 last, 11 sky_mask, 12 is_gnd (any sample)
+                    const int s_ray = (int)(code & 0xffu);
+                    const bool act = rq >= 0 && rq != skip_ray;
+                    if (act && (code & 0x100u)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) outc[j] = 0.0f;
+                        Wsum = 0.0f; Dsum = 0.0f; Dcomp = 0.0f; Eexcl = 0.0f;
+                    }
+                    float w = 0.0f;
+                    bool fin = false;
+                    if (act) {
+                        const float depth = __uint_as_float(info.x), nd = __uint_as_float(info.y);
+                        const float e = __fmul_rn(fmaxf(sigma, 0.0f), __fmul_rn(nd, p.dists_scale));      // mc_utils.py:155
+                        const float a = 1.0f - expf(-e);
+                        const float b = expf(-Eexcl);
+                        w = a * b;
+                        Eexcl = __fadd_rn(Eexcl, e);
+                        Wsum += w;
+                        {
+                            const float pr = __fmul_rn(w, depth);
+                            const float pe = __fmaf_rn(w, depth, -pr);
+                            const float sn = __fadd_rn(Dsum, pr);
+                            const float bv = __fsub_rn(sn, Dsum);
+                            Dcomp = __fadd_rn(Dcomp, __fadd_rn(__fadd_rn(__fsub_rn(Dsum, __fsub_rn(sn, bv)), __fsub_rn(pr, bv)), pe));
+                            Dsum = sn;
+                        }
+                        if (half == 0 && p.weights_out) p.weights_out[(long long)rq * S + s_ray] = w;
+                        fin = (code & 0x200u) || (p.early_T > 0.0f && expf(-Eexcl) < p.early_T);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float rgb = fminf(fmaxf(c[j], -1.0f), 1.0f) + 1.0f;                     // :407-408
+                        outc[j] = fmaf(w, rgb, outc[j]);
+                    }
+                    if (act && fin) {
+                        // ---- this slot's ray is finished: sky blend + output (scenedreamer.py:380-413) ----
+                        const bool nosky = !(code & 0x800u) || (code & 0x1000u);
+                        const float sky_w = 1.0f - Wsum;
+                        const float4 *skp = reinterpret_cast<const float4 *>((nosky ? p.sky_avg : p.sky + (long long)rq * kOutC) + half * 32);
+                        float4 *dst = reinterpret_cast<float4 *>(p.net_out + (long long)rq * kOutC + half * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 sk = __ldg(skp + q);
+                            float4 o;
+                            o.x = (outc[4 * q + 0] + sky_w * (fminf(fmaxf(sk.x, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                            o.y = (outc[4 * q + 1] + sky_w * (fminf(fmaxf(sk.y, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                            o.z = (outc[4 * q + 2] + sky_w * (fminf(fmaxf(sk.z, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                            o.w = (outc[4 * q + 3] + sky_w * (fminf(fmaxf(sk.w, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+                            dst[q] = o;
+                        }
+                        if (half == 0) {
+                            if (p.depth_out) p.depth_out[rq] = __fadd_rn(Dsum, Dcomp);
+                            if (p.total_weight) p.total_weight[rq] = Wsum;
+                        }
+                        skip_ray = (code & 0x200u) ? -1 : rq;
+                    }
+                    // early finishes are reported to the gather role (it replaces the ray two steps on); natural ends it sees itself
+                    if (half == 0) sDone[(s & 1) * kRows + row] = (act && fin && !(code & 0x200u)) ? rq + 1 : 0;
+                    // is the CTA done?  every slot idle or finished AND the queue was already empty when this step was built
+                    {
+                        const bool idle = !act || fin;
+                        const bool wall = __all_sync(0xffffffffu, idle);
+                        if (lane == 0 && !wall) sVote[s & 1] = 1;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (tid == 0) {
+                            if (sVote[s & 1] == 0 && sExh[s & 3] != 0 && sStop[0] > s + 2) sStop[0] = s + 2;
+                            sVote[s & 1] = 0;
+                        }
+                    }
+                    tc05::mbar_arrive(&bars[B_COMP]);                      // compositing of step s is complete (done flags visible)
                 } else {
                     // ---- compositing (a10/a11) ----
                     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -527,6 +627,8 @@ mlp_kernel(const Params p)
                 if (tid < kOutC)
                     p.sky_partial[(long long)tile * kOutC + tid] =
                         (red[tid] + red[kOutC + tid]) + (red[2 * kOutC + tid] + red[3 * kOutC + tid]);
+            } else if constexpr (RAYQ) {
+                if (tid == 0 && p.steps_done != nullptr) atomicAdd(p.steps_done, s_done);      // CTA steps of 128 slots each
             } else if constexpr (!BWD) {
                 if constexpr (ESTOP) {
                     // samples the tile did not shade: their weights are below early_T (reported as 0); the ground test of
@@ -583,10 +685,10 @@ mlp_kernel(const Params p)
             for (int it = 0;; it++) {
                 const int work = fetch_work(it);
                 if (work < 0) break;
-                const int tile = ONE_STEP ? work : p.tile_list[work / wmult];
+                const int tile = RAYQ ? 0 : (ONE_STEP ? work : p.tile_list[work / wmult]);
                 const TileCoord tc = tile_coord(p, tile);
                 const uint8_t *pack = p.pack + (long long)tc.img * p.pack_stride;
-                for (int s = 0; s < S; s++, n++) {
+                for (int s = 0; s < SL; s++, n++) {
                     if (ESTOP && s >= 2 && s >= sStop[it & 1]) break;
                     const uint32_t flip = kStepFlip & n;
 #pragma unroll
@@ -630,7 +732,7 @@ mlp_kernel(const Params p)
         const uint64_t dB0_128 = tc05::make_smem_desc(tc05::smem_u32(sRing), kFeat * 16, kSbo);
         for (int it = 0;; it++) {
             if (fetch_work(it) < 0) break;                              // warp-uniform
-            for (int s = 0; s < S; s++, n++) {
+            for (int s = 0; s < SL; s++, n++) {
                 if (ESTOP && s >= 2 && s >= sStop[it & 1]) break;       // warp-uniform (same shared word for every lane)
                 const uint32_t flip = kStepFlip & n;
                 const uint32_t nodd = n & 1u;
@@ -728,7 +830,7 @@ mlp_kernel(const Params p)
             }
             const int work = fetch_work(it);
             if (work < 0) break;
-            const int tile = ONE_STEP ? work : p.tile_list[work / wmult];
+            const int tile = RAYQ ? 0 : (ONE_STEP ? work : p.tile_list[work / wmult]);
             const TileCoord tc = tile_coord(p, tile);
             const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
             const bool valid = (y < p.H) && (x < p.W);
@@ -810,6 +912,145 @@ mlp_kernel(const Params p)
                         const uint32_t off = tc05::chunk_off(kRows, row, half * 4 + q);
                         *reinterpret_cast<uint4 *>(sHhi + off) = gh[q];
                         if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = gl[q];
+                    }
+                    tc05::fence_proxy_async_smem();
+                    tc05::mbar_arrive(&bars[B_FEAT]);
+                }
+            } else if constexpr (RAYQ) {
+                // ---- ray slots: this role owns the cursors; it refills a slot whose ray has marched all S samples, or was
+                //      reported finished by the compositing of two steps ago, from the frame-wide queue of live rays ----
+                float *st = sState;                                   // state buffer 0, private to this role in this mode
+                const int n_rays = __ldg(p.n_live);                   // live rays listed by prepass_rays_kernel
+                const int32_t *rlist = p.tile_list;                   // ... in tile order (ray index inside the image)
+                const float o0 = __ldg(p.cam_ori + 0), o1 = __ldg(p.cam_ori + 1), o2 = __ldg(p.cam_ori + 2);
+                float x5[5];
+                x5[3] = __fmul_rn(__fadd_rn(__ldg(p.genc + 0), 1.0f), 0.5f);   // grid.py:144 on dims 3,4
+                x5[4] = __fmul_rn(__fadd_rn(__ldg(p.genc + 1), 1.0f), 0.5f);
+                for (int s = 0;; s++, n++) {
+                    if (s >= 2) {
+                        tc05::mbar_wait_backoff(&bars[B_COMP], (uint32_t)(s - 2) & 1u, 32);    // done flags (and stop decision) of step s - 2
+                        if (s >= sStop[0]) break;
+                    }
+                    if (half == 0) {
+                        const int2 cur = sCur[row];
+                        int rq = cur.x, sr = cur.y + 1;
+                        const bool need = rq < 0 || sr >= S || (s >= 2 && sDone[(s & 1) * kRows + row] == rq + 1);
+                        if (need) {
+                            rq = -1;
+                            sr = 0;
+                            if (sExh[4] == 0) {
+                                const int idx = atomicAdd(p.work_counter, 1);
+                                if (idx < n_rays) rq = __ldg(rlist + idx);
+                                else sExh[4] = 1;
+                            }
+                            uint32_t code0 = 0;
+                            if (rq >= 0) {
+                                // per-ray sampling state (mc_utils.py:102-107, :141-143), as in the tile variant below
+                                float accu = 0.0f, cum = 0.0f, entry0 = 0.0f, prev_exit = 0.0f;
+                                uint32_t labs = 0;
+                                int32_t idl = 0;
+#pragma unroll
+                                for (int j = 0; j < kMaxM; j++) {
+                                    if (j < p.M) {
+                                        const int32_t id = __ldg(p.voxel_id + (long long)rq * p.M + j);
+                                        const float en = __ldg(p.depth2 + (long long)rq * p.M + j);
+                                        const float ex = __ldg(p.depth2 + ((long long)p.H * p.W + rq) * p.M + j);
+                                        float d = __fsub_rn(ex, en);
+                                        if (d != d) d = 0.0f;
+                                        accu = (j == 0) ? d : __fadd_rn(accu, d);
+                                        st[(kStAccu + j) * kRows + row] = accu;
+                                        if (j == 0) {
+                                            entry0 = en;
+                                            st[(kStHeads + 0) * kRows + row] = en;
+                                        } else {
+                                            const float dd = __fsub_rn(en, prev_exit);
+                                            cum = (j == 1) ? dd : __fadd_rn(cum, dd);
+                                            st[(kStHeads + j) * kRows + row] = __fadd_rn(cum, entry0);
+                                        }
+                                        prev_exit = ex;
+                                        const int lid = (id >= 0 && id < p.n_lut) ? __ldg(p.lut + id) : 0;
+                                        labs |= ((uint32_t)lid & 15u) << (4 * j);
+                                        idl = id;
+                                    }
+                                }
+                                st[kStTotal * kRows + row] = fminf(accu, p.sample_depth);
+                                st[kStLab * kRows + row] = __uint_as_float(labs);
+                                const float dx = __ldg(p.raydirs + (long long)rq * 3 + 0);
+                                st[(kStDir + 0) * kRows + row] = dx;
+                                st[(kStDir + 1) * kRows + row] = __ldg(p.raydirs + (long long)rq * 3 + 1);
+                                st[(kStDir + 2) * kRows + row] = __ldg(p.raydirs + (long long)rq * 3 + 2);
+                                // the ground test of the sky-leak logic looks at EVERY sample position (scenedreamer.py:380), also at
+                                // those an early finish will skip; per-sample outputs of skipped samples: weight 0, depth as sampled
+                                bool gnd = false;
+                                for (int k = 0; k < S; k++) {
+                                    const Sample sk = sample_at(p, st, row, k, sFrac, rq);
+                                    gnd = gnd || (__fadd_rn(__fmul_rn(dx, sk.depth), o0) <= 1.0f);
+                                    if (p.rdepth_out) p.rdepth_out[(long long)rq * S + k] = sk.depth;
+                                    if (p.weights_out) p.weights_out[(long long)rq * S + k] = 0.0f;
+                                }
+                                code0 = (idl == 0 ? 0x800u : 0u) | (gnd ? 0x1000u : 0u);
+                            }
+                            st[kStFlags * kRows + row] = __uint_as_float(code0);
+                        }
+                        sCur[row] = make_int2(rq, sr);
+                    }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    const int2 cur = sCur[row];
+                    const bool act = cur.x >= 0;
+                    const uint32_t labs = __float_as_uint(st[kStLab * kRows + row]);
+                    Sample sm{0.0f, 0.0f, 0};
+                    bool oob = true;
+                    uint4 fh[8], fl[8];
+                    if (act) {
+                        sm = sample_at(p, st, row, cur.y, sFrac, cur.x);
+                        const float d0 = st[(kStDir + 0) * kRows + row], d1 = st[(kStDir + 1) * kRows + row], d2 = st[(kStDir + 2) * kRows + row];
+                        const float pw[3] = {__fadd_rn(__fmul_rn(d0, sm.depth), o0), __fadd_rn(__fmul_rn(d1, sm.depth), o1),
+                                             __fadd_rn(__fmul_rn(d2, sm.depth), o2)};
+                        oob = false;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(pw[k], p.vdim[k]), 2.0f), 1.0f);
+                            x5[k] = __fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f);
+                            if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int level = half + 2 * i;
+                        float res[8];
+                        if (oob) {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) res[c] = 0.0f;
+                        } else {
+                            encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                        }
+                        split8<PREC>(res, fh[i], fl[i]);
+                    }
+                    const uint32_t label = (labs >> (4 * sm.idx)) & 15u;
+                    uint32_t oh[4] = {0u, 0u, 0u, 0u};
+                    {
+                        const int k = (int)label - 8 * half;
+                        if (k >= 0 && k < 8) oh[k >> 1] = one16<PREC>() << (16 * (k & 1));
+                        if (half == 1) oh[3] |= one16<PREC>() << 16;             // column 143
+                    }
+                    if (half == 0) {
+                        const uint32_t code = __float_as_uint(st[kStFlags * kRows + row]) | (uint32_t)cur.y | (cur.y == 0 ? 0x100u : 0u) |
+                                              (cur.y == S - 1 ? 0x200u : 0u);
+                        sInfo[(s & 3) * kRows + row] = make_uint4(__float_as_uint(sm.depth), __float_as_uint(sm.nd), (uint32_t)cur.x, code);
+                    }
+                    if (gt == 0) sExh[s & 3] = sExh[4];               // after the bar.sync: every fetch of this step has been made
+                    if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
+                    if (s >= 2 && s >= sStop[0]) break;                // the CTA ended before this step: drop the features
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t off = tc05::chunk_off(kRows, row, half + 2 * i);
+                        *reinterpret_cast<uint4 *>(sHhi + off) = fh[i];
+                        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = fl[i];
+                    }
+                    {
+                        const uint32_t off = tc05::chunk_off(kRows, row, kFeat / 8 + half);
+                        *reinterpret_cast<uint4 *>(sHhi + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                        if constexpr (X3) *reinterpret_cast<uint4 *>(sHlo + off) = make_uint4(0, 0, 0, 0);
                     }
                     tc05::fence_proxy_async_smem();
                     tc05::mbar_arrive(&bars[B_FEAT]);
@@ -993,6 +1234,54 @@ prepass_kernel(const Params p, int32_t *tile_list, int32_t *n_live)
     }
 }
 
+// ---- pre-pass of the ray-slot kernel: queue of live rays (tile order) + outputs of every ray that hits nothing ----
+__global__ void __launch_bounds__(kRows)
+prepass_rays_kernel(const Params p, int32_t *ray_list, int32_t *n_rays)
+{
+    __shared__ int s_cnt[4], s_base;
+    const int tile = blockIdx.x, row = threadIdx.x, warp = row >> 5, lane = row & 31;
+    const TileCoord tc = tile_coord(p, tile);
+    const int y = tc.y0 + (row >> 4), x = tc.x0 + (row & 15);
+    const bool valid = (y < p.H) && (x < p.W);
+    const long long ray = ((long long)tc.img * p.H + y) * p.W + x;
+    const bool live = valid && (__ldg(p.voxel_id + ray * p.M) != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (row == 0) {
+        const int tot = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+        s_base = tot ? atomicAdd(n_rays, tot) : 0;
+    }
+    __syncthreads();
+    if (live) {
+        int pre = __popc(bal & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; w++) pre += s_cnt[w];
+        ray_list[s_base + pre] = (int32_t)ray;
+        return;
+    }
+    if (!valid) return;
+    // sky-only ray: weights are zero, all samples sit at the camera origin (scenedreamer.py:350-354,376)
+    const bool is_gnd = __ldg(p.cam_ori + tc.img * 3) <= 1.0f;
+    const float4 *skp = reinterpret_cast<const float4 *>(is_gnd ? p.sky_avg + (long long)tc.img * kOutC : p.sky + ray * kOutC);
+    float4 *dst = reinterpret_cast<float4 *>(p.net_out + ray * kOutC);
+#pragma unroll
+    for (int q = 0; q < kOutC / 4; q++) {
+        const float4 sk = __ldg(skp + q);
+        float4 o;
+        o.x = (0.0f + 1.0f * (fminf(fmaxf(sk.x, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        o.y = (0.0f + 1.0f * (fminf(fmaxf(sk.y, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        o.z = (0.0f + 1.0f * (fminf(fmaxf(sk.z, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        o.w = (0.0f + 1.0f * (fminf(fmaxf(sk.w, -1.0f), 1.0f) + 1.0f)) - 1.0f;
+        dst[q] = o;
+    }
+    if (p.depth_out) p.depth_out[ray] = 0.0f;
+    if (p.total_weight) p.total_weight[ray] = 0.0f;
+    for (int s = 0; s < p.S; s++) {
+        if (p.weights_out) p.weights_out[ray * p.S + s] = 0.0f;
+        if (p.rdepth_out) p.rdepth_out[ray * p.S + s] = 0.0f;
+    }
+}
+
 // frame-global sky mean from the per-tile partial sums, fixed summation order (deterministic): 16 groups of 64
 // threads each add every 16th tile in order, then the 16 partial sums are added in order
 constexpr int kMeanGroups = 16;
@@ -1136,14 +1425,14 @@ int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels
     return SDB_OK;
 }
 
-template <int PREC, bool RAW5D, int MODE, bool TRAIN = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false>
 int launch_mlp(const Params &p, int grid, cudaStream_t st) {
     const size_t smem = smem_map(PREC != 0).total;
     cudaFuncAttributes fa;
-    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN>));
+    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>));
     if (fa.numRegs < kRegsLaunch) return SDB_EUNSUPPORTED;   // setmaxnreg pool would be too small: refuse rather than hang
-    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_kernel<PREC, RAW5D, MODE, TRAIN><<<grid, kThreads, smem, st>>>(p);
+    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ><<<grid, kThreads, smem, st>>>(p);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
@@ -1266,15 +1555,17 @@ static int64_t sdb_num_tiles(int32_t n_img, int32_t H, int32_t W) {
     return (int64_t)n_img * sdb_div_up(H, rf::kTileH) * sdb_div_up(W, rf::kTileW);
 }
 
-// workspace (int32 words): [0] live tiles, [1] tile-steps executed, [2] work counter, [3] -, [4 .. 4+tiles) live-tile list,
-// then 4 floats: the by-value camera origin (when sdb_render_params.d_cam_ori is NULL)
+// workspace (int32 words): [0] live tiles (tile kernel) / live rays (ray-slot kernel), [1] steps executed (x 128 rows), [2] work
+// counter / queue head, [3] 1 = the ray-slot kernel ran, [4 .. 4+tiles) live-tile list, then 4 floats: the by-value camera origin
+// (when sdb_render_params.d_cam_ori is NULL), then [R] the queue of live rays
 extern "C" int64_t sdb_render_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
     if (n_img <= 0 || H <= 0 || W <= 0) return 0;
-    return (sdb_num_tiles(n_img, H, W) + 8) * 4;
+    return (sdb_num_tiles(n_img, H, W) + 8 + (int64_t)n_img * H * W) * 4;      // ... + the live-ray queue of the ray-slot kernel
 }
 
 namespace rf {
 __global__ void set_cam_kernel(float *dst, float a, float b, float c) { dst[0] = a; dst[1] = b; dst[2] = c; }
+__global__ void set_flag_kernel(int32_t *dst) { *dst = 1; }
 }
 
 extern "C" int64_t sdb_sky_workspace_bytes(int32_t n_img, int32_t H, int32_t W) {
@@ -1400,6 +1691,26 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
     {
         const int rc = stage_cam_ori(sp, p, st);
         if (rc != SDB_OK) return rc;
+    }
+    // Ray slots (mlp_kernel<.., RAYQ>): one image over the pre-blended table -- what inference renders.  SDB_RAY_SLOTS=0 keeps the
+    // tile kernel (diagnostics / comparison).
+    const char *env_rq = getenv("SDB_RAY_SLOTS");
+    const bool rayq = !p.raw5d && p.n_img == 1 && !(env_rq && atoi(env_rq) == 0);
+    if (rayq) {
+        int32_t *ray_list = ws + 8 + p.n_tiles;
+        SDB_CUDA(cudaMemsetAsync(ws, 0, 16, st));
+        prepass_rays_kernel<<<p.n_tiles, kRows, 0, st>>>(p, ray_list, ws);
+        SDB_CHECK_LAUNCH();
+        p.tile_list = ray_list;
+        const int grid = sdb_num_sms();
+        int rc;
+        if (sp->precision == 0) rc = launch_mlp<0, false, kRender, false, true>(p, grid, st);
+        else if (sp->precision == 1) rc = launch_mlp<1, false, kRender, false, true>(p, grid, st);
+        else rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
+        if (rc != SDB_OK) return rc;
+        set_flag_kernel<<<1, 1, 0, st>>>(ws + 3);
+        SDB_CHECK_LAUNCH();
+        return SDB_OK;
     }
     {
         const int rc = launch_prepass(p, ws, st);

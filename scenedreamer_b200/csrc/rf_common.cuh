@@ -144,7 +144,7 @@ constexpr int kStFloats = 2 * kMaxM + 6;
 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = 4, B_FEAT = 8, B_HFREE, B_CHUNK, B_ACC = B_CHUNK + 16, B_OUTRDY, B_EPIDONE,
-       B_STRDY = B_EPIDONE + 2, B_STFREE = B_STRDY + 2, B_COUNT = B_STFREE + 2 };
+       B_STRDY = B_EPIDONE + 2, B_STFREE = B_STRDY + 2, B_COMP = B_STFREE + 2, B_COUNT = B_COMP + 1 };
 constexpr int kBarSlots = 40;
 static_assert(B_COUNT <= kBarSlots, "barrier table");
 

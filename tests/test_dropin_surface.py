@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     of, os_, ou = oracle.camera_frame([-45.25, 204.8, -409.6], [1, 0, 0])
     assert list(f) == of.tolist() and list(s) == os_.tolist() and list(u) == ou.tolist()
     assert L.sdb_mlp_pack_bytes(2) > L.sdb_mlp_pack_bytes(0) > 700000
-    assert L.sdb_render_workspace_bytes(1, 570, 990) == (72 * 62 + 8) * 4      # counters, tile list, by-value camera slot
+    assert L.sdb_render_workspace_bytes(1, 570, 990) == (72 * 62 + 8 + 570 * 990) * 4      # counters, tile list, camera slot, live-ray queue
 
 
 def test_render_params_struct_matches_header():
