@@ -429,7 +429,7 @@ def run_gpu_arm(args):
         kern_s = tot_kern_ms * 1e-3 / args.steps
         # executed tensor work: live 16x8 ray tiles x steps x 128 rows, MMAs as issued (x3 split: 3 per product)
         # (rank 0 alone: no collective in here)
-        wss = [fr.frame(cams[(k if strong else k * world_size) % len(cams)], rows=rows)['workspace'][:8].view(torch.int32).cpu()   # (strong: first band only)
+        wss = [fr.frame(cams[(k if strong else k * world_size) % len(cams)], rows=rows)['workspace'][:16].view(torch.int32).cpu()   # (strong: first band only)
                for k in range(min(args.steps, 8))]
         live_tiles = float(np.mean([int(w[0]) for w in wss]))         # live 16x8 tiles (tile kernel) or live RAYS (ray-slot kernel)
         steps_exec = float(np.mean([int(w[1]) for w in wss]))         # steps of 128 rows executed (after early termination)
