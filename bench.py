@@ -9,14 +9,19 @@ scene_size 1024, cam_mode 0, pad 30 -> 570x990 rays raycast + shaded:
     a1  ray/voxel DDA                        (sdb_ray_voxel_intersection_perspective_ex, exact empty-space flight)
     a9  sky branch: PE + SKYMLP + frame mean  (sdb_sky_forward: same tcgen05 engine, per ray)
     a2-a8, a10-a12 fused per-pixel kernel    (sdb_render_rays_forward: tcgen05 MLP, hash gather, compositing)
+    f1  RenderCNN + tanh (e2e only)          (sdb_cnn_forward: tcgen05 implicit-GEMM convolution over the whole padded frame)
 Credit = OUTPUT samples: 518,400 px x 24 = 12,441,600 samples per frame (padding rays are overhead).
-`value` / `e2e` are the product default (ray tiles stop once every live ray's transmittance is < 1e-7);
-`value_exact_march` is the same measurement with that early termination off (every sample of every live
-tile shaded) -- the two differ by less than 2e-7 in the rendered features.
-Each step renders a different pose of the 40-frame cam_mode-0 trajectory and L2 is flushed between
-steps (256 MiB memset outside the per-step CUDA events).
-Multi-GPU (weak scaling): every rank renders its own frames (frame f -> rank f mod N); the finished
-per-pixel scalar maps (depth, opacity) are all-gathered once per step over NCCL.
+`value` is the per-pixel path a1-a12 with inputs resident; `e2e` goes from a host pose to the RGB image on
+the host (RenderCNN included).  Both are the product default: the fused kernel runs its rows as RAY SLOTS -- a ray leaves its
+row once its transmittance is < 1e-7 and the next live ray of the frame takes the row; `value_exact_march` is the same
+measurement with that early termination off (every sample of every live ray shaded) -- the two differ by less than 2e-7 in the
+rendered features.  `samples_shaded_per_frame` says how many of the credited samples were actually evaluated.
+Each step renders a different pose of the 40-frame trajectory and L2 is flushed between steps (256 MiB memset outside the
+per-step CUDA events).
+Multi-GPU: weak scaling by default (every rank renders its own frames, frame f -> rank f mod N; the finished frames are
+all-gathered once per step over NCCL); `--mode strong` splits ONE frame into two row bands per rank.
+Extra keys at N=1: `c4` (2160x3840x40), `c5_train_step` (bench_train.py), `reference_cuda_b200` (the reference renderer itself
+on this GPU, and the same Python with dropin/ on the path), `cpu_baseline`.
 """
 import argparse
 import json
@@ -485,7 +490,7 @@ def run_gpu_arm(args):
                        'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
                        'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)',
                        'early_termination': ('off' if args.no_early_stop else
-                                             'ray tiles stop once every live ray has transmittance < %g (skipped samples carry less than '
+                                             'a ray leaves its MMA row once its transmittance is < %g (skipped samples carry less than '
                                              'that compositing weight; credited like sky-only rays); --no-early-stop marches everything'
                                              % render.EARLY_STOP_T),
                        'host_affinity': 'each rank pinned to the CPUs of its GPU (NVML affinity), %s CPUs for rank 0' % pinned_cpus},
@@ -498,8 +503,9 @@ def run_gpu_arm(args):
                              'differ by the RenderCNN time (`rendercnn_ms`)') if e2e_image else
                             'per step: pose (by value) -> DDA -> sky -> fused render of this rank\'s row band -> band maps gathered -> host'},
             'gpu_launches': launches,
-            'gpu_launches_note': 'counted by the library (sdb_launch_count) over the timed region on rank 0: per step dda_perspective, '
-                                 'mlp_kernel<sky>, sky_mean, set_cam, prepass, mlp_kernel<render> (all ours)',
+            'gpu_launches_note': 'counted by the library (sdb_launch_count) over the timed (e2e) region on rank 0: per step dda_perspective, '
+                                 'mlp_kernel<sky>, sky_mean, set_cam, prepass_rays, mlp_kernel<render, ray slots>, set_flag, pack_input, '
+                                 '7 x conv_kernel (all ours; torch adds a few slicing / copy kernels for the crop and the gather)',
             'roofline': {'bound': 'tensor', 'achieved': alg_tflops, 'peak': tf, 'unit': 'TFLOP/s', 'frac': alg_tflops / tf,
                          'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_unit': 'B of DRAM per launch (ncu dram__bytes)',
                          'traffic_source': (traffic or {}).get('source'),

@@ -65,7 +65,7 @@ def sass_census(prefix):
 
 if __name__ == '__main__':
     prefix = sys.argv[1] if len(sys.argv) > 1 else 'r02'
-    summarise('render', prefix, 'python bench.py --steps 2 --warmup 3 --no-cpu --no-extras  (-k regex:mlp_kernel -s 9 -c 1)')
+    summarise('render', prefix, 'python bench.py --steps 2 --warmup 3 --no-cpu --no-extras  (-k regex:mlp_kernel -s 9 -c 1; the ray-slot kernel mlp_kernel<2,0,0,0,1>)')
     summarise('conv', prefix, 'python bench.py ...  (-k regex:conv_kernel -s 8 -c 1: conv2a, 3x3 256->256, fp16x3)')
     summarise('dda', prefix, 'python bench.py ...  (-k regex:dda_perspective -s 3 -c 1)')
     summarise('wgrad', prefix, 'python bench_train.py --steps 2 --warmup 3 --no-composition  (-k regex:wgrad_kernel -s 2 -c 1)')
