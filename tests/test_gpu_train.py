@@ -9,12 +9,16 @@ Tolerances (no gradient tolerance is stated by the north star; these are the one
     relative per product) and the weight-gradient GEMMs take bf16 operands (2^-9 per element,
     fp32 accumulation over >= 10^4 samples); observed errors are printed per tensor.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import oracle
 from scenedreamer_b200 import ops, render, synth
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 DEV = 'cuda:0'
@@ -206,3 +210,61 @@ def test_adam_step_hook_takes_over_tagged_table_only():
     assert float(opt.state[table]['step']) == 3.0 and set(opt.state[table]) == {'step', 'exp_avg', 'exp_avg_sq'}
     sd = opt.state_dict()                                              # interchangeable with a plain Adam
     opt_r.load_state_dict(sd)
+
+
+def test_c5_size_gradients_vs_unfused_composition(golden_ops):
+    """BASELINE C5 size: one 262x262 view, 24 samples/ray, stratified sampling (record 6.9 GB, workspace 7.1 GB).  The fused
+    forward(record) + backward against the UNFUSED composition on the same GPU (torch fp32 autograd for MLP / compositing / sky
+    on cuBLAS + the reference's own GridEncoder autograd.Function over the stand-alone grid kernels): output and every gradient."""
+    import sys
+    import bench_train
+    from oracle import refgen
+    ref_py = refgen.reference_python_root()
+    if ref_py is None:
+        pytest.skip('reference Python not staged (gridencoder package)')
+    for pth in (os.path.join(ROOT, 'dropin'), ref_py):
+        if pth not in sys.path:
+            sys.path.append(pth)
+    from gridencoder import GridEncoder
+    world = synth.SyntheticVoxelWorld(1024, 3407)
+    pose = synth.eval_camera_poses(world, maxstep=40, pattern=0)[5]
+    o, d, u, f, c, res = synth.frame_camera(world, pose, (256, 256), 6)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(world.voxel_t.to(DEV), o, d, u, f, c, res, 6)
+    vid, dep, rd, ori = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0), o.unsqueeze(0).to(DEV)
+    P0 = oracle.make_params(seed=3, stress=True)
+    g = torch.Generator().manual_seed(8888)
+    z0 = oracle.style_mlp(torch.randn(1, 128, generator=g), P0)
+    genc0 = torch.tanh(torch.randn(1, 2, generator=g))
+    lut = render.reduced_label_lut(golden_ops['mc2reduced_lut']).to(DEV)
+    _, pls = oracle.grid_offsets()
+    H = W = 262
+    uni = torch.rand(1, H, W, 25, 1, generator=g).to(DEV)
+    G = torch.randn(1, H, W, 64, generator=g).to(DEV)
+    vdims = [float(v) for v in world.voxel_t.shape]
+
+    def leaves():
+        P = {k: v.to(DEV).clone().requires_grad_(True) for k, v in P0.items()}
+        return P, z0.to(DEV).clone().requires_grad_(True), genc0.to(DEV).clone().requires_grad_(True)
+    P, z, genc = leaves()
+    out = render.render_rays_train(P, vid, dep, rd, ori, z, genc, vdims, lut, pls, num_samples=24, uniforms=uni)
+    (out['net_out'] * G).sum().backward()
+    Pc, zc, gc = leaves()
+    ge = GridEncoder(input_dim=5, num_levels=16, level_dim=8, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048).to(DEV)
+    ge.embeddings = torch.nn.Parameter(Pc['hash_encoder.embeddings'].detach().clone())
+    ref_out = bench_train.composition_step(Pc, ge, vid, dep, rd, ori, zc, gc, vdims, lut, uni, G)
+    Pc['hash_encoder.embeddings'].grad = ge.embeddings.grad
+    torch.cuda.synchronize()
+    e_out = float((out['net_out'].detach() - ref_out.detach()).abs().max())
+    print('C5 size (262x262x24): forward max|fused - composition| %.3e' % e_out)
+    assert e_out <= 1e-3
+    worst = 0.0
+    for name in list(P0.keys()) + ['z', 'global_enc']:
+        a = (z.grad if name == 'z' else genc.grad if name == 'global_enc' else P[name].grad)
+        b = (zc.grad if name == 'z' else gc.grad if name == 'global_enc' else Pc[name].grad)
+        if name.startswith('style_net') or b is None:
+            continue
+        rel = float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+        worst = max(worst, rel)
+        assert rel <= 1e-2, (name, rel)
+    print('C5 size: worst parameter-gradient rel-L2 vs the unfused composition %.3e' % worst)
+    render.clear_scratch()
