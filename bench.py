@@ -269,7 +269,10 @@ def run_gpu_arm(args):
     world_size = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    pinned_cpus = pin_rank_to_gpu_numa(local)
+    # one process per GPU: pin each rank to its GPU's NUMA node (8 unpinned ranks migrate across sockets: round 1's straggler).  A
+    # single process is left to the OS scheduler -- on a shared host the node-local cores may be the busy ones, and the host-bound
+    # legs measured 3-5x slower when confined to them.
+    pinned_cpus = pin_rank_to_gpu_numa(local) if world_size > 1 else None
     torch.set_num_threads(max(1, min(8, (pinned_cpus or os.cpu_count() or 8) // max(1, world_size))))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -493,7 +496,7 @@ def run_gpu_arm(args):
                                              'a ray leaves its MMA row once its transmittance is < %g (skipped samples carry less than '
                                              'that compositing weight; credited like sky-only rays); --no-early-stop marches everything'
                                              % render.EARLY_STOP_T),
-                       'host_affinity': 'each rank pinned to the CPUs of its GPU (NVML affinity), %s CPUs for rank 0' % pinned_cpus},
+                       'host_affinity': ('each rank pinned to the CPUs of its GPU (NVML affinity), %s CPUs for rank 0' % pinned_cpus) if world_size > 1 else 'not pinned (single process)'},
             'e2e': {'value': e2e, 'unit': 'Msamples/s', 'h2d_bytes_per_step': int(pose_pinned[0].numel() * 4),
                     'd2h_bytes_per_step': int((host_rgb if e2e_image else host_out).numel() * 4), 'ms_per_step': tot_ms / args.steps,
                     'result': 'RGB image [3,%d,%d] fp32' % out_hw if e2e_image else 'depth + opacity maps',
@@ -542,7 +545,12 @@ def extra_legs(args):
     ex = {}
 
     def run(cmd, timeout):
-        o = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        def unpin():                                   # children must not inherit a CPU mask
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))
+            except OSError:
+                pass
+        o = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, preexec_fn=unpin)
         if o.returncode != 0:
             raise RuntimeError((o.stderr or o.stdout)[-300:])
         return o
