@@ -463,17 +463,8 @@ def run_gpu_arm(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.precision)
         extras = {}
-        cpu = None
-        if world_size == 1 and not args.no_cpu:
-            # the CPU leg runs in a clean subprocess (its own OpenMP settings, no CUDA context)
-            try:
-                o = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '12',
-                                    '--warmup', '1'], capture_output=True, text=True, timeout=600)
-                cpu = json.loads(o.stdout.strip().splitlines()[-1])['cpu_baseline']
-            except Exception as e:          # noqa: BLE001
-                cpu = {'error': repr(e)[:200]}
-        if world_size == 1 and not args.no_extras and args.workload == 'c2':
-            extras = extra_legs(args)
+        cpu = getattr(args, 'cpu_result', None)
+        extras = getattr(args, 'extras_result', None) or {}
         line = {
             'metric': 'rendered Msamples/sec at 960x540x24spp', 'value': value, 'unit': 'Msamples/s',
             'mpix_per_s': value / spp, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -613,6 +604,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback '
                          '(use --impl reference for the CPU baseline)')
+    # The legs reported NEXT TO the headline at N=1 run first, each in its own process, before this process creates its CUDA
+    # context: they are host-bound in places (the reference's tile loop, autograd) and measured 3-5x slower as children of a
+    # process that already held the GPU and a CPU mask.
+    if int(os.environ.get('WORLD_SIZE', '1')) == 1:
+        if not args.no_cpu:
+            try:
+                o = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '12', '--warmup', '1'],
+                                   capture_output=True, text=True, timeout=600)
+                args.cpu_result = json.loads(o.stdout.strip().splitlines()[-1])['cpu_baseline']
+            except Exception as e:          # noqa: BLE001
+                args.cpu_result = {'error': repr(e)[:200]}
+        if not args.no_extras and args.workload == 'c2':
+            args.extras_result = extra_legs(args)
     run_gpu_arm(args)
 
 
