@@ -230,3 +230,37 @@ def test_early_termination_error_bound_and_savings(scene, lut, golden_ops):
               % (T, 100.0 * float(skipped.float().sum() / max(1.0, float((exact['weights'] != 0).sum()))),
                  float((d['net_out'] - exact['net_out']).abs().max())))
     assert bool(((outs[1e-3]['weights'] == 0) & (exact['weights'] != 0)).any())       # something was skipped
+
+
+def test_ray_slots_equal_the_tile_kernel(scene, lut, golden_ops, monkeypatch):
+    """The ray-slot kernel (every MMA row a ray with its own cursor, the inference default) against the tile kernel
+    (SDB_RAY_SLOTS=0): bit-identical with early termination off -- every ray's arithmetic is the same, only its row and
+    its companions differ -- and within the termination threshold otherwise, with fewer steps executed."""
+    P = oracle.make_params(seed=21, stress=True)
+    P['render_net.fc_sigma.bias'] = torch.full((1,), 60.0)
+    g = torch.Generator().manual_seed(8888)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)
+    genc = torch.tanh(torch.randn(1, 2, generator=g))
+    _, pls = oracle.grid_offsets()
+    r = render.FusedPerPixelRenderer(to_dev(P), scene['world'].voxel_t.shape, lut, pls)
+    args = (scene['vid'], scene['dep'], scene['rd'], scene['o'].unsqueeze(0), z.to(DEV), genc.to(DEV))
+    keys = ('net_out', 'depth', 'total_weight', 'weights', 'rand_depth')
+    res = {}
+    for T in (0.0, None):
+        r.early_stop = T
+        for variant in ('1', '0'):
+            monkeypatch.setenv('SDB_RAY_SLOTS', variant)
+            o = r.forward(*args, want_samples=True)
+            torch.cuda.synchronize()
+            ws = o['workspace'][:16].view(torch.int32).cpu()
+            assert int(ws[3]) == int(variant)
+            res[(T, variant)] = ({k: o[k].clone() for k in keys}, int(ws[1]))
+    for k in keys:
+        assert torch.equal(res[(0.0, '1')][0][k], res[(0.0, '0')][0][k]), k
+    a, b = res[(None, '1')][0], res[(None, '0')][0]
+    assert float((a['net_out'] - b['net_out']).abs().max()) <= 5 * render.EARLY_STOP_T
+    assert torch.equal(a['rand_depth'], b['rand_depth'])
+    steps_rq, steps_tile = res[(None, '1')][1], res[(None, '0')][1]
+    print('steps of 128 rows: ray slots %d, tiles %d (early termination on); %d / %d with it off'
+          % (steps_rq, steps_tile, res[(0.0, '1')][1], res[(0.0, '0')][1]))
+    assert steps_rq < steps_tile
