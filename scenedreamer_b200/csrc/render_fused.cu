@@ -1702,7 +1702,9 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         prepass_rays_kernel<<<p.n_tiles, kRows, 0, st>>>(p, ray_list, ws);
         SDB_CHECK_LAUNCH();
         p.tile_list = ray_list;
-        const int grid = sdb_num_sms();
+        // one CTA per SM, but never more CTAs than 128-ray groups the frame could fill (small frames)
+        const long long groups = ((long long)p.H * p.W + kRows - 1) / kRows;
+        const int grid = groups < sdb_num_sms() ? (int)groups : sdb_num_sms();
         int rc;
         if (sp->precision == 0) rc = launch_mlp<0, false, kRender, false, true>(p, grid, st);
         else if (sp->precision == 1) rc = launch_mlp<1, false, kRender, false, true>(p, grid, st);
