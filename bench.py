@@ -246,6 +246,18 @@ class FrameRenderer:
         sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
         return vid, dep, rd, sky, sky_avg, res[0] * res[1]
 
+    def cast_bands(self, cam, bands):
+        """Several row bands of one frame as ONE virtual image (rays are independent: the fused kernel only sees a list of them):
+        one raycast per band, their outputs concatenated, one sky launch -- and later one render launch -- over all of them."""
+        o, d, u, f, c, res = cam
+        parts = [self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, [c[0] - y0, c[1]], [y1 - y0, res[1]], 6)
+                 for (y0, y1) in bands if y1 > y0]
+        vid = torch.cat([p_[0] for p_ in parts], 0).unsqueeze(0)
+        dep = torch.cat([p_[1] for p_ in parts], 1).unsqueeze(0)
+        rd = torch.cat([p_[2] for p_ in parts], 0).unsqueeze(0)
+        sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
+        return vid, dep, rd, sky, sky_avg, vid.shape[1] * vid.shape[2]
+
     def shade(self, cam, rays, sky_avg, events=None):
         vid, dep, rd, sky = rays[:4]
         if events is not None:
@@ -289,11 +301,12 @@ def run_gpu_arm(args):
     # pinned host copies of the per-frame inputs (camera pose) and of the per-frame result
     pose_pinned = [torch.stack([c[0], c[1], c[2]]).pin_memory() for c in cams]
     res = cams[0][5]
-    bands = [b for b in sharding.paired_bands(res[0], rank, world_size)] if strong else None     # two bands per rank (top + mirrored bottom)
+    bands = sharding.cyclic_bands(res[0], rank, world_size) if strong else None      # thin bands, band b -> rank b mod N
     rows = bands[0] if strong else None
     band_h = sum(b[1] - b[0] for b in bands) if strong else res[0]
-    band_cap = sharding.tile_rows_for_rank(res[0], 0, 2 * world_size)[1] if strong else res[0]  # tallest band (band 0)
-    host_out = torch.empty(2, (2 * band_cap * world_size) if strong else res[0], res[1], dtype=torch.float32).pin_memory()
+    band_cap = 16 if strong else res[0]                                              # rows of one band slot (2 tile rows)
+    n_slots = len(bands) if strong else 1
+    host_out = torch.empty(2, (n_slots * band_cap * world_size) if strong else res[0], res[1], dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     L = _lib.lib()
 
@@ -311,24 +324,20 @@ def run_gpu_arm(args):
         return (allp[:, :64].sum(0) / allp[:, 64].sum()).reshape(1, 64)
 
     def strong_step(cam, kev):
-        """ONE frame over all ranks: this rank's two bands -> [2, 2 * band_cap, W] maps (bands padded to the tallest)."""
-        rays = [fr.cast(cam, b) for b in bands if b[1] > b[0]]
-        avg = global_sky_mean([(r[4], r[5]) for r in rays])
-        outs = []
-        if kev is not None:
-            kev[0].record()
-        for r in rays:
-            outs.append(fr.shade(cam, r, avg))
-        if kev is not None:
-            kev[1].record()
-        parts, i = [], 0
+        """ONE frame over all ranks: this rank's bands -> [2, n_slots * band_cap, W] maps (every slot padded to band_cap rows)."""
+        rays = fr.cast_bands(cam, bands)
+        avg = global_sky_mean([(rays[4], rays[5])])
+        out = fr.shade(cam, rays, avg, kev)
+        got = torch.stack([out['depth'][0], out['total_weight'][0]])          # [2, rows of this rank's bands, W], band after band
+        parts, y = [], 0
         for b in bands:
             h = b[1] - b[0]
             m = torch.zeros(2, band_cap, res[1], device=dev)
             if h > 0:
-                m[:, :h] = torch.stack([outs[i]['depth'][0], outs[i]['total_weight'][0]])
-                i += 1
+                m[:, :h] = got[:, y:y + h]
+                y += h
             parts.append(m)
+        outs = [out]
         return torch.cat(parts, 1), (outs[-1] if outs else None)
 
     host_rgb = torch.empty(3, out_hw[0], out_hw[1], dtype=torch.float32).pin_memory()
@@ -352,9 +361,9 @@ def run_gpu_arm(args):
             allm = sharding.gather_frames(maps.unsqueeze(0))         # THE collective of the path: finished frames / bands of every rank
             if cev is not None:
                 cev[1].record()
-            if strong:                                               # rank r holds bands r and 2N-1-r: back into frame order
-                a = allm.reshape(world_size, 2, 2, band_cap, res[1])
-                maps = torch.cat([a[:, :, 0], a[:, :, 1].flip(0)], 0).permute(1, 0, 2, 3).reshape(2, -1, res[1])
+            if strong:                                               # slot j of rank r is band j * N + r: back into frame order
+                a = allm.reshape(world_size, 2, n_slots, band_cap, res[1])
+                maps = a.permute(1, 2, 0, 3, 4).reshape(2, -1, res[1])
         if want_host:                                                # D2H of the step's result
             if to_image:
                 host_rgb.copy_(maps, non_blocking=True)
@@ -480,7 +489,7 @@ def run_gpu_arm(args):
                       'fp16x3': 'f16x3 split (f32-grade), f32 accumulate'}[args.precision] + '; table/compositing f32',
             'data': 'synthetic',
             'config': {'workload': wl_name + ', pad %d (%dx%d rays cast+shaded, %d px credited); ' % (PAD, res[0], res[1], out_hw[0] * out_hw[1]) +
-                                   ('ONE frame per step split into 2 row bands per GPU (band r and its mirror 2N-1-r)' if strong else 'one frame per GPU per step'),
+                                   ('ONE frame per step in 16-row bands dealt round-robin to the GPUs' if strong else 'one frame per GPU per step'),
                        'precision': args.precision, 'l2': 'flushed between steps (256 MiB memset) + a different pose each step',
                        'table': 'per-scene pre-blended 3-D table (8 corners/level)', 'sky_mlp': 'tcgen05 engine (sdb_sky_forward)',
                        'early_termination': ('off' if args.no_early_stop else
@@ -521,7 +530,7 @@ def run_gpu_arm(args):
             'per_rank_ms': {'columns': ['e2e_step', 'dda_sky', 'fused_kernel_window', 'collective_incl_wait', 'e2e_step_max', 'cpus_in_affinity'],
                             'rows': table},
             'rendercnn_ms': cnn_ms,
-            'collective': {'op': 'all_gather_into_tensor(%s)' % ('RGB frames in the e2e loop, depth+opacity maps in the device-only loops' if e2e_image else 'row bands of depth+opacity maps'), 'bytes_per_rank': int(2 * 2 * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
+            'collective': {'op': 'all_gather_into_tensor(%s)' % ('RGB frames in the e2e loop, depth+opacity maps in the device-only loops' if e2e_image else 'row bands of depth+opacity maps'), 'bytes_per_rank': int(2 * n_slots * band_cap * res[1] * 4) if strong else int(host_out.numel() * 4),
                            'ms_per_step_incl_wait_for_slowest_rank': float(np.mean(coll_ms))} if world_size > 1 else None,
         }
         line.update(extras)

@@ -51,3 +51,20 @@ def paired_bands(H, rank, world_size, tile_h=8):
     first = tile_rows_for_rank(H, rank, 2 * world_size, tile_h)
     second = tile_rows_for_rank(H, 2 * world_size - 1 - rank, 2 * world_size, tile_h)
     return [first, second]
+
+
+def cyclic_bands(H, rank, world_size, band_tiles=2, tile_h=8):
+    """Single-frame sharding, balanced without knowing the cost profile: the frame is cut into thin bands of `band_tiles`
+    tile rows and band b goes to rank b mod world_size.  (The cost of a row is neither flat nor monotonic -- sky at the top
+    is free, near ground at the bottom terminates within a few samples, the horizon in the middle is the expensive part -- so
+    contiguous or mirrored bands leave some ranks idle: 0.1 vs 3.1 ms of kernel time at 8 GPUs.)
+    Returns the rank's bands as (y0, y1) in frame order; every rank gets the same NUMBER of slots, trailing ones may be empty."""
+    bh = band_tiles * tile_h
+    n_bands = (H + bh - 1) // bh
+    per_rank = (n_bands + world_size - 1) // world_size
+    out = []
+    for j in range(per_rank):
+        b = j * world_size + rank
+        y0 = min(H, b * bh)
+        out.append((y0, min(H, y0 + bh)))
+    return out

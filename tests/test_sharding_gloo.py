@@ -67,3 +67,14 @@ def test_paired_bands_cover_the_frame_once():
             # rank r owns band r and its mirror: top + bottom
             first, second = sharding.paired_bands(H, 0, world)
             assert first[0] == 0 and (second[1] == H or second[1] == second[0])
+
+
+def test_cyclic_bands_cover_the_frame_once():
+    for world in (1, 2, 4, 8):
+        for H in (570, 2190, 64, 9):
+            per = [sharding.cyclic_bands(H, r, world) for r in range(world)]
+            assert len({len(p) for p in per}) == 1                      # same number of slots on every rank (equal-size gather)
+            bands = sorted(b for p in per for b in p if b[1] > b[0])
+            assert bands[0][0] == 0 and bands[-1][1] == H
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(len(bands) - 1))
+            assert all(b[0] % 8 == 0 and b[1] - b[0] <= 16 for b in bands)
