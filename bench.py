@@ -247,16 +247,19 @@ class FrameRenderer:
         return vid, dep, rd, sky, sky_avg, res[0] * res[1]
 
     def cast_bands(self, cam, bands):
-        """Several row bands of one frame as ONE virtual image (rays are independent: the fused kernel only sees a list of them):
-        one raycast per band, their outputs concatenated, one sky launch -- and later one render launch -- over all of them."""
+        """Several equally spaced row bands of one frame as ONE virtual image (rays are independent: the fused kernel only sees a
+        list of them): one banded raycast, one sky launch -- and later one render launch -- over all of them."""
         o, d, u, f, c, res = cam
-        parts = [self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, [c[0] - y0, c[1]], [y1 - y0, res[1]], 6)
-                 for (y0, y1) in bands if y1 > y0]
-        vid = torch.cat([p_[0] for p_ in parts], 0).unsqueeze(0)
-        dep = torch.cat([p_[1] for p_ in parts], 1).unsqueeze(0)
-        rd = torch.cat([p_[2] for p_ in parts], 0).unsqueeze(0)
+        bands = [b for b in bands if b[1] > b[0]]
+        rows = sum(y1 - y0 for (y0, y1) in bands)
+        bh = bands[0][1] - bands[0][0]
+        stride = (bands[1][0] - bands[0][0]) if len(bands) > 1 else bh
+        assert all(b[0] == bands[0][0] + k * stride for k, b in enumerate(bands)) and all(b[1] - b[0] == bh for b in bands[:-1])
+        vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, [rows, res[1]], 6,
+                                                                   band=(bands[0][0], bh, stride))
+        vid, dep, rd = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0)
         sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
-        return vid, dep, rd, sky, sky_avg, vid.shape[1] * vid.shape[2]
+        return vid, dep, rd, sky, sky_avg, rows * res[1]
 
     def shade(self, cam, rays, sky_avg, events=None):
         vid, dep, rd, sky = rays[:4]
@@ -304,7 +307,7 @@ def run_gpu_arm(args):
     bands = sharding.cyclic_bands(res[0], rank, world_size) if strong else None      # thin bands, band b -> rank b mod N
     rows = bands[0] if strong else None
     band_h = sum(b[1] - b[0] for b in bands) if strong else res[0]
-    band_cap = 16 if strong else res[0]                                              # rows of one band slot (2 tile rows)
+    band_cap = (16 if world_size > 1 else res[0]) if strong else res[0]              # rows of one band slot (2 tile rows; N=1: the frame)
     n_slots = len(bands) if strong else 1
     host_out = torch.empty(2, (n_slots * band_cap * world_size) if strong else res[0], res[1], dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -329,16 +332,11 @@ def run_gpu_arm(args):
         avg = global_sky_mean([(rays[4], rays[5])])
         out = fr.shade(cam, rays, avg, kev)
         got = torch.stack([out['depth'][0], out['total_weight'][0]])          # [2, rows of this rank's bands, W], band after band
-        parts, y = [], 0
-        for b in bands:
-            h = b[1] - b[0]
-            m = torch.zeros(2, band_cap, res[1], device=dev)
-            if h > 0:
-                m[:, :h] = got[:, y:y + h]
-                y += h
-            parts.append(m)
-        outs = [out]
-        return torch.cat(parts, 1), (outs[-1] if outs else None)
+        if got.shape[1] == n_slots * band_cap:
+            return got, out
+        m = torch.zeros(2, n_slots * band_cap, res[1], device=dev)            # only a rank's LAST band can be short or missing
+        m[:, :got.shape[1]] = got
+        return m, out
 
     host_rgb = torch.empty(3, out_hw[0], out_hw[1], dtype=torch.float32).pin_memory()
     e2e_image = not strong                    # the user-facing result of a frame is the IMAGE: RenderCNN + tanh (f1) on top of the path

@@ -69,6 +69,17 @@ int sdb_ray_voxel_intersection_perspective_ex(
     int32_t *d_voxel_id, float *d_depth2, float *d_raydirs, const int16_t *d_height_bound, int32_t block_log2,
     void *stream);
 
+/* Row bands of one frame as ONE call (multi-GPU single-frame sharding): output row v of the
+ * img_dims[0]-row result is frame row band[0] + (v / band[1]) * band[2] + v % band[1], i.e. bands of band[1] rows
+ * starting at frame row band[0], band[2] frame rows apart; cam_c is the principal point of the WHOLE frame.  Every
+ * ray is computed exactly as the whole-frame call computes it (c0 - row is exact in float32).                  */
+int sdb_ray_voxel_intersection_perspective_bands(
+    const int32_t *d_voxel, const int64_t dims[3], const int64_t strides[3],
+    const float cam_ori[3], const float cam_dir[3], const float cam_up[3],
+    float cam_f, const float cam_c[2], const int32_t img_dims[2], int32_t max_samples, const int32_t band[3],
+    int32_t *d_voxel_id, float *d_depth2, float *d_raydirs, const int16_t *d_height_bound, int32_t block_log2,
+    void *stream);
+
 /* Host-only helper (no GPU needed): the camera frame the call above derives. */
 void sdb_camera_frame(const float cam_dir[3], const float cam_up[3], float fwd[3], float side[3], float up[3]);
 

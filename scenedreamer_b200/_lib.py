@@ -24,6 +24,9 @@ SIGNATURES = {
     'sdb_ray_voxel_intersection_perspective_ex': (c_int, [
         c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), _F3, _F3, _F3, c_f32, _F3,
         ctypes.POINTER(c_i32), c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p]),
+    'sdb_ray_voxel_intersection_perspective_bands': (c_int, [
+        c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), _F3, _F3, _F3, c_f32, _F3,
+        ctypes.POINTER(c_i32), c_i32, ctypes.POINTER(c_i32), c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p]),
     'sdb_grid_encode_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_f32,
                                         c_u32, c_int, c_void_p, c_u32, c_int, c_void_p]),
     'sdb_grid_encode_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32,

@@ -76,9 +76,11 @@ def invalidate_height_bound(in_voxel):
 
 
 def ray_voxel_intersection_perspective(in_voxel, cam_ori, cam_dir, cam_up, cam_f, cam_c, img_dims, max_samples,
-                                       empty_space_bound=True):
+                                       empty_space_bound=True, band=None):
     """-> [voxel_id int32 [H,W,M,1], depth2 f32 [2,H,W,M,1], raydirs f32 [H,W,1,3]]  (voxlib.cpp:11).
-    empty_space_bound: use the cached height bound of the volume (bit-identical results, see height_bound)."""
+    empty_space_bound: use the cached height bound of the volume (bit-identical results, see height_bound).
+    band = (first_row, band_rows, band_stride): img_dims[0] output rows taken from the frame in bands of band_rows rows that start
+    at first_row and lie band_stride frame rows apart (single-frame sharding; cam_c stays the whole frame's principal point)."""
     _check_cuda(in_voxel, 'in_voxel')
     if in_voxel.dtype != torch.int32 or in_voxel.dim() != 3:
         raise RuntimeError('in_voxel must be a 3-D int32 tensor')
@@ -95,9 +97,15 @@ def ray_voxel_intersection_perspective(in_voxel, cam_ori, cam_dir, cam_up, cam_f
         strides = (ctypes.c_int64 * 3)(*in_voxel.stride())
         cc = (ctypes.c_float * 2)(float(cam_c[0]), float(cam_c[1]))
         im = (ctypes.c_int32 * 2)(H, W)
-        code = _lib.lib().sdb_ray_voxel_intersection_perspective_ex(
-            _ptr(in_voxel), dims, strides, _f3(cam_ori), _f3(cam_dir), _f3(cam_up), float(cam_f), cc, im, M,
-            _ptr(voxel_id), _ptr(depth2), _ptr(raydirs), _ptr(hb), int(L), _stream(in_voxel))
+        if band is None:
+            code = _lib.lib().sdb_ray_voxel_intersection_perspective_ex(
+                _ptr(in_voxel), dims, strides, _f3(cam_ori), _f3(cam_dir), _f3(cam_up), float(cam_f), cc, im, M,
+                _ptr(voxel_id), _ptr(depth2), _ptr(raydirs), _ptr(hb), int(L), _stream(in_voxel))
+        else:
+            bd = (ctypes.c_int32 * 3)(int(band[0]), int(band[1]), int(band[2]))
+            code = _lib.lib().sdb_ray_voxel_intersection_perspective_bands(
+                _ptr(in_voxel), dims, strides, _f3(cam_ori), _f3(cam_dir), _f3(cam_up), float(cam_f), cc, im, M, bd,
+                _ptr(voxel_id), _ptr(depth2), _ptr(raydirs), _ptr(hb), int(L), _stream(in_voxel))
     _lib.check(code, 'ray_voxel_intersection_perspective')
     return [voxel_id, depth2, raydirs]
 

@@ -59,7 +59,7 @@ def cyclic_bands(H, rank, world_size, band_tiles=2, tile_h=8):
     is free, near ground at the bottom terminates within a few samples, the horizon in the middle is the expensive part -- so
     contiguous or mirrored bands leave some ranks idle: 0.1 vs 3.1 ms of kernel time at 8 GPUs.)
     Returns the rank's bands as (y0, y1) in frame order; every rank gets the same NUMBER of slots, trailing ones may be empty."""
-    bh = band_tiles * tile_h
+    bh = band_tiles * tile_h if world_size > 1 else H          # one GPU: the frame is one band
     n_bands = (H + bh - 1) // bh
     per_rank = (n_bands + world_size - 1) // world_size
     out = []

@@ -85,6 +85,21 @@ def test_dda_bit_exact_vs_reference_cuda(world):
         assert torch.equal(bits(torch.nan_to_num(dep, nan=-1.0)), bits(torch.nan_to_num(rdep, nan=-1.0)))
 
 
+def test_dda_row_bands_equal_the_rows_of_the_frame(world):
+    """Single-frame sharding: the banded call returns exactly the rows the whole-frame call computes."""
+    vox = world.voxel_t.to(DEV)
+    o, d, u, f, c, res = _frame(world, 2, hw=(135, 240), pad=30, pattern=0)
+    vid, dep, rd = ops.ray_voxel_intersection_perspective(vox, o, d, u, f, c, res, 6)
+    for first, bh, stride in ((0, 16, 64), (48, 16, 64), (16, 16, 32), (0, res[0], res[0])):
+        rows = [y for y0 in range(first, res[0], stride) for y in range(y0, min(res[0], y0 + bh))]
+        bvid, bdep, brd = ops.ray_voxel_intersection_perspective(vox, o, d, u, f, c, [len(rows), res[1]], 6, band=(first, bh, stride))
+        idx = torch.tensor(rows, device=DEV)
+        assert torch.equal(bvid, vid[idx]) and torch.equal(bits(brd), bits(rd[idx]))
+        assert torch.equal(bits(torch.nan_to_num(bdep, nan=-1.0)), bits(torch.nan_to_num(dep[:, idx], nan=-1.0)))
+    with pytest.raises(RuntimeError):
+        ops.ray_voxel_intersection_perspective(vox, o, d, u, f, c, [16, res[1]], 6, band=(0, 16, 8))       # overlapping bands
+
+
 GE_CASES = [
     # D, C, L, base, log2T, desired, gridtype, B
     (5, 8, 16, 16, 19, 2048, 0, 4096),      # the SceneDreamer encoder

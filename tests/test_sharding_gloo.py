@@ -77,4 +77,4 @@ def test_cyclic_bands_cover_the_frame_once():
             bands = sorted(b for p in per for b in p if b[1] > b[0])
             assert bands[0][0] == 0 and bands[-1][1] == H
             assert all(bands[i][1] == bands[i + 1][0] for i in range(len(bands) - 1))
-            assert all(b[0] % 8 == 0 and b[1] - b[0] <= 16 for b in bands)
+            assert all(b[0] % 8 == 0 and (b[1] - b[0] <= 16 or world == 1) for b in bands)      # one GPU: the frame is one band
