@@ -33,6 +33,25 @@ def summarise(kind, prefix, cmd):
     print('wrote', out)
 
 
+def summarise_many(kind, prefix, cmd):
+    """Same, for a capture holding several kernels (one block per launch)."""
+    src = os.path.join(ROOT, 'gpurun_out', 'prof_%s_raw.csv' % kind)
+    if not os.path.exists(src):
+        return
+    rows = list(csv.reader(open(src)))
+    out = os.path.join(ROOT, 'profiles', '%s_%s_ncu.txt' % (prefix, kind))
+    with open(out, 'w') as f:
+        f.write('# ncu --set full --clock-control none\n# command: %s\n' % cmd)
+        f.write('# (numbers under a profiler: cold caches, serialised -- shares and ratios, not bench values)\n')
+        for r in rows[2:]:
+            d = {h: (v, u) for h, v, u in zip(rows[0], r, rows[1])}
+            f.write('\n## %s\n' % d.get('Kernel Name', ('?',))[0][:160])
+            for m in METRICS:
+                if m in d:
+                    f.write('%-82s %s %s\n' % (m, d[m][0], d[m][1]))
+    print('wrote', out)
+
+
 def sass_census(prefix):
     lib = os.path.join(ROOT, 'scenedreamer_b200', 'libsdb200.so')
     txt = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
@@ -69,4 +88,5 @@ if __name__ == '__main__':
     summarise('conv', prefix, 'python bench.py ...  (-k regex:conv_kernel -s 8 -c 1: conv2a, 3x3 256->256, fp16x3)')
     summarise('dda', prefix, 'python bench.py ...  (-k regex:dda_perspective -s 3 -c 1)')
     summarise('wgrad', prefix, 'python bench_train.py --steps 2 --warmup 3 --no-composition  (-k regex:wgrad_kernel -s 2 -c 1)')
+    summarise_many('gridenc', prefix, 'python tools/gridenc_run.py  (-k regex:grid_|input_backward -s 3 -c 3: forward, table backward, input backward; 599k samples, D=5)')
     sass_census(prefix)
