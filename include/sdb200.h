@@ -84,7 +84,7 @@ int sdb_ray_voxel_intersection_perspective_bands(
 void sdb_camera_frame(const float cam_dir[3], const float cam_up[3], float fwd[3], float side[3], float up[3]);
 
 /* --------------------------------------------------------------------------------------------
- * a6/a7. Multi-resolution hash / tiled grid encoding, float32.
+ * a6/a7. Multi-resolution hash / tiled grid encoding, float32 (float16 tables: the _f16 pair below).
  * Replace _gridencoder.grid_encode_forward / grid_encode_backward
  *   (gridencoder/src/bindings.cpp:5-8, gridencoder.h:12-13, gridencoder.cu:423-478).
  * Same argument meaning as the reference: caller pre-allocates everything;
@@ -103,6 +103,22 @@ int sdb_grid_encode_backward(
     const float *d_grad, const float *d_inputs, const float *d_embeddings, const int32_t *d_offsets,
     float *d_grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
     int calc_grad_inputs, const float *d_dy_dx, float *d_grad_inputs, uint32_t gridtype,
+    int align_corners, void *stream);
+
+/* The same two calls on a float16 table -- the reference under autocast (gridencoder/grid.py:38-39 casts the
+ * embeddings to half when C is even; the binding dispatches on the table's dtype, gridencoder.cu:442-444, 473-475):
+ * d_embeddings / d_outputs / d_dy_dx / d_grad / d_grad_embeddings / d_grad_inputs are IEEE half, d_inputs stays float32.
+ * Arithmetic as c10::Half performs it (every operator rounds its result to half), so outputs and dy_dx are
+ * bit-identical to the reference; the table gradient uses half2 atomics like the reference (:299-305).
+ * C in {2,4,8} (odd C never reaches this path in the reference; SDB_EUNSUPPORTED).                              */
+int sdb_grid_encode_forward_f16(
+    const float *d_inputs, const void *d_embeddings, const int32_t *d_offsets, void *d_outputs,
+    uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, void *d_dy_dx, uint32_t gridtype, int align_corners, void *stream);
+int sdb_grid_encode_backward_f16(
+    const void *d_grad, const float *d_inputs, const void *d_embeddings, const int32_t *d_offsets,
+    void *d_grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, const void *d_dy_dx, void *d_grad_inputs, uint32_t gridtype,
     int align_corners, void *stream);
 
 /* --------------------------------------------------------------------------------------------

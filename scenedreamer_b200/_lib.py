@@ -31,6 +31,10 @@ SIGNATURES = {
                                         c_u32, c_int, c_void_p, c_u32, c_int, c_void_p]),
     'sdb_grid_encode_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32,
                                          c_u32, c_f32, c_u32, c_int, c_void_p, c_void_p, c_u32, c_int, c_void_p]),
+    'sdb_grid_encode_forward_f16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32, c_u32, c_f32,
+                                        c_u32, c_int, c_void_p, c_u32, c_int, c_void_p]),
+    'sdb_grid_encode_backward_f16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_u32, c_u32,
+                                         c_u32, c_f32, c_u32, c_int, c_void_p, c_void_p, c_u32, c_int, c_void_p]),
     'sdb_positional_encoding': (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_int, c_void_p]),
     'sdb_positional_encoding_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_int, c_void_p]),
     'sdb_sp_trilinear_worldcoord': (c_int, [c_void_p, c_i64, c_i32, c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),

@@ -1,4 +1,4 @@
-// a6/a7: stand-alone multi-resolution hash / tiled grid encoder, float32, sm_100a.
+// a6/a7: stand-alone multi-resolution hash / tiled grid encoder, float32 and (autocast) float16 tables, sm_100a.
 //
 // Behavioural contract = _gridencoder.grid_encode_forward / grid_encode_backward of the reference
 // (gridencoder/src/gridencoder.cu:423-478 wrappers; :75-224 kernel_grid, :227-314
@@ -10,6 +10,15 @@
 // loads; the backward scatters with vector reductions (red.global.add.v4.f32, sm_90+) -- 2 per
 // corner for C=8 instead of 8 scalar atomics; blocks are level-major (blockIdx.y = level) so a
 // wave of CTAs keeps one level's table slice hot in the 126 MB L2.
+//
+// T = __half is the reference's autocast path (grid.py:38-39 converts the table to half when C is even; the binding
+// dispatches on the table's dtype, gridencoder.cu:442-444): table, outputs, dy_dx, grad and grad_inputs are half, the
+// coordinates stay float32.  The reference computes it with c10::Half, whose every operator returns through a float
+// and rounds back (Half += float rounds the addend FIRST, then the sum; Half - Half and Half * Half round their result) --
+// `hr()` below marks each of those roundings, so forward and dy_dx are bit-identical; the table gradient accumulates with
+// half2 atomics (:299-305) and is order-dependent in both implementations.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -53,6 +62,50 @@ __device__ __forceinline__ void load_feat(const float *__restrict__ g, float (&v
         v[0] = __ldg(g);
     }
 }
+// half features: one vector load of C halves (16 B for C = 8), widened to float registers
+template <uint32_t C>
+__device__ __forceinline__ void load_feat(const __half *__restrict__ g, float (&v)[C]) {
+    static_assert(C % 2 == 0, "half tables: even C only (grid.py:38)");
+    uint32_t w[C / 2];
+    if constexpr (C == 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(g));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else if constexpr (C == 4) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(g));
+        w[0] = a.x; w[1] = a.y;
+    } else {
+        w[0] = __ldg(reinterpret_cast<const uint32_t *>(g));
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < C / 2; k++) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[k]));
+        v[2 * k] = f.x;
+        v[2 * k + 1] = f.y;
+    }
+}
+template <uint32_t C>
+__device__ __forceinline__ void store_feat(float *__restrict__ o, const float (&v)[C]) {
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) o[c] = v[c];
+}
+template <uint32_t C>
+__device__ __forceinline__ void store_feat(__half *__restrict__ o, const float (&v)[C]) {   // v already holds half values
+    uint32_t w[C / 2];
+#pragma unroll
+    for (uint32_t k = 0; k < C / 2; k++) {
+        const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        w[k] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    if constexpr (C == 8) *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    else if constexpr (C == 4) *reinterpret_cast<uint2 *>(o) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint32_t *>(o) = w[0];
+}
+// one c10::Half rounding (float -> half -> float); identity for float tables
+template <typename T>
+__device__ __forceinline__ float hr(float x) {
+    if constexpr (sizeof(T) == 2) return __half2float(__float2half_rn(x));
+    else return x;
+}
 
 template <uint32_t D>
 __device__ __forceinline__ bool locate(const float *__restrict__ x, float scale, bool align_corners,
@@ -70,18 +123,19 @@ __device__ __forceinline__ bool locate(const float *__restrict__ x, float scale,
     return oob;
 }
 
-template <uint32_t D, uint32_t C>
+template <typename T, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256)
-grid_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ grid,
-                    const int *__restrict__ offsets, float *__restrict__ outputs, uint32_t B, uint32_t L,
-                    float S, uint32_t H, bool calc_grad_inputs, float *__restrict__ dy_dx, uint32_t gridtype,
+grid_forward_kernel(const float *__restrict__ inputs, const T *__restrict__ grid,
+                    const int *__restrict__ offsets, T *__restrict__ outputs, uint32_t B, uint32_t L,
+                    float S, uint32_t H, bool calc_grad_inputs, T *__restrict__ dy_dx, uint32_t gridtype,
                     bool align_corners)
 {
+    constexpr bool kHalf = sizeof(T) == 2;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
     grid += (size_t)(uint32_t)offsets[level] * C;
-    float *out = outputs + ((size_t)level * B + b) * C;
+    T *out = outputs + ((size_t)level * B + b) * C;
     const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
     const float scale = exp2f(level * S) * H - 1.0f;
     const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
@@ -90,12 +144,14 @@ grid_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ 
     uint32_t pg[D];
     const bool oob = locate<D>(inputs + (size_t)b * D, scale, align_corners, pos, pg);
     if (oob) {
+        float zero[C];
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) out[c] = 0;
+        for (uint32_t c = 0; c < C; c++) zero[c] = 0;
+        store_feat<C>(out, zero);
         if (calc_grad_inputs) {
-            float *dd = dy_dx + ((size_t)b * L + level) * D * C;
+            T *dd = dy_dx + ((size_t)b * L + level) * D * C;
 #pragma unroll
-            for (uint32_t k = 0; k < D * C; k++) dd[k] = 0;
+            for (uint32_t k = 0; k < D; k++) store_feat<C>(dd + k * C, zero);
         }
         return;
     }
@@ -115,13 +171,15 @@ grid_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ 
         float v[C];
         load_feat<C>(grid + (size_t)index * C, v);
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) res[c] += w * v[c];
+        for (uint32_t c = 0; c < C; c++) {
+            if constexpr (kHalf) res[c] = hr<T>(res[c] + hr<T>(w * v[c]));      // Half += float (:166)
+            else res[c] += w * v[c];
+        }
     }
-#pragma unroll
-    for (uint32_t c = 0; c < C; c++) out[c] = res[c];
+    store_feat<C>(out, res);
 
     if (calc_grad_inputs) {
-        float *dd = dy_dx + ((size_t)b * L + level) * D * C;
+        T *dd = dy_dx + ((size_t)b * L + level) * D * C;
 #pragma unroll
         for (uint32_t gd = 0; gd < D; gd++) {
             float rg[C];
@@ -145,10 +203,12 @@ grid_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ 
                 load_feat<C>(grid + (size_t)il * C, vl);
                 load_feat<C>(grid + (size_t)ir * C, vr);
 #pragma unroll
-                for (uint32_t c = 0; c < C; c++) rg[c] += w * (vr[c] - vl[c]);
+                for (uint32_t c = 0; c < C; c++) {
+                    if constexpr (kHalf) rg[c] = hr<T>(rg[c] + hr<T>(w * hr<T>(vr[c] - vl[c])));   // (:213)
+                    else rg[c] += w * (vr[c] - vl[c]);
+                }
             }
-#pragma unroll
-            for (uint32_t c = 0; c < C; c++) dd[gd * C + c] = rg[c];
+            store_feat<C>(dd + gd * C, rg);
         }
     }
 }
@@ -167,10 +227,17 @@ __device__ __forceinline__ void red_add(float *__restrict__ g, const float (&v)[
     }
 }
 
-template <uint32_t D, uint32_t C>
+// half table gradient: (__half)(w * g) pairs added with half2 atomics, as the reference does (:299-305)
+template <uint32_t C>
+__device__ __forceinline__ void red_add(__half *__restrict__ g, const float (&v)[C]) {
+#pragma unroll
+    for (uint32_t c = 0; c < C; c += 2) atomicAdd(reinterpret_cast<__half2 *>(g + c), __floats2half2_rn(v[c], v[c + 1]));
+}
+
+template <typename T, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256)
-grid_backward_kernel(const float *__restrict__ grad, const float *__restrict__ inputs,
-                     const int *__restrict__ offsets, float *__restrict__ grad_grid, uint32_t B, uint32_t L,
+grid_backward_kernel(const T *__restrict__ grad, const float *__restrict__ inputs,
+                     const int *__restrict__ offsets, T *__restrict__ grad_grid, uint32_t B, uint32_t L,
                      float S, uint32_t H, uint32_t gridtype, bool align_corners)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,39 +269,46 @@ grid_backward_kernel(const float *__restrict__ grad, const float *__restrict__ i
     }
 }
 
-template <uint32_t D, uint32_t C>
+template <typename T, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256)
-input_backward_kernel(const float *__restrict__ grad, const float *__restrict__ dy_dx,
-                      float *__restrict__ grad_inputs, uint32_t B, uint32_t L)
+input_backward_kernel(const T *__restrict__ grad, const T *__restrict__ dy_dx,
+                      T *__restrict__ grad_inputs, uint32_t B, uint32_t L)
 {
     const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
     if (t >= B * D) return;
     const uint32_t b = t / D, d = t - b * D;
-    const float *dd = dy_dx + (size_t)b * L * D * C;
+    const T *dd = dy_dx + (size_t)b * L * D * C;
     float r = 0;
     for (uint32_t l = 0; l < L; l++) {
+        float g[C], y[C];
+        load_feat<C>(grad + ((size_t)l * B + b) * C, g);
+        load_feat<C>(dd + (l * D + d) * C, y);
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) r += grad[((size_t)l * B + b) * C + c] * dd[(l * D + d) * C + c];
+        for (uint32_t c = 0; c < C; c++) {
+            if constexpr (sizeof(T) == 2) r = hr<T>(r + hr<T>(g[c] * y[c]));      // Half += Half * Half (:338)
+            else r += g[c] * y[c];
+        }
     }
-    grad_inputs[t] = r;
+    if constexpr (sizeof(T) == 2) grad_inputs[t] = __float2half_rn(r);
+    else grad_inputs[t] = r;
 }
 
-template <uint32_t D, uint32_t C>
-int launch_fwd(const float *in, const float *emb, const int *off, float *out, uint32_t B, uint32_t L, float S,
-               uint32_t H, bool calc, float *dy_dx, uint32_t gt, bool ac, cudaStream_t st) {
+template <uint32_t D, uint32_t C, typename T>
+int launch_fwd(const float *in, const T *emb, const int *off, T *out, uint32_t B, uint32_t L, float S,
+               uint32_t H, bool calc, T *dy_dx, uint32_t gt, bool ac, cudaStream_t st) {
     dim3 grid(sdb_div_up(B, 256u), L);
-    grid_forward_kernel<D, C><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
+    grid_forward_kernel<T, D, C><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
-template <uint32_t D, uint32_t C>
-int launch_bwd(const float *grad, const float *in, const int *off, float *gg, uint32_t B, uint32_t L, float S,
-               uint32_t H, bool calc, const float *dy_dx, float *gi, uint32_t gt, bool ac, cudaStream_t st) {
+template <uint32_t D, uint32_t C, typename T>
+int launch_bwd(const T *grad, const float *in, const int *off, T *gg, uint32_t B, uint32_t L, float S,
+               uint32_t H, bool calc, const T *dy_dx, T *gi, uint32_t gt, bool ac, cudaStream_t st) {
     dim3 grid(sdb_div_up(B, 256u), L);
-    grid_backward_kernel<D, C><<<grid, 256, 0, st>>>(grad, in, off, gg, B, L, S, H, gt, ac);
+    grid_backward_kernel<T, D, C><<<grid, 256, 0, st>>>(grad, in, off, gg, B, L, S, H, gt, ac);
     SDB_CHECK_LAUNCH();
     if (calc) {
-        input_backward_kernel<D, C><<<sdb_div_up(B * D, 256u), 256, 0, st>>>(grad, dy_dx, gi, B, L);
+        input_backward_kernel<T, D, C><<<sdb_div_up(B * D, 256u), 256, 0, st>>>(grad, dy_dx, gi, B, L);
         SDB_CHECK_LAUNCH();
     }
     return SDB_OK;
@@ -287,4 +361,49 @@ extern "C" int sdb_grid_encode_backward(
     if (B == 0 || L == 0) return SDB_OK;
     SDB_DISPATCH_DC(launch_bwd, d_grad, d_inputs, d_offsets, d_grad_embeddings, B, L, S, H, calc_grad_inputs != 0,
                     d_dy_dx, d_grad_inputs, gridtype, align_corners != 0, (cudaStream_t)stream)
+}
+
+#define SDB_DISPATCH_DC_EVEN(FN, ...)                                     \
+    switch (D * 16 + C) {                                                 \
+        case 2 * 16 + 2: return FN<2, 2>(__VA_ARGS__);                    \
+        case 2 * 16 + 4: return FN<2, 4>(__VA_ARGS__);                    \
+        case 2 * 16 + 8: return FN<2, 8>(__VA_ARGS__);                    \
+        case 3 * 16 + 2: return FN<3, 2>(__VA_ARGS__);                    \
+        case 3 * 16 + 4: return FN<3, 4>(__VA_ARGS__);                    \
+        case 3 * 16 + 8: return FN<3, 8>(__VA_ARGS__);                    \
+        case 4 * 16 + 2: return FN<4, 2>(__VA_ARGS__);                    \
+        case 4 * 16 + 4: return FN<4, 4>(__VA_ARGS__);                    \
+        case 4 * 16 + 8: return FN<4, 8>(__VA_ARGS__);                    \
+        case 5 * 16 + 2: return FN<5, 2>(__VA_ARGS__);                    \
+        case 5 * 16 + 4: return FN<5, 4>(__VA_ARGS__);                    \
+        case 5 * 16 + 8: return FN<5, 8>(__VA_ARGS__);                    \
+        default: return SDB_EUNSUPPORTED;                                 \
+    }
+
+// float16 tables (the reference under autocast; even C only -- grid.py:38 keeps odd C in float32)
+extern "C" int sdb_grid_encode_forward_f16(
+    const float *d_inputs, const void *d_embeddings, const int32_t *d_offsets, void *d_outputs,
+    uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, void *d_dy_dx, uint32_t gridtype, int align_corners, void *stream)
+{
+    if (!d_inputs || !d_embeddings || !d_offsets || !d_outputs) return SDB_EINVAL;
+    if (calc_grad_inputs && !d_dy_dx) return SDB_EINVAL;
+    if (B == 0 || L == 0) return SDB_OK;
+    SDB_DISPATCH_DC_EVEN(launch_fwd, d_inputs, (const __half *)d_embeddings, d_offsets, (__half *)d_outputs, B, L, S, H,
+                         calc_grad_inputs != 0, (__half *)d_dy_dx, gridtype, align_corners != 0, (cudaStream_t)stream)
+}
+
+extern "C" int sdb_grid_encode_backward_f16(
+    const void *d_grad, const float *d_inputs, const void *d_embeddings, const int32_t *d_offsets,
+    void *d_grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+    int calc_grad_inputs, const void *d_dy_dx, void *d_grad_inputs, uint32_t gridtype,
+    int align_corners, void *stream)
+{
+    (void)d_embeddings;
+    if (!d_grad || !d_inputs || !d_offsets || !d_grad_embeddings) return SDB_EINVAL;
+    if (calc_grad_inputs && (!d_dy_dx || !d_grad_inputs)) return SDB_EINVAL;
+    if (B == 0 || L == 0) return SDB_OK;
+    SDB_DISPATCH_DC_EVEN(launch_bwd, (const __half *)d_grad, d_inputs, d_offsets, (__half *)d_grad_embeddings, B, L, S, H,
+                         calc_grad_inputs != 0, (const __half *)d_dy_dx, (__half *)d_grad_inputs, gridtype, align_corners != 0,
+                         (cudaStream_t)stream)
 }

@@ -163,9 +163,11 @@ def _live_params(gen):
 # ------------------------------------------------------------------------------------------------
 def supported(gen, voxel_id, z, global_enc):
     """The fused path covers what both SceneDreamer configs use (configs/scenedreamer_{train,inference}.yaml):
-    no view-direction input to the MLP, segmentation labels on, clipped feature blending, global sky average."""
+    no view-direction input to the MLP, segmentation labels on, clipped feature blending, global sky average, AMP off (under
+    autocast the reference composition runs instead, over the drop-in ops -- the grid encoder then takes its float16 table path)."""
     rn = gen.render_net
     return bool(
+        not torch.is_autocast_enabled() and
         z is not None and global_enc is not None and voxel_id.is_cuda and
         gen.clip_feat_map is True and gen.keep_sky_out and gen.keep_sky_out_avgpool and gen.sky_global_avgpool and
         not gen.sample_use_box_boundaries and gen.raw_noise_std == 0 and
@@ -341,7 +343,7 @@ def fused_forward_global(self, net_out, z):
     return eng.forward(net_out, z)
 
 
-SAMPLER_SPECULATION = 4          # candidate poses judged per synchronisation
+SAMPLER_SPECULATION = 8          # most candidate poses judged per synchronisation (the depth adapts to the rejection rate)
 
 
 def fused_get_batch(self, batch_size, device):
@@ -365,11 +367,12 @@ def fused_get_batch(self, batch_size, device):
         if hasattr(self.voxel, 'sample_world'):
             self.voxel.sample_world(device)
         ids, deps, dirs, oris = [], [], [], []
+        depth = max(1, min(SAMPLER_SPECULATION, int(getattr(self, '_sdb200_sampler_depth', 1))))
         for _ in range(batch_size):
             picked = None
             while picked is None:
                 cands = []
-                for _k in range(SAMPLER_SPECULATION):
+                for _k in range(depth):
                     cam_res = self.cam_res                                           # scenedreamer.py:97-122, verbatim order of draws
                     cam_c = [(cam_res[0] - 1) / 2, (cam_res[1] - 1) / 2]
                     if self.camera_sampler_type == 'traditional' and torch.rand(1).item() > 0.5:
@@ -380,24 +383,27 @@ def fused_get_batch(self, batch_size, device):
                         cam_f = 0.5 / np.tan(np.deg2rad(73 / 2) * (np.random.rand(1) * 0.5 + 0.5)) * (cam_res[1] - 1)
                     cam_res_crop = [self.crop_size[0] + self.pad, self.crop_size[1] + self.pad]
                     cam_c = mc_utils.rand_crop(cam_c, cam_res, cam_res_crop)
-                    rng = (torch.get_rng_state(), np.random.get_state())
+                    rng = (torch.get_rng_state(), np.random.get_state()) if _k + 1 < depth else None    # nothing drawn after the last
                     out = smod.voxlib.ray_voxel_intersection_perspective(self.voxel.voxel_t, cam_ori_t, cam_dir_t, cam_up_t, cam_f, cam_c,
                                                                          cam_res_crop, self.num_blocks_early_stop)
                     cands.append((out, cam_ori_t, rng, ops.pose_stats(out[0], out[1])))
                 stats = torch.stack([c[3] for c in cands]).cpu()                     # the ONE synchronisation of this round
-                for (out, ori, rng, _s), (avg_depth, entropy) in zip(cands, stats.tolist()):
+                for k, ((out, ori, rng, _s), (avg_depth, entropy)) in enumerate(zip(cands, stats.tolist())):
                     if self.camera_rej_avg_depth > 0 and avg_depth < self.camera_rej_avg_depth:
                         continue
                     if self.camera_min_entropy > 0 and entropy < self.camera_min_entropy:
                         continue
                     picked = (out, ori)
-                    torch.set_rng_state(rng[0])                                      # forget the candidates drawn after the winner
-                    np.random.set_state(rng[1])
+                    if rng is not None:
+                        torch.set_rng_state(rng[0])                                  # forget the candidates drawn after the winner
+                        np.random.set_state(rng[1])
                     break
+                depth = max(1, depth // 2) if (picked is not None and k == 0) else min(SAMPLER_SPECULATION, depth * 2)
             ids.append(picked[0][0])
             deps.append(picked[0][1])
             dirs.append(picked[0][2])
             oris.append(picked[1])
+        self._sdb200_sampler_depth = depth
         return torch.stack(ids, 0), torch.stack(deps, 0), torch.stack(dirs, 0), torch.stack(oris, 0).to(device), None
 
 

@@ -207,23 +207,36 @@ def sp_trilinear_worldcoord_backward(out_feature_grad, in_feature, corner_lut_t,
 # ------------------------------------------------------------------------------------------------
 # _gridencoder
 # ------------------------------------------------------------------------------------------------
-def _check_ge(t, name, floating=True):
+def _check_ge(t, name, floating=True, dtype=torch.float32):
     _check_input(t, name)
-    if floating and t.dtype != torch.float32:
-        raise RuntimeError('%s must be a float32 tensor (scenedreamer_b200 implements the fp32 path; '
-                           'the SceneDreamer configs run with AMP disabled)' % name)
+    if floating and t.dtype != dtype:
+        raise RuntimeError('%s must be a %s tensor (the table\'s dtype decides: float32, or float16 for the reference\'s '
+                           'autocast path; coordinates are always float32)' % (name, str(dtype).replace('torch.', '')))
     if not floating and t.dtype != torch.int32:
         raise RuntimeError('%s must be an int tensor' % name)
 
 
+def _ge_dtype(embeddings, C):
+    """The reference dispatches on the table's dtype (gridencoder.cu:442); float64 tables are not built here."""
+    if embeddings.dtype == torch.float32:
+        return torch.float32, ''
+    if embeddings.dtype == torch.float16:
+        if int(C) % 2:
+            raise RuntimeError('GridEncoding: float16 tables need an even C (gridencoder/grid.py:38 keeps odd C in float32)')
+        return torch.float16, '_f16'
+    raise RuntimeError('embeddings must be a float32 or float16 tensor')
+
+
 def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx, gridtype,
                         align_corners):
-    """Caller-allocated outputs [L,B,C] / dy_dx, returns None (gridencoder.h:12)."""
-    for t, n in ((inputs, 'inputs'), (embeddings, 'embeddings'), (outputs, 'outputs'), (dy_dx, 'dy_dx')):
-        _check_ge(t, n)
+    """Caller-allocated outputs [L,B,C] / dy_dx in the table's dtype, returns None (gridencoder.h:12)."""
+    dt, sfx = _ge_dtype(embeddings, C)
+    _check_ge(inputs, 'inputs')
+    for t, n in ((embeddings, 'embeddings'), (outputs, 'outputs'), (dy_dx, 'dy_dx')):
+        _check_ge(t, n, dtype=dt)
     _check_ge(offsets, 'offsets', floating=False)
     with torch.cuda.device(inputs.device):
-        code = _lib.lib().sdb_grid_encode_forward(
+        code = getattr(_lib.lib(), 'sdb_grid_encode_forward' + sfx)(
             _ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(outputs), int(B), int(D), int(C), int(L), float(S),
             int(H), int(bool(calc_grad_inputs)), _ptr(dy_dx), int(gridtype), int(bool(align_corners)),
             _stream(inputs))
@@ -234,12 +247,14 @@ def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, 
 
 def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs,
                          dy_dx, grad_inputs, gridtype, align_corners):
-    for t, n in ((grad, 'grad'), (inputs, 'inputs'), (embeddings, 'embeddings'), (grad_embeddings, 'grad_embeddings'),
+    dt, sfx = _ge_dtype(embeddings, C)
+    _check_ge(inputs, 'inputs')
+    for t, n in ((grad, 'grad'), (embeddings, 'embeddings'), (grad_embeddings, 'grad_embeddings'),
                  (dy_dx, 'dy_dx'), (grad_inputs, 'grad_inputs')):
-        _check_ge(t, n)
+        _check_ge(t, n, dtype=dt)
     _check_ge(offsets, 'offsets', floating=False)
     with torch.cuda.device(inputs.device):
-        code = _lib.lib().sdb_grid_encode_backward(
+        code = getattr(_lib.lib(), 'sdb_grid_encode_backward' + sfx)(
             _ptr(grad), _ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(grad_embeddings), int(B), int(D), int(C),
             int(L), float(S), int(H), int(bool(calc_grad_inputs)), _ptr(dy_dx), _ptr(grad_inputs), int(gridtype),
             int(bool(align_corners)), _stream(inputs))

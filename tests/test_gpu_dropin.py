@@ -70,6 +70,30 @@ def test_gridencoder_module_forward_backward(gridencoder_pkg, D, L, C, base, log
     np.testing.assert_allclose(ge.embeddings.grad.cpu().numpy(), ege.numpy(), rtol=1e-4, atol=1e-5)
 
 
+def test_gridencoder_module_under_autocast(gridencoder_pkg):
+    """AMP on: the reference's grid.py hands the drop-in a float16 table (grid.py:38-39); outputs come back half, within half
+    precision of the float32 module, and both gradients arrive (table gradient in float32 through autograd's cast)."""
+    ge = gridencoder_pkg.GridEncoder(input_dim=5, num_levels=16, level_dim=8, base_resolution=16, log2_hashmap_size=19,
+                                     desired_resolution=2048).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    ge.embeddings.data = ((torch.rand(ge.embeddings.shape, generator=g) * 2 - 1) * 0.1).to(DEV)
+    x = (torch.rand(3000, 5, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    y32 = ge(x).detach()
+    with torch.autocast('cuda', dtype=torch.float16):
+        y16 = ge(x)
+    assert y16.dtype == torch.float16 and y16.shape == y32.shape
+    assert float((y16.float() - y32).abs().max()) < 1e-2 * float(y32.abs().max()) + 1e-4
+    gy = torch.randn(y16.shape, generator=g).to(DEV) * 0.1
+    y16.backward(gy.half())
+    assert ge.embeddings.grad is not None and ge.embeddings.grad.dtype == torch.float32 and x.grad is not None
+    g16, gx16 = ge.embeddings.grad.clone(), x.grad.clone()
+    ge.zero_grad()
+    x.grad = None
+    ge(x).backward(gy)
+    assert float((g16 - ge.embeddings.grad).abs().max()) < 2e-2 * float(ge.embeddings.grad.abs().max())
+    assert float((gx16 - x.grad).abs().max()) < 5e-2 * float(x.grad.abs().max())
+
+
 def test_patched_forward_perpix_matches_oracle(golden_ops):
     """A duck-typed stand-in for the reference Generator (same attribute names as
     imaginaire/generators/scenedreamer.py / gancraft_base.py) through integration.patch_generator."""

@@ -174,16 +174,20 @@ def test_fused_camera_sampler_reproduces_the_reference(fused_generator):
     gen.voxel.sample_world = lambda device: None                           # PCGCache's per-batch scene switch (pcg_gen.py:26)
     try:
         outs, rngs = [], []
-        for fn in (cls._sdb200_reference_get_batch, cls._get_batch):
+        for fn, depth in ((cls._sdb200_reference_get_batch, None), (cls._get_batch, 4), (cls._get_batch, 1)):
             torch.manual_seed(123)
             np.random.seed(123)
+            if depth is not None:
+                gen._sdb200_sampler_depth = depth          # 4: candidates drawn past the winner, RNGs rewound; 1: the adaptive floor
             outs.append(fn(gen, 3, torch.device(DEV)))
             rngs.append((torch.get_rng_state().clone(), np.random.get_state()[1].copy()))
-        ref, ours = outs
-        assert ours[0].shape == (3, 262, 262, 6, 1)
-        assert torch.equal(ref[0], ours[0]) and torch.equal(ref[2], ours[2]) and torch.equal(ref[3], ours[3])
-        assert torch.equal(torch.nan_to_num(ref[1], nan=-1.0), torch.nan_to_num(ours[1], nan=-1.0))
-        assert torch.equal(rngs[0][0], rngs[1][0]) and np.array_equal(rngs[0][1], rngs[1][1])
+        ref = outs[0]
+        for ours, rng in zip(outs[1:], rngs[1:]):
+            assert ours[0].shape == (3, 262, 262, 6, 1)
+            assert torch.equal(ref[0], ours[0]) and torch.equal(ref[2], ours[2]) and torch.equal(ref[3], ours[3])
+            assert torch.equal(torch.nan_to_num(ref[1], nan=-1.0), torch.nan_to_num(ours[1], nan=-1.0))
+            assert torch.equal(rngs[0][0], rng[0]) and np.array_equal(rngs[0][1], rng[1])
+        assert 1 <= gen._sdb200_sampler_depth <= 8
     finally:
         gen.cam_res, gen.crop_size, gen.pad, gen.num_blocks_early_stop = saved
         del gen.voxel.sample_world

@@ -198,6 +198,50 @@ def test_grid_encode_vs_reference_cuda():
         np.testing.assert_allclose(gi.cpu().numpy(), rgi.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(rgi.abs().max()))
 
 
+def test_grid_encode_float16_table_vs_reference_cuda():
+    """The reference's autocast path (grid.py:38-39: half table, half outputs / dy_dx / gradients, float32 coordinates):
+    forward, dy_dx and the coordinate gradient are bit-identical to the reference's CUDA (c10::Half rounding after every
+    operator, restated in gridenc.cu); the table gradient is accumulated with half2 atomics in both, so it is order-dependent."""
+    ref = load_ref('ref_gridencoder')
+    if ref is None:
+        pytest.skip('oracle/_ref/ref_gridencoder not built')
+    for (D, C, L, base, log2T, desired, gridtype, B) in ((5, 8, 16, 16, 19, 2048, 0, 4096), (3, 2, 8, 4, 12, 64, 0, 3000),
+                                                         (3, 4, 6, 4, 10, 48, 1, 1025)):
+        offsets, pls, emb, g = _ge_setup(D, C, L, base, log2T, desired, seed=5)
+        x = torch.rand(B, D, generator=g).to(DEV)
+        x[::97] = 1.5                                                     # out-of-range samples: zero rows
+        S = np.log2(pls)
+        ee, oe = emb.to(DEV).half(), offsets.to(DEV)
+        mk = lambda *shape: torch.full(shape, float('nan'), device=DEV, dtype=torch.float16)
+        out, rout, dd, rdd = mk(L, B, C), mk(L, B, C), mk(B, L * D * C), mk(B, L * D * C)
+        ops.grid_encode_forward(x, ee, oe, out, B, D, C, L, S, base, True, dd, gridtype, False)
+        ref.grid_encode_forward(x, ee, oe, rout, B, D, C, L, S, base, True, rdd, gridtype, False)
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(torch.int16), rout.view(torch.int16))
+        assert torch.equal(dd.view(torch.int16), rdd.view(torch.int16))
+        assert float(out[:, ::97].abs().max()) == 0.0 and float(out.float().abs().max()) > 0
+        grad = (torch.randn(L, B, C, generator=g) * 0.1).to(DEV).half()
+        ge, rge = torch.zeros_like(ee), torch.zeros_like(ee)
+        gi, rgi = torch.zeros(B, D, device=DEV, dtype=torch.float16), torch.zeros(B, D, device=DEV, dtype=torch.float16)
+        ops.grid_encode_backward(grad, x, ee, oe, ge, B, D, C, L, S, base, True, dd, gi, gridtype, False)
+        ref.grid_encode_backward(grad, x, ee, oe, rge, B, D, C, L, S, base, True, rdd, rgi, gridtype, False)
+        torch.cuda.synchronize()
+        assert torch.equal(gi.view(torch.int16), rgi.view(torch.int16))
+        # float32 accumulation of the same addends as the referee of both half-atomic results
+        g32, e32 = torch.zeros(ee.shape, device=DEV), ee.float()
+        d32 = torch.empty(1, device=DEV)
+        ops.grid_encode_backward(grad.float(), x, e32, oe, g32, B, D, C, L, S, base, False, d32, d32, gridtype, False)
+        scale = float(g32.abs().max())
+        err_ours, err_ref = float((ge.float() - g32).abs().max()), float((rge.float() - g32).abs().max())
+        print('f16 table grad: max |ours - fp32| %.3e, |reference - fp32| %.3e (max |g| %.3e)' % (err_ours, err_ref, scale))
+        assert err_ours <= max(2.0 * err_ref, 2e-3 * scale)
+    with pytest.raises(RuntimeError):                                     # odd C stays float32 in the reference (grid.py:38)
+        ops.grid_encode_forward(x, torch.zeros(64, 1, device=DEV, dtype=torch.float16), oe, mk(L, B, 1), B, D, 1, L, S, base,
+                                False, mk(1), gridtype, False)
+    with pytest.raises(RuntimeError):                                     # mixed dtypes
+        ops.grid_encode_forward(x, ee, oe, torch.empty(L, B, C, device=DEV), B, D, C, L, S, base, False, mk(1), gridtype, False)
+
+
 def test_positional_encoding_vs_oracle_and_reference():
     g = torch.Generator().manual_seed(4)
     x = (torch.rand(37, 50, 1, 3, generator=g) * 2 - 1)
