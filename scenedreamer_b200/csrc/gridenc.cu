@@ -19,6 +19,8 @@
 // half2 atomics (:299-305) and is order-dependent in both implementations.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -123,8 +125,8 @@ __device__ __forceinline__ bool locate(const float *__restrict__ x, float scale,
     return oob;
 }
 
-template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(256)
+template <typename T, uint32_t D, uint32_t C, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 grid_forward_kernel(const float *__restrict__ inputs, const T *__restrict__ grid,
                     const int *__restrict__ offsets, T *__restrict__ outputs, uint32_t B, uint32_t L,
                     float S, uint32_t H, bool calc_grad_inputs, T *__restrict__ dy_dx, uint32_t gridtype,
@@ -158,6 +160,60 @@ grid_forward_kernel(const float *__restrict__ inputs, const T *__restrict__ grid
     float res[C];
 #pragma unroll
     for (uint32_t c = 0; c < C; c++) res[c] = 0;
+
+    if constexpr (!kHalf) {
+        // float32: ONE pass over the 2^D corners feeds the interpolation and all D derivative rows.  d out / d x_gd is
+        // scale * sum over corners of (+-1 by the corner's side along gd) * (product of the OTHER axes' weights) * feature;
+        // the reference walks the corners once more per axis (160 more gathers per (sample, level) at D = 5,
+        // gridencoder.cu:180-222) -- same sum, different association (parity 1e-6 relative, tests/test_gpu_ops.py).
+        // The interpolation itself keeps the reference's order of operations exactly.
+        float rg[D][C];
+#pragma unroll
+        for (uint32_t gd = 0; gd < D; gd++)
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) rg[gd][c] = 0;
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); idx++) {
+            float wd[D], pre[D + 1];
+            uint32_t pl[D];
+            pre[0] = 1;
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) {
+                if ((idx & (1u << d)) == 0) { wd[d] = 1 - pos[d]; pl[d] = pg[d]; }
+                else { wd[d] = pos[d]; pl[d] = pg[d] + 1; }
+                pre[d + 1] = pre[d] * wd[d];
+            }
+            const uint32_t index = grid_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+            float v[C];
+            load_feat<C>(grid + (size_t)index * C, v);
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) res[c] += pre[D] * v[c];
+            if (calc_grad_inputs) {
+                float suf = 1;
+#pragma unroll
+                for (int gd = (int)D - 1; gd >= 0; gd--) {
+                    const float e = pre[gd] * suf;
+                    const float coef = (idx & (1u << gd)) ? e : -e;
+#pragma unroll
+                    for (uint32_t c = 0; c < C; c++) rg[gd][c] += coef * v[c];
+                    suf *= wd[gd];
+                }
+            }
+        }
+        store_feat<C>(out, res);
+        if (calc_grad_inputs) {
+            T *dd = dy_dx + ((size_t)b * L + level) * D * C;
+#pragma unroll
+            for (uint32_t gd = 0; gd < D; gd++) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) rg[gd][c] *= scale;
+                store_feat<C>(dd + gd * C, rg[gd]);
+            }
+        }
+        return;
+    }
+
+    // float16 tables: the reference's loop structure, every c10::Half rounding in place (bit-identical results)
 #pragma unroll
     for (uint32_t idx = 0; idx < (1u << D); idx++) {
         float w = 1;
@@ -171,10 +227,7 @@ grid_forward_kernel(const float *__restrict__ inputs, const T *__restrict__ grid
         float v[C];
         load_feat<C>(grid + (size_t)index * C, v);
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) {
-            if constexpr (kHalf) res[c] = hr<T>(res[c] + hr<T>(w * v[c]));      // Half += float (:166)
-            else res[c] += w * v[c];
-        }
+        for (uint32_t c = 0; c < C; c++) res[c] = hr<T>(res[c] + hr<T>(w * v[c]));      // Half += float (:166)
     }
     store_feat<C>(out, res);
 
@@ -203,10 +256,7 @@ grid_forward_kernel(const float *__restrict__ inputs, const T *__restrict__ grid
                 load_feat<C>(grid + (size_t)il * C, vl);
                 load_feat<C>(grid + (size_t)ir * C, vr);
 #pragma unroll
-                for (uint32_t c = 0; c < C; c++) {
-                    if constexpr (kHalf) rg[c] = hr<T>(rg[c] + hr<T>(w * hr<T>(vr[c] - vl[c])));   // (:213)
-                    else rg[c] += w * (vr[c] - vl[c]);
-                }
+                for (uint32_t c = 0; c < C; c++) rg[c] = hr<T>(rg[c] + hr<T>(w * hr<T>(vr[c] - vl[c])));   // (:213)
             }
             store_feat<C>(dd + gd * C, rg);
         }
@@ -297,7 +347,13 @@ template <uint32_t D, uint32_t C, typename T>
 int launch_fwd(const float *in, const T *emb, const int *off, T *out, uint32_t B, uint32_t L, float S,
                uint32_t H, bool calc, T *dy_dx, uint32_t gt, bool ac, cudaStream_t st) {
     dim3 grid(sdb_div_up(B, 256u), L);
-    grid_forward_kernel<T, D, C><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
+    // the float32 kernel with dy_dx holds D*C + C accumulators and 2^D gathers in flight: 174 registers at one CTA per SM,
+    // 128 (56 B spilled) at two.  SDB_GRIDENC_MINB picks (default below = the faster one measured, profiles/r02_ops_timing.json)
+    static const int minb = [] { const char *e = getenv("SDB_GRIDENC_MINB"); return e ? atoi(e) : 1; }();
+    if (minb == 2 && D * C >= 32)
+        grid_forward_kernel<T, D, C, 2><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
+    else
+        grid_forward_kernel<T, D, C, 1><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }

@@ -27,4 +27,21 @@ for _ in range(2):
     ops.grid_encode_forward(x, emb, offsets, out, B, D, C, L, float(np.log2(pls)), H, True, dydx, 0, False)
     ops.grid_encode_backward(grad, x, emb, offsets, ge, B, D, C, L, float(np.log2(pls)), H, True, dydx, gi, 0, False)
 torch.cuda.synchronize()
-print('ok', float(out.abs().mean()), float(ge.abs().sum()))
+
+
+def ms(fn, reps=10):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+S = float(np.log2(pls))
+print('ok', float(out.abs().mean()), float(ge.abs().sum()), 'SDB_GRIDENC_MINB=%s' % __import__('os').environ.get('SDB_GRIDENC_MINB', 'default'),
+      'fwd+dy_dx %.3f ms, fwd %.3f ms, bwd(table+input) %.3f ms' % (
+          ms(lambda: ops.grid_encode_forward(x, emb, offsets, out, B, D, C, L, S, H, True, dydx, 0, False)),
+          ms(lambda: ops.grid_encode_forward(x, emb, offsets, out, B, D, C, L, S, H, False, dydx, 0, False)),
+          ms(lambda: ops.grid_encode_backward(grad, x, emb, offsets, ge, B, D, C, L, S, H, True, dydx, gi, 0, False))))
