@@ -348,8 +348,9 @@ int launch_fwd(const float *in, const T *emb, const int *off, T *out, uint32_t B
                uint32_t H, bool calc, T *dy_dx, uint32_t gt, bool ac, cudaStream_t st) {
     dim3 grid(sdb_div_up(B, 256u), L);
     // the float32 kernel with dy_dx holds D*C + C accumulators and 2^D gathers in flight: 174 registers at one CTA per SM,
-    // 128 (56 B spilled) at two.  SDB_GRIDENC_MINB picks (default below = the faster one measured, profiles/r02_ops_timing.json)
-    static const int minb = [] { const char *e = getenv("SDB_GRIDENC_MINB"); return e ? atoi(e) : 1; }();
+    // 128 (56 B spilled) at two.  Two is faster at D=5, C=8 (3.98 vs 4.88 ms on 599k samples, profiles/r02_gridenc_minb.log);
+    // SDB_GRIDENC_MINB=1 selects the other build.
+    static const int minb = [] { const char *e = getenv("SDB_GRIDENC_MINB"); return e ? atoi(e) : 2; }();
     if (minb == 2 && D * C >= 32)
         grid_forward_kernel<T, D, C, 2><<<grid, 256, 0, st>>>(in, emb, off, out, B, L, S, H, calc, dy_dx, gt, ac);
     else

@@ -5,7 +5,7 @@ python -m scenedreamer_b200.build > gpurun_out/build.log 2>&1 || { tail -20 gpur
 export OMP_WAIT_POLICY=PASSIVE GOMP_SPINCOUNT=0
 N=${1:-2}
 run() { n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n "$@"; }
-timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu --no-extras --mode strong > gpurun_out/strong_n1.json 2> gpurun_out/strong_n1.err
+[ "$N" = 1 ] && timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu --no-extras --mode strong > gpurun_out/strong_n1.json 2> gpurun_out/strong_n1.err
 timeout 400 bash -c "$(declare -f run); run $N --steps 10 --warmup 3 --mode strong" > gpurun_out/strong_nN.json 2> gpurun_out/strong_nN.err
 python - <<'PY'
 import json
