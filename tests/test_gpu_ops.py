@@ -353,9 +353,9 @@ def test_tcgen05_mn_major_operands_from_activation_tiles(G):
     assert float((c - ref).abs().max()) <= 1e-3
 
 
-def _sp_case(seed, ign_zero, strided_lut):
+def _sp_case(seed, ign_zero, strided_lut, C=40):
     g = torch.Generator().manual_seed(seed)
-    X, Y, Z, M, C = 9, 12, 10, 300, 40
+    X, Y, Z, M = 9, 12, 10, 300
     lut = torch.randint(0, M + (1 if ign_zero else 0), (X, Y, Z), generator=g, dtype=torch.int32)
     if strided_lut:
         lut = lut.permute(2, 0, 1).contiguous().permute(1, 2, 0)            # same values, non-contiguous strides
@@ -367,11 +367,13 @@ def _sp_case(seed, ign_zero, strided_lut):
     return lut, feat, wc
 
 
-@pytest.mark.parametrize('ign_zero,strided', [(False, False), (True, False), (True, True)])
-def test_sp_trilinear_worldcoord_vs_oracle_and_reference(ign_zero, strided):
+@pytest.mark.parametrize('ign_zero,strided,C', [(False, False, 40), (True, False, 40), (True, True, 40), (True, False, 64),
+                                                 (False, True, 7), (True, False, 132)])
+def test_sp_trilinear_worldcoord_vs_oracle_and_reference(ign_zero, strided, C):
     """voxlib.sp_trilinear_worldcoord[_backward] (surface parity): forward bit-exact against the CPU oracle and the
-    reference's own CUDA extension, backward (atomics) to 1e-5."""
-    lut, feat, wc = _sp_case(3, ign_zero, strided)
+    reference's own CUDA extension, backward (atomics) to 1e-5.  C = 40 / 64 / 132: float4 lanes (16, 16, 32 per entry, the
+    last with two chunks per lane); C = 7: the scalar kernel."""
+    lut, feat, wc = _sp_case(3, ign_zero, strided, C)
     out = ops.sp_trilinear_worldcoord(feat.to(DEV), lut.to(DEV) if not strided else lut.to(DEV), wc.to(DEV), ign_zero, -1)
     ref = oracle.sp_trilinear_worldcoord(feat, lut, wc, ign_zero)
     assert out.shape == wc.shape[:-1] + (feat.shape[1],)
