@@ -172,6 +172,13 @@ def main():
             sys.stdout.close()
             sys.stdout = stdout
 
+    # ---- a9 boundary op: positional encoding of the C2 frame's ray directions (pe degree 5 + original, the sky branch's input) ----
+    rdirs = torch.nn.functional.normalize(torch.randn(1, 570, 990, 1, 3, generator=g), dim=-1).to(DEV)
+    r = {'ours': dev_ms(lambda: ops.positional_encoding(rdirs, 5, -1, True))}
+    if rv is not None:
+        r['reference_cuda'] = dev_ms(lambda: rv.positional_encoding(rdirs, 5, -1, True))
+    out['a9_positional_encoding_564k_rays'] = r
+
     # ---- voxlib surface: sp_trilinear ----
     lut = torch.randint(0, 200000, (64, 256, 256), generator=g, dtype=torch.int32).to(DEV)
     feat = torch.randn(200000, 64, generator=g).to(DEV)
