@@ -353,6 +353,7 @@ mlp_kernel(const Params p)
                     tc05::mbar_wait(&bars[B_ACC], (n * NH + l) & 1);
                     tc05::fence_after_thread_sync();
                     if ((tid & 127) == 0) SDB_MARK(half, 2, n, l);
+                    if ((tid & 127) == 0) SDB_STAMP(n, l, 2 + 2 * half);
 #pragma unroll 1
                     for (int c0 = 0; c0 < 128; c0 += 32) {
                         // a 32-column chunk in two 16-column halves (16 live accumulator registers instead of 32: the
@@ -424,6 +425,7 @@ mlp_kernel(const Params p)
                     }
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (g & 1u)]);        // accumulator buffer (g & 1) is free again
+                    if ((tid & 127) == 0) SDB_STAMP(n, l, 3 + 2 * half);
                     if (MODE == kRender && l == 3) sSig[half * kRows + row] = sig_part;
                     if constexpr (TRAIN) {   // the constant-1 column that turns the weight-gradient GEMM's column 256 into the bias gradient
                         if (half == 0) {
@@ -438,6 +440,7 @@ mlp_kernel(const Params p)
                 if ((tid & 127) == 0) SDB_MARK(half, 3, n, NH);
                 tc05::mbar_wait(&bars[B_OUTRDY], n & 1);
                 if ((tid & 127) == 0) SDB_MARK(half, 4, n, NH);
+                if ((tid & 127) == 0) SDB_STAMP(n, NH, 2 + 2 * half);
                 tc05::fence_after_thread_sync();
                 if constexpr (SKYBWD) {
                     // last layer of the sky chain: dA1 [128 x 256] -> dZ1 = dA1 * LeakyReLU'(z1) -> bf16 record only
@@ -459,6 +462,8 @@ mlp_kernel(const Params p)
                     }
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
+                if ((tid & 127) == 0) SDB_STAMP(n, NH, 3 + 2 * half);
+                    if ((tid & 127) == 0) SDB_STAMP(n, NH, 3 + 2 * half);
                     continue;
                 }
                 float c[32];
@@ -470,6 +475,8 @@ mlp_kernel(const Params p)
                     tc05::tmem_ld_wait();
                     tc05::fence_before_thread_sync();
                     tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
+                if ((tid & 127) == 0) SDB_STAMP(n, NH, 3 + 2 * half);
+                    if ((tid & 127) == 0) SDB_STAMP(n, NH, 3 + 2 * half);
                     float *dst = p.tr.dx0 + slot * kFeat + half * 64;
 #pragma unroll
                     for (int q = 0; q < 4; q++) st_global_v8f(dst + 8 * q, &c[8 * q]);
@@ -480,6 +487,7 @@ mlp_kernel(const Params p)
                 tc05::tmem_ld_wait();
                 tc05::fence_before_thread_sync();
                 tc05::mbar_arrive(&bars[B_EPIDONE + (go & 1u)]);
+                if ((tid & 127) == 0) SDB_STAMP(n, NH, 3 + 2 * half);
                 if constexpr (SKY) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) outc[j] = c[j];
@@ -747,6 +755,7 @@ mlp_kernel(const Params p)
                     if (lane == 0) SDB_MARK(2, 1, n, l);
                     if (g >= 2) tc05::mbar_wait(&bars[B_EPIDONE + buf], ((g >> 1) - 1) & 1);
                     if (l == 0) tc05::mbar_wait(&bars[B_FEAT], nodd);
+                    if (lane == 0) SDB_STAMP(n, l, 0);
                     const int N = layerN<MODE>(l);                                  // compile-time after unrolling
                     const uint32_t idesc = tc05::make_idesc(kRows, N, BF16);
                     const uint32_t slab16 = (uint32_t)(N * 32) >> 4;              // one part of one k16 slab, in 16-byte units
@@ -790,6 +799,7 @@ mlp_kernel(const Params p)
                                     }
                                     tc05::mma_commit(&bars[B_WEMPTY + stg]);
                                     if (j == num_stages<KS, MODE>(l) - 1) {
+                                        SDB_STAMP(n, l, 1);
                                         if (l == NL - 1) {
                                             tc05::mma_commit(&bars[B_OUTRDY]);
                                             tc05::mma_commit(&bars[B_HFREE]);
