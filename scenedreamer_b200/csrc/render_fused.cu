@@ -129,6 +129,51 @@ __device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint
     }
 }
 
+// The same level for the TWO rays of a lane pair (3-D pre-blended table).  Lanes 2k / 2k+1 each fetch one 16-byte half
+// (`part`) of every corner row of BOTH rays: a warp-wide LDG.128 then touches 16 sectors and uses all 32 bytes of each, where
+// the one-ray-per-lane form touches 32 sectors twice (once per half) -- half the L1 wavefronts for the same bytes.  The gather
+// shares the LSU with the epilogue's operand stores, and its burst is what stretches the epilogues of fc_3 / fc_4
+// (profiles/r02_render_timeline.txt).  Per feature the arithmetic is encode_level<false>'s, operation for operation.
+__device__ __forceinline__ void encode_level_pair(const float *__restrict__ tbl, uint32_t mask, float scale, const float (&xa)[3],
+                                                  const float (&xb)[3], bool oob_a, bool oob_b, int part, float (&ra)[4],
+                                                  float (&rb)[4]) {
+    float fa[3], fb[3];
+    uint32_t ga[3], gb[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float pa = fmaf(xa[d], scale, 0.5f), pb = fmaf(xb[d], scale, 0.5f);
+        ga[d] = (uint32_t)floorf(pa);
+        gb[d] = (uint32_t)floorf(pb);
+        fa[d] = pa - (float)ga[d];
+        fb[d] = pb - (float)gb[d];
+    }
+    const uint32_t a0[2] = {ga[0], ga[0] + 1u}, a1[2] = {ga[1] * kPrime1, (ga[1] + 1u) * kPrime1},
+                   a2[2] = {ga[2] * kPrime2, (ga[2] + 1u) * kPrime2};
+    const uint32_t b0[2] = {gb[0], gb[0] + 1u}, b1[2] = {gb[1] * kPrime1, (gb[1] + 1u) * kPrime1},
+                   b2[2] = {gb[2] * kPrime2, (gb[2] + 1u) * kPrime2};
+#pragma unroll
+    for (int c = 0; c < 4; c++) { ra[c] = 0.0f; rb[c] = 0.0f; }
+    const float *tp = tbl + part * 4;
+#pragma unroll
+    for (int idx = 0; idx < 8; idx++) {
+        const int c0 = idx & 1, c1 = (idx >> 1) & 1, c2 = (idx >> 2) & 1;
+        if (!oob_a) {
+            float w = c0 ? fa[0] : 1.0f - fa[0];
+            w *= c1 ? fa[1] : 1.0f - fa[1];
+            w *= c2 ? fa[2] : 1.0f - fa[2];
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((a0[c0] ^ a1[c1] ^ a2[c2]) & mask) * 8));
+            ra[0] = fmaf(w, v.x, ra[0]); ra[1] = fmaf(w, v.y, ra[1]); ra[2] = fmaf(w, v.z, ra[2]); ra[3] = fmaf(w, v.w, ra[3]);
+        }
+        if (!oob_b) {
+            float w = c0 ? fb[0] : 1.0f - fb[0];
+            w *= c1 ? fb[1] : 1.0f - fb[1];
+            w *= c2 ? fb[2] : 1.0f - fb[2];
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((b0[c0] ^ b1[c1] ^ b2[c2]) & mask) * 8));
+            rb[0] = fmaf(w, v.x, rb[0]); rb[1] = fmaf(w, v.y, rb[1]); rb[2] = fmaf(w, v.z, rb[2]); rb[3] = fmaf(w, v.w, rb[3]);
+        }
+    }
+}
+
 // 8 fp32 values -> one 16-byte chunk of 16-bit operand (hi) and, for the x3 split, the residual (lo)
 // PREC: 0 = fp16 single pass, 1 = bf16 hi/lo split, 2 = fp16 hi/lo split
 template <int PREC>
@@ -1024,17 +1069,42 @@ mlp_kernel(const Params p)
                             if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
                         }
                     }
+                    if (p.pair_gather) {
+                        // lane pair (2k, 2k+1) = rays A (even lane's) and B (odd lane's): see encode_level_pair
+                        const int part = gt & 1;
+                        float xo[3];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int level = half + 2 * i;
-                        float res[8];
-                        if (oob) {
+                        for (int k = 0; k < 3; k++) xo[k] = __shfl_xor_sync(0xffffffffu, x5[k], 1);
+                        const bool oobo = __shfl_xor_sync(0xffffffffu, (int)oob, 1) != 0;
+                        const float xa[3] = {part ? xo[0] : x5[0], part ? xo[1] : x5[1], part ? xo[2] : x5[2]};
+                        const float xb[3] = {part ? x5[0] : xo[0], part ? x5[1] : xo[1], part ? x5[2] : xo[2]};
+                        const bool oob_a = part ? oobo : oob, oob_b = part ? oob : oobo;
 #pragma unroll
-                            for (int c = 0; c < 8; c++) res[c] = 0.0f;
-                        } else {
-                            encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                        for (int i = 0; i < 8; i++) {
+                            const int level = half + 2 * i;
+                            float ra[4], rb[4], res[8];
+                            encode_level_pair(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], xa, xb, oob_a, oob_b, part, ra, rb);
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const float got = __shfl_xor_sync(0xffffffffu, part ? ra[c] : rb[c], 1);   // the other half of MY ray
+                                res[c] = part ? got : ra[c];            // features 0-3: computed by the even lane
+                                res[4 + c] = part ? rb[c] : got;        // features 4-7: computed by the odd lane
+                            }
+                            split8<PREC>(res, fh[i], fl[i]);
                         }
-                        split8<PREC>(res, fh[i], fl[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int level = half + 2 * i;
+                            float res[8];
+                            if (oob) {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) res[c] = 0.0f;
+                            } else {
+                                encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                            }
+                            split8<PREC>(res, fh[i], fl[i]);
+                        }
                     }
                     const uint32_t label = (labs >> (4 * sm.idx)) & 15u;
                     uint32_t oh[4] = {0u, 0u, 0u, 0u};
@@ -1671,6 +1741,10 @@ int params_from_abi(const sdb_render_params *sp, Params &p)
     p.net_out = sp->d_net_out; p.depth_out = sp->d_depth_out; p.total_weight = sp->d_total_weight;
     p.weights_out = sp->d_weights_out; p.rdepth_out = sp->d_rand_depth_out;
     p.debug = g_debug_buffer;
+    {
+        const char *env_pg = getenv("SDB_PAIR_GATHER");
+        p.pair_gather = (env_pg == nullptr || env_pg[0] != '0') ? 1 : 0;
+    }
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
     p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
     if (!sp->d_cam_ori) p.cam_ori = reinterpret_cast<const float *>((const int32_t *)sp->d_workspace + 4 + p.n_tiles);

@@ -213,6 +213,7 @@ struct Params {
     float *sky_out;                // [R, 64]
     float *sky_partial;            // [n_tiles, 64] per-tile column sums (deterministic mean)
     int32_t *debug;                // optional host-mapped progress buffer (diagnostics), else nullptr
+    int pair_gather;               // ray slots: lane pairs share every corner row's two 16-byte halves (SDB_PAIR_GATHER, default 1)
     TrainBuf tr;                   // training record (TRAIN forward writes it, the kBwd chain reads it)
 };
 
