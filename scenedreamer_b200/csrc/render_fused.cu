@@ -215,7 +215,7 @@ template <int PREC> __device__ __forceinline__ uint32_t one16() { return PREC ==
 // tile no longer marches until its slowest ray is opaque: per C2 frame 4.4-4.7 M + ~0.5 M (one wasted step per terminated ray)
 // instead of 6.5-6.8 M samples are shaded (tools/ray_stats.py).  The CTA runs ONE open-ended "tile": the loop control of all four
 // roles is the early-termination mechanism below (stop_step decided by the epilogue two steps ahead).
-template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const Params p)
 {
@@ -1069,7 +1069,7 @@ mlp_kernel(const Params p)
                             if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
                         }
                     }
-                    if (p.pair_gather) {
+                    if constexpr (PAIR) {
                         // lane pair (2k, 2k+1) = rays A (even lane's) and B (odd lane's): see encode_level_pair
                         const int part = gt & 1;
                         float xo[3];
@@ -1505,14 +1505,14 @@ int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels
     return SDB_OK;
 }
 
-template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false, bool PAIR = false>
 int launch_mlp(const Params &p, int grid, cudaStream_t st) {
     const size_t smem = smem_map(PREC != 0).total;
     cudaFuncAttributes fa;
-    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>));
+    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, PAIR>));
     if (fa.numRegs < kRegsLaunch) return SDB_EUNSUPPORTED;   // setmaxnreg pool would be too small: refuse rather than hang
-    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ><<<grid, kThreads, smem, st>>>(p);
+    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, PAIR><<<grid, kThreads, smem, st>>>(p);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
@@ -1792,6 +1792,7 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         int rc;
         if (sp->precision == 0) rc = launch_mlp<0, false, kRender, false, true>(p, grid, st);
         else if (sp->precision == 1) rc = launch_mlp<1, false, kRender, false, true>(p, grid, st);
+        else if (p.pair_gather) rc = launch_mlp<2, false, kRender, false, true, true>(p, grid, st);
         else rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
         if (rc != SDB_OK) return rc;
         set_flag_kernel<<<1, 1, 0, st>>>(ws + 3);

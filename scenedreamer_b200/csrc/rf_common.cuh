@@ -226,12 +226,15 @@ struct Params {
         }                                                                         \
     } while (0)
 
-// timeline of CTA 0 (diagnostics, tools/render_timeline.py): with debug[60] == kTraceMagic, sample steps
+// timeline of CTA 0 (diagnostics, tools/render_timeline.py; library built with SDB_NVCC_EXTRA=-DSDB_TIMELINE): with debug[60] == kTraceMagic, sample steps
 // debug[61] .. debug[61]+kTraceSteps-1 of the CTA record clock() stamps, debug[64 + ((n - first) * 8 + layer) * 8 + slot]:
 //   slot 0 issuer: operands of the layer's first stage may be waited for   1 issuer: last MMA of the layer issued
 //   slot 2/4 epilogue half 0/1: accumulator of the layer complete          3/5 epilogue half 0/1: last slab handed over
 constexpr int32_t kTraceMagic = 0x7131;
 constexpr int kTraceSteps = 6;
+#ifndef SDB_TIMELINE
+#define SDB_STAMP(n_, layer, slot) do { } while (0)      // compiled out: the stamps cost the epilogue role registers (spills)
+#else
 #define SDB_STAMP(n_, layer, slot)                                                                                 \
     do {                                                                                                           \
         if (p.debug != nullptr && blockIdx.x == 0 && p.debug[60] == kTraceMagic) {                                 \
@@ -239,6 +242,7 @@ constexpr int kTraceSteps = 6;
             if (rel__ >= 0 && rel__ < kTraceSteps) p.debug[64 + (rel__ * 8 + (layer)) * 8 + (slot)] = (int32_t)clock(); \
         }                                                                                                          \
     } while (0)
+#endif
 
 __device__ __constant__ uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u, kPrime3 = 3674653429u, kPrime4 = 2097192037u;
 

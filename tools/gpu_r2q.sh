@@ -13,4 +13,9 @@ d=json.loads(open('gpurun_out/bench_pg$v.json').read().strip().splitlines()[-1])
 print('pair_gather=$v value %.1f e2e %.1f exact %.1f ms/step %.2f kernel_ms %.3f frac %.3f clocks %s' % (d['value'], d['e2e']['value'], d['value_exact_march'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['clocks']['sm_mhz']))
 PY
 done
-PYTHONPATH=. timeout 300 python tools/render_timeline.py 60 > gpurun_out/render_timeline_pg1.txt 2> gpurun_out/render_timeline.err; cat gpurun_out/render_timeline_pg1.txt | tail -10; tail -3 gpurun_out/render_timeline.err
+# diagnostics build for the timeline (stamps compiled in), then back to the product build
+SDB_NVCC_EXTRA=-DSDB_TIMELINE python -m scenedreamer_b200.build > gpurun_out/build_tl.log 2>&1
+for v in 1 0; do
+SDB_PAIR_GATHER=$v PYTHONPATH=. timeout 300 python tools/render_timeline.py 60 > gpurun_out/render_timeline_pg$v.txt 2> gpurun_out/render_timeline.err; tail -10 gpurun_out/render_timeline_pg$v.txt; tail -3 gpurun_out/render_timeline.err
+done
+python -m scenedreamer_b200.build > gpurun_out/build.log 2>&1
