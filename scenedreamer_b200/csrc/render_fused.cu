@@ -135,8 +135,9 @@ __device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint
 // shares the LSU with the epilogue's operand stores, and its burst is what stretches the epilogues of fc_3 / fc_4
 // (profiles/r02_render_timeline.txt).  Per feature the arithmetic is encode_level<false>'s, operation for operation.
 __device__ __forceinline__ void encode_level_pair(const float *__restrict__ tbl, uint32_t mask, float scale, const float (&xa)[3],
-                                                  const float (&xb)[3], bool oob_a, bool oob_b, int part, float (&ra)[4],
-                                                  float (&rb)[4]) {
+                                                  const float (&xb)[3], int part, float (&ra)[4], float (&rb)[4]) {
+    // No branches: the 16 loads of a level are independent and issue back to back.  A ray outside the volume (or an idle slot)
+    // still produces in-range addresses (the index is masked); its caller discards the result.
     float fa[3], fb[3];
     uint32_t ga[3], gb[3];
 #pragma unroll
@@ -151,26 +152,26 @@ __device__ __forceinline__ void encode_level_pair(const float *__restrict__ tbl,
                    a2[2] = {ga[2] * kPrime2, (ga[2] + 1u) * kPrime2};
     const uint32_t b0[2] = {gb[0], gb[0] + 1u}, b1[2] = {gb[1] * kPrime1, (gb[1] + 1u) * kPrime1},
                    b2[2] = {gb[2] * kPrime2, (gb[2] + 1u) * kPrime2};
-#pragma unroll
-    for (int c = 0; c < 4; c++) { ra[c] = 0.0f; rb[c] = 0.0f; }
     const float *tp = tbl + part * 4;
+    float4 va[8], vb[8];
 #pragma unroll
     for (int idx = 0; idx < 8; idx++) {
         const int c0 = idx & 1, c1 = (idx >> 1) & 1, c2 = (idx >> 2) & 1;
-        if (!oob_a) {
-            float w = c0 ? fa[0] : 1.0f - fa[0];
-            w *= c1 ? fa[1] : 1.0f - fa[1];
-            w *= c2 ? fa[2] : 1.0f - fa[2];
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((a0[c0] ^ a1[c1] ^ a2[c2]) & mask) * 8));
-            ra[0] = fmaf(w, v.x, ra[0]); ra[1] = fmaf(w, v.y, ra[1]); ra[2] = fmaf(w, v.z, ra[2]); ra[3] = fmaf(w, v.w, ra[3]);
-        }
-        if (!oob_b) {
-            float w = c0 ? fb[0] : 1.0f - fb[0];
-            w *= c1 ? fb[1] : 1.0f - fb[1];
-            w *= c2 ? fb[2] : 1.0f - fb[2];
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((b0[c0] ^ b1[c1] ^ b2[c2]) & mask) * 8));
-            rb[0] = fmaf(w, v.x, rb[0]); rb[1] = fmaf(w, v.y, rb[1]); rb[2] = fmaf(w, v.z, rb[2]); rb[3] = fmaf(w, v.w, rb[3]);
-        }
+        va[idx] = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((a0[c0] ^ a1[c1] ^ a2[c2]) & mask) * 8));
+        vb[idx] = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((b0[c0] ^ b1[c1] ^ b2[c2]) & mask) * 8));
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) { ra[c] = 0.0f; rb[c] = 0.0f; }
+#pragma unroll
+    for (int idx = 0; idx < 8; idx++) {
+        const int c0 = idx & 1, c1 = (idx >> 1) & 1, c2 = (idx >> 2) & 1;
+        float wa = c0 ? fa[0] : 1.0f - fa[0], wb = c0 ? fb[0] : 1.0f - fb[0];
+        wa *= c1 ? fa[1] : 1.0f - fa[1];
+        wb *= c1 ? fb[1] : 1.0f - fb[1];
+        wa *= c2 ? fa[2] : 1.0f - fa[2];
+        wb *= c2 ? fb[2] : 1.0f - fb[2];
+        ra[0] = fmaf(wa, va[idx].x, ra[0]); ra[1] = fmaf(wa, va[idx].y, ra[1]); ra[2] = fmaf(wa, va[idx].z, ra[2]); ra[3] = fmaf(wa, va[idx].w, ra[3]);
+        rb[0] = fmaf(wb, vb[idx].x, rb[0]); rb[1] = fmaf(wb, vb[idx].y, rb[1]); rb[2] = fmaf(wb, vb[idx].z, rb[2]); rb[3] = fmaf(wb, vb[idx].w, rb[3]);
     }
 }
 
@@ -1075,20 +1076,18 @@ mlp_kernel(const Params p)
                         float xo[3];
 #pragma unroll
                         for (int k = 0; k < 3; k++) xo[k] = __shfl_xor_sync(0xffffffffu, x5[k], 1);
-                        const bool oobo = __shfl_xor_sync(0xffffffffu, (int)oob, 1) != 0;
                         const float xa[3] = {part ? xo[0] : x5[0], part ? xo[1] : x5[1], part ? xo[2] : x5[2]};
                         const float xb[3] = {part ? x5[0] : xo[0], part ? x5[1] : xo[1], part ? x5[2] : xo[2]};
-                        const bool oob_a = part ? oobo : oob, oob_b = part ? oob : oobo;
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const int level = half + 2 * i;
                             float ra[4], rb[4], res[8];
-                            encode_level_pair(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], xa, xb, oob_a, oob_b, part, ra, rb);
+                            encode_level_pair(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], xa, xb, part, ra, rb);
 #pragma unroll
                             for (int c = 0; c < 4; c++) {
                                 const float got = __shfl_xor_sync(0xffffffffu, part ? ra[c] : rb[c], 1);   // the other half of MY ray
-                                res[c] = part ? got : ra[c];            // features 0-3: computed by the even lane
-                                res[4 + c] = part ? rb[c] : got;        // features 4-7: computed by the odd lane
+                                res[c] = oob ? 0.0f : (part ? got : ra[c]);         // features 0-3: computed by the even lane
+                                res[4 + c] = oob ? 0.0f : (part ? rb[c] : got);     // features 4-7: computed by the odd lane
                             }
                             split8<PREC>(res, fh[i], fl[i]);
                         }

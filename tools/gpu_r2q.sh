@@ -13,6 +13,7 @@ d=json.loads(open('gpurun_out/bench_pg$v.json').read().strip().splitlines()[-1])
 print('pair_gather=$v value %.1f e2e %.1f exact %.1f ms/step %.2f kernel_ms %.3f frac %.3f clocks %s' % (d['value'], d['e2e']['value'], d['value_exact_march'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['clocks']['sm_mhz']))
 PY
 done
+[ -n "$SKIP_TIMELINE" ] && exit 0
 # diagnostics build for the timeline (stamps compiled in), then back to the product build
 SDB_NVCC_EXTRA=-DSDB_TIMELINE python -m scenedreamer_b200.build > gpurun_out/build_tl.log 2>&1
 for v in 1 0; do
