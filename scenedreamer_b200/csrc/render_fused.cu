@@ -129,52 +129,6 @@ __device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint
     }
 }
 
-// The same level for the TWO rays of a lane pair (3-D pre-blended table).  Lanes 2k / 2k+1 each fetch one 16-byte half
-// (`part`) of every corner row of BOTH rays: a warp-wide LDG.128 then touches 16 sectors and uses all 32 bytes of each, where
-// the one-ray-per-lane form touches 32 sectors twice (once per half) -- half the L1 wavefronts for the same bytes.  The gather
-// shares the LSU with the epilogue's operand stores, and its burst is what stretches the epilogues of fc_3 / fc_4
-// (profiles/r02_render_timeline.txt).  Per feature the arithmetic is encode_level<false>'s, operation for operation.
-__device__ __forceinline__ void encode_level_pair(const float *__restrict__ tbl, uint32_t mask, float scale, const float (&xa)[3],
-                                                  const float (&xb)[3], int part, float (&ra)[4], float (&rb)[4]) {
-    // No branches: the 16 loads of a level are independent and issue back to back.  A ray outside the volume (or an idle slot)
-    // still produces in-range addresses (the index is masked); its caller discards the result.
-    float fa[3], fb[3];
-    uint32_t ga[3], gb[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        const float pa = fmaf(xa[d], scale, 0.5f), pb = fmaf(xb[d], scale, 0.5f);
-        ga[d] = (uint32_t)floorf(pa);
-        gb[d] = (uint32_t)floorf(pb);
-        fa[d] = pa - (float)ga[d];
-        fb[d] = pb - (float)gb[d];
-    }
-    const uint32_t a0[2] = {ga[0], ga[0] + 1u}, a1[2] = {ga[1] * kPrime1, (ga[1] + 1u) * kPrime1},
-                   a2[2] = {ga[2] * kPrime2, (ga[2] + 1u) * kPrime2};
-    const uint32_t b0[2] = {gb[0], gb[0] + 1u}, b1[2] = {gb[1] * kPrime1, (gb[1] + 1u) * kPrime1},
-                   b2[2] = {gb[2] * kPrime2, (gb[2] + 1u) * kPrime2};
-    const float *tp = tbl + part * 4;
-    float4 va[8], vb[8];
-#pragma unroll
-    for (int idx = 0; idx < 8; idx++) {
-        const int c0 = idx & 1, c1 = (idx >> 1) & 1, c2 = (idx >> 2) & 1;
-        va[idx] = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((a0[c0] ^ a1[c1] ^ a2[c2]) & mask) * 8));
-        vb[idx] = __ldg(reinterpret_cast<const float4 *>(tp + (size_t)((b0[c0] ^ b1[c1] ^ b2[c2]) & mask) * 8));
-    }
-#pragma unroll
-    for (int c = 0; c < 4; c++) { ra[c] = 0.0f; rb[c] = 0.0f; }
-#pragma unroll
-    for (int idx = 0; idx < 8; idx++) {
-        const int c0 = idx & 1, c1 = (idx >> 1) & 1, c2 = (idx >> 2) & 1;
-        float wa = c0 ? fa[0] : 1.0f - fa[0], wb = c0 ? fb[0] : 1.0f - fb[0];
-        wa *= c1 ? fa[1] : 1.0f - fa[1];
-        wb *= c1 ? fb[1] : 1.0f - fb[1];
-        wa *= c2 ? fa[2] : 1.0f - fa[2];
-        wb *= c2 ? fb[2] : 1.0f - fb[2];
-        ra[0] = fmaf(wa, va[idx].x, ra[0]); ra[1] = fmaf(wa, va[idx].y, ra[1]); ra[2] = fmaf(wa, va[idx].z, ra[2]); ra[3] = fmaf(wa, va[idx].w, ra[3]);
-        rb[0] = fmaf(wb, vb[idx].x, rb[0]); rb[1] = fmaf(wb, vb[idx].y, rb[1]); rb[2] = fmaf(wb, vb[idx].z, rb[2]); rb[3] = fmaf(wb, vb[idx].w, rb[3]);
-    }
-}
-
 // 8 fp32 values -> one 16-byte chunk of 16-bit operand (hi) and, for the x3 split, the residual (lo)
 // PREC: 0 = fp16 single pass, 1 = bf16 hi/lo split, 2 = fp16 hi/lo split
 template <int PREC>
@@ -216,7 +170,7 @@ template <int PREC> __device__ __forceinline__ uint32_t one16() { return PREC ==
 // tile no longer marches until its slowest ray is opaque: per C2 frame 4.4-4.7 M + ~0.5 M (one wasted step per terminated ray)
 // instead of 6.5-6.8 M samples are shaded (tools/ray_stats.py).  The CTA runs ONE open-ended "tile": the loop control of all four
 // roles is the early-termination mechanism below (stop_step decided by the epilogue two steps ahead).
-template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false, bool PAIR = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const Params p)
 {
@@ -987,6 +941,7 @@ mlp_kernel(const Params p)
                         tc05::mbar_wait_backoff(&bars[B_COMP], (uint32_t)(s - 2) & 1u, 32);    // done flags (and stop decision) of step s - 2
                         if (s >= sStop[0]) break;
                     }
+                    if (gt == 0) SDB_STAMP(n, 7, 0);                   // (timeline row 7 = this role, preparing step n)
                     if (half == 0) {
                         const int2 cur = sCur[row];
                         int rq = cur.x, sr = cur.y + 1;
@@ -1051,6 +1006,7 @@ mlp_kernel(const Params p)
                         sCur[row] = make_int2(rq, sr);
                     }
                     asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (gt == 0) SDB_STAMP(n, 7, 1);
                     const int2 cur = sCur[row];
                     const bool act = cur.x >= 0;
                     const uint32_t labs = __float_as_uint(st[kStLab * kRows + row]);
@@ -1070,40 +1026,17 @@ mlp_kernel(const Params p)
                             if (x5[k] < 0.0f || x5[k] > 1.0f) oob = true;       // gridencoder.cu:98-104
                         }
                     }
-                    if constexpr (PAIR) {
-                        // lane pair (2k, 2k+1) = rays A (even lane's) and B (odd lane's): see encode_level_pair
-                        const int part = gt & 1;
-                        float xo[3];
 #pragma unroll
-                        for (int k = 0; k < 3; k++) xo[k] = __shfl_xor_sync(0xffffffffu, x5[k], 1);
-                        const float xa[3] = {part ? xo[0] : x5[0], part ? xo[1] : x5[1], part ? xo[2] : x5[2]};
-                        const float xb[3] = {part ? x5[0] : xo[0], part ? x5[1] : xo[1], part ? x5[2] : xo[2]};
+                    for (int i = 0; i < 8; i++) {
+                        const int level = half + 2 * i;
+                        float res[8];
+                        if (oob) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int level = half + 2 * i;
-                            float ra[4], rb[4], res[8];
-                            encode_level_pair(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], xa, xb, part, ra, rb);
-#pragma unroll
-                            for (int c = 0; c < 4; c++) {
-                                const float got = __shfl_xor_sync(0xffffffffu, part ? ra[c] : rb[c], 1);   // the other half of MY ray
-                                res[c] = oob ? 0.0f : (part ? got : ra[c]);         // features 0-3: computed by the even lane
-                                res[4 + c] = oob ? 0.0f : (part ? rb[c] : got);     // features 4-7: computed by the odd lane
-                            }
-                            split8<PREC>(res, fh[i], fl[i]);
+                            for (int c = 0; c < 8; c++) res[c] = 0.0f;
+                        } else {
+                            encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int level = half + 2 * i;
-                            float res[8];
-                            if (oob) {
-#pragma unroll
-                                for (int c = 0; c < 8; c++) res[c] = 0.0f;
-                            } else {
-                                encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
-                            }
-                            split8<PREC>(res, fh[i], fl[i]);
-                        }
+                        split8<PREC>(res, fh[i], fl[i]);
                     }
                     const uint32_t label = (labs >> (4 * sm.idx)) & 15u;
                     uint32_t oh[4] = {0u, 0u, 0u, 0u};
@@ -1118,7 +1051,9 @@ mlp_kernel(const Params p)
                         sInfo[(s & 3) * kRows + row] = make_uint4(__float_as_uint(sm.depth), __float_as_uint(sm.nd), (uint32_t)cur.x, code);
                     }
                     if (gt == 0) sExh[s & 3] = sExh[4];               // after the bar.sync: every fetch of this step has been made
+                    if (gt == 0) SDB_STAMP(n, 7, 2);
                     if (n > 0) tc05::mbar_wait_backoff(&bars[B_HFREE], (n - 1) & 1);
+                    if (gt == 0) SDB_STAMP(n, 7, 3);
                     if (s >= 2 && s >= sStop[0]) break;                // the CTA ended before this step: drop the features
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
@@ -1504,14 +1439,14 @@ int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels
     return SDB_OK;
 }
 
-template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false, bool PAIR = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false>
 int launch_mlp(const Params &p, int grid, cudaStream_t st) {
     const size_t smem = smem_map(PREC != 0).total;
     cudaFuncAttributes fa;
-    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, PAIR>));
+    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>));
     if (fa.numRegs < kRegsLaunch) return SDB_EUNSUPPORTED;   // setmaxnreg pool would be too small: refuse rather than hang
-    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, PAIR><<<grid, kThreads, smem, st>>>(p);
+    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ><<<grid, kThreads, smem, st>>>(p);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
@@ -1740,10 +1675,6 @@ int params_from_abi(const sdb_render_params *sp, Params &p)
     p.net_out = sp->d_net_out; p.depth_out = sp->d_depth_out; p.total_weight = sp->d_total_weight;
     p.weights_out = sp->d_weights_out; p.rdepth_out = sp->d_rand_depth_out;
     p.debug = g_debug_buffer;
-    {
-        const char *env_pg = getenv("SDB_PAIR_GATHER");
-        p.pair_gather = (env_pg == nullptr || env_pg[0] != '0') ? 1 : 0;
-    }
     p.tiles_x = sdb_div_up(p.W, kTileW); p.tiles_y = sdb_div_up(p.H, kTileH);
     p.n_tiles = p.n_img * p.tiles_x * p.tiles_y;
     if (!sp->d_cam_ori) p.cam_ori = reinterpret_cast<const float *>((const int32_t *)sp->d_workspace + 4 + p.n_tiles);
@@ -1791,7 +1722,6 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         int rc;
         if (sp->precision == 0) rc = launch_mlp<0, false, kRender, false, true>(p, grid, st);
         else if (sp->precision == 1) rc = launch_mlp<1, false, kRender, false, true>(p, grid, st);
-        else if (p.pair_gather) rc = launch_mlp<2, false, kRender, false, true, true>(p, grid, st);
         else rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
         if (rc != SDB_OK) return rc;
         set_flag_kernel<<<1, 1, 0, st>>>(ws + 3);

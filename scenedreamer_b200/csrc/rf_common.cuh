@@ -213,7 +213,6 @@ struct Params {
     float *sky_out;                // [R, 64]
     float *sky_partial;            // [n_tiles, 64] per-tile column sums (deterministic mean)
     int32_t *debug;                // optional host-mapped progress buffer (diagnostics), else nullptr
-    int pair_gather;               // ray slots: lane pairs share every corner row's two 16-byte halves (SDB_PAIR_GATHER, default 1)
     TrainBuf tr;                   // training record (TRAIN forward writes it, the kBwd chain reads it)
 };
 
@@ -230,6 +229,7 @@ struct Params {
 // debug[61] .. debug[61]+kTraceSteps-1 of the CTA record clock() stamps, debug[64 + ((n - first) * 8 + layer) * 8 + slot]:
 //   slot 0 issuer: operands of the layer's first stage may be waited for   1 issuer: last MMA of the layer issued
 //   slot 2/4 epilogue half 0/1: accumulator of the layer complete          3/5 epilogue half 0/1: last slab handed over
+//   layer row 7 = the gather role preparing step n: 0 compositing of step n-2 seen, 1 slots refilled, 2 features gathered, 3 operand buffer free
 constexpr int32_t kTraceMagic = 0x7131;
 constexpr int kTraceSteps = 6;
 #ifndef SDB_TIMELINE

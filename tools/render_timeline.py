@@ -56,4 +56,11 @@ for s in range(1, 5):
     step = d(t[s + 1, 0][0], t[s, 0][0])
     tot += np.array([sum(mma), step, 0, 0, 0])
     cnt += 1
+print('# gather role preparing step n+1, relative to the issuer entering fc_1 of step n (cycles): start (compositing of n-1 seen), slots refilled,')
+print('#   features gathered (all loads + interpolation done), operand buffer free (colour-layer MMAs of step n retired)')
+for s in range(1, 5):
+    g = t[s + 1, 7]
+    base = t[s, 0][0]
+    print('gather for step %d: %s   | issuer layer starts of step %d: %s' % (first + s + 1, [d(g[k], base) for k in range(4)], first + s,
+                                                                              [d(t[s, l][0], base) for l in range(NL)]))
 print('step period (issuer, fc_1 to fc_1): %s cycles; MMA floor per step %d' % ([d(t[s + 1, 0][0], t[s, 0][0]) for s in range(0, 5)], sum(mma)))
