@@ -129,6 +129,37 @@ __device__ __forceinline__ void encode_level(const float *__restrict__ tbl, uint
     }
 }
 
+// encode_level<false> with at most 2 * GU gathers of a lane in flight (the corner loop is unrolled GU times only): the ray-slot
+// kernel's gather shares the LSU with the epilogue's operand stores, and a fully unrolled level queues 16 scattered LDG.128 per
+// lane -- up to 4,096 L1 wavefronts ahead of every epilogue store (profiles/r02_render_timeline.txt).  Same arithmetic per feature.
+template <int GU>
+__device__ __forceinline__ void encode_level_thin(const float *__restrict__ tbl, uint32_t mask, float scale, const float (&x)[5],
+                                                  float (&res)[8]) {
+    float f[3];
+    uint32_t g[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float pos = fmaf(x[d], scale, 0.5f);
+        const float fl = floorf(pos);
+        g[d] = (uint32_t)fl;
+        f[d] = pos - (float)g[d];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) res[c] = 0.0f;
+#pragma unroll(GU)
+    for (int idx = 0; idx < 8; idx++) {
+        const uint32_t b0 = idx & 1, b1 = (idx >> 1) & 1, b2 = (idx >> 2) & 1;
+        float w = b0 ? f[0] : 1.0f - f[0];
+        w *= b1 ? f[1] : 1.0f - f[1];
+        w *= b2 ? f[2] : 1.0f - f[2];
+        const uint32_t index = ((g[0] + b0) ^ ((g[1] + b1) * kPrime1) ^ ((g[2] + b2) * kPrime2)) & mask;
+        float v[8];
+        ld8(tbl + (size_t)index * 8, v);
+#pragma unroll
+        for (int c = 0; c < 8; c++) res[c] = fmaf(w, v[c], res[c]);
+    }
+}
+
 // 8 fp32 values -> one 16-byte chunk of 16-bit operand (hi) and, for the x3 split, the residual (lo)
 // PREC: 0 = fp16 single pass, 1 = bf16 hi/lo split, 2 = fp16 hi/lo split
 template <int PREC>
@@ -170,7 +201,7 @@ template <int PREC> __device__ __forceinline__ uint32_t one16() { return PREC ==
 // tile no longer marches until its slowest ray is opaque: per C2 frame 4.4-4.7 M + ~0.5 M (one wasted step per terminated ray)
 // instead of 6.5-6.8 M samples are shaded (tools/ray_stats.py).  The CTA runs ONE open-ended "tile": the loop control of all four
 // roles is the early-termination mechanism below (stop_step decided by the epilogue two steps ahead).
-template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN, bool RAYQ = false, int GU = 8>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const Params p)
 {
@@ -1034,7 +1065,8 @@ mlp_kernel(const Params p)
 #pragma unroll
                             for (int c = 0; c < 8; c++) res[c] = 0.0f;
                         } else {
-                            encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                            if constexpr (GU == 8) encode_level<RAW5D>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
+                            else encode_level_thin<GU>(p.table + ((size_t)level << p.log2_T) * 8, mask, sScale[level], x5, res);
                         }
                         split8<PREC>(res, fh[i], fl[i]);
                     }
@@ -1439,14 +1471,14 @@ int launch_pack(const float *w0, const float *b0, const float *emb, int n_labels
     return SDB_OK;
 }
 
-template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false>
+template <int PREC, bool RAW5D, int MODE, bool TRAIN = false, bool RAYQ = false, int GU = 8>
 int launch_mlp(const Params &p, int grid, cudaStream_t st) {
     const size_t smem = smem_map(PREC != 0).total;
     cudaFuncAttributes fa;
-    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>));
+    SDB_CUDA(cudaFuncGetAttributes(&fa, mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, GU>));
     if (fa.numRegs < kRegsLaunch) return SDB_EUNSUPPORTED;   // setmaxnreg pool would be too small: refuse rather than hang
-    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ><<<grid, kThreads, smem, st>>>(p);
+    SDB_CUDA(cudaFuncSetAttribute(mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, GU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_kernel<PREC, RAW5D, MODE, TRAIN, RAYQ, GU><<<grid, kThreads, smem, st>>>(p);
     SDB_CHECK_LAUNCH();
     return SDB_OK;
 }
@@ -1722,7 +1754,13 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         int rc;
         if (sp->precision == 0) rc = launch_mlp<0, false, kRender, false, true>(p, grid, st);
         else if (sp->precision == 1) rc = launch_mlp<1, false, kRender, false, true>(p, grid, st);
-        else rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
+        else {
+            static const int gu = [] { const char *e = getenv("SDB_GATHER_UNROLL"); return e ? atoi(e) : 8; }();
+            if (gu == 1) rc = launch_mlp<2, false, kRender, false, true, 1>(p, grid, st);
+            else if (gu == 2) rc = launch_mlp<2, false, kRender, false, true, 2>(p, grid, st);
+            else if (gu == 4) rc = launch_mlp<2, false, kRender, false, true, 4>(p, grid, st);
+            else rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
+        }
         if (rc != SDB_OK) return rc;
         set_flag_kernel<<<1, 1, 0, st>>>(ws + 3);
         SDB_CHECK_LAUNCH();
