@@ -1755,11 +1755,11 @@ extern "C" int sdb_render_rays_forward(const sdb_render_params *sp, void *stream
         if (sp->precision == 0) rc = launch_mlp<0, false, kRender, false, true>(p, grid, st);
         else if (sp->precision == 1) rc = launch_mlp<1, false, kRender, false, true>(p, grid, st);
         else {
-            static const int gu = [] { const char *e = getenv("SDB_GATHER_UNROLL"); return e ? atoi(e) : 8; }();
-            if (gu == 1) rc = launch_mlp<2, false, kRender, false, true, 1>(p, grid, st);
-            else if (gu == 2) rc = launch_mlp<2, false, kRender, false, true, 2>(p, grid, st);
-            else if (gu == 4) rc = launch_mlp<2, false, kRender, false, true, 4>(p, grid, st);
-            else rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
+            // gathers in flight per lane: 2 corners (4 LDG.128) measured best -- kernel 9.48 ms vs 9.81 fully unrolled, 9.68 / 9.53 at
+            // 4 / 1 corners (profiles/r02_exp_gather_unroll.json); SDB_GATHER_UNROLL=8 selects the fully unrolled level
+            static const int gu = [] { const char *e = getenv("SDB_GATHER_UNROLL"); return e ? atoi(e) : 2; }();
+            if (gu == 8) rc = launch_mlp<2, false, kRender, false, true>(p, grid, st);
+            else rc = launch_mlp<2, false, kRender, false, true, 2>(p, grid, st);
         }
         if (rc != SDB_OK) return rc;
         set_flag_kernel<<<1, 1, 0, st>>>(ws + 3);
