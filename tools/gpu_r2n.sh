@@ -27,3 +27,5 @@ timeout 600 python tests/ops_timing.py > gpurun_out/ops_timing.json 2> gpurun_ou
 timeout 300 ncu --set full --clock-control none -k 'regex:grid_|input_backward' -s 3 -c 3 -f -o gpurun_out/prof_gridenc env PYTHONPATH=. python tools/gridenc_run.py > gpurun_out/prof_gridenc.log 2>&1
 ncu -i gpurun_out/prof_gridenc.ncu-rep --page raw --csv > gpurun_out/prof_gridenc_raw.csv 2>/dev/null; rm -f gpurun_out/prof_gridenc.ncu-rep; tail -2 gpurun_out/prof_gridenc.log
 timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu --no-extras --mode strong > gpurun_out/strong_n1.json 2> gpurun_out/strong_n1.err; cut -c1-200 gpurun_out/strong_n1.json; tail -2 gpurun_out/strong_n1.err
+timeout 400 ncu --clock-control none --set full -k regex:mlp_kernel -s 9 -c 1 -f -o gpurun_out/prof_render python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/ncu_render.log 2>&1
+ncu -i gpurun_out/prof_render.ncu-rep --page raw --csv > gpurun_out/prof_render_raw.csv 2>/dev/null; rm -f gpurun_out/prof_render.ncu-rep; tail -1 gpurun_out/ncu_render.log
