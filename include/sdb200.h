@@ -352,6 +352,22 @@ int sdb_cnn_forward(const float *d_net_out, int32_t H, int32_t W, const void *d_
                     void *stream);
 
 /* --------------------------------------------------------------------------------------------
+ * a8 (training): the style modulation of LightningMLP's five ModLinear layers for ONE style code, folded into plain
+ * weights, forward and backward (imaginaire/model_utils/layers.py:241-271 as used at :92-126):
+ *   alpha = weight_alpha z + bias_alpha [I], beta = weight_beta z + bias_beta [O], W' = W * alpha (per input column).
+ * d_params / d_grads: 25 device pointers, float32, contiguous, in the order
+ *   weight[0..4] [O,I], weight_alpha[0..4] [I,Cz], bias_alpha[0..4] [I], weight_beta[0..4] [O,Cz], bias_beta[0..4] [O]
+ * (layers fc_2 .. fc_6).  forward: d_alpha [5,I], d_wh [5,O,I], d_bh [5,O] (= beta).  backward: from d_g_wh [5,O,I] and
+ * d_g_bh [5,O] every parameter gradient (d_grads, same order, OVERWRITTEN) and d_dz [Cz]; d_dalpha [5,I] is scratch.
+ * Replaces ~110 ATen launches per training view of the torch formulation (the backward is host-bound there).
+ * ------------------------------------------------------------------------------------------ */
+int sdb_modulate_forward(const void *const d_params[25], const float *d_z, int32_t O, int32_t I, int32_t Cz, float *d_alpha,
+                         float *d_wh, float *d_bh, void *stream);
+int sdb_modulate_backward(const void *const d_params[25], void *const d_grads[25], const float *d_z, const float *d_alpha,
+                          const float *d_g_wh, const float *d_g_bh, int32_t O, int32_t I, int32_t Cz, float *d_dalpha,
+                          float *d_dz, void *stream);
+
+/* --------------------------------------------------------------------------------------------
  * f2. The Adam step of the hash table in one pass over (param, grad, exp_avg,
  * exp_avg_sq) -- torch.optim.Adam's arithmetic and state (imaginaire/utils/trainer.py:297-323,
  * configs/scenedreamer_train.yaml:36-61: betas (0, 0.999), eps 1e-7, no weight decay / amsgrad).

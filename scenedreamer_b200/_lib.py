@@ -79,6 +79,9 @@ SIGNATURES = {
     'sdb_launch_count': (c_i64, []),
     'sdb_debug_train_layout': (c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_i64)]),
     'sdb_debug_set_progress_buffer': (None, [c_void_p]),
+    'sdb_modulate_forward': (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sdb_modulate_backward': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
     'sdb_tc_selftest_mn': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
     'sdb_tc_selftest': (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p]),
 }

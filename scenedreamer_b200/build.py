@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 LIB = os.path.join(HERE, 'libsdb200.so')
-SOURCES = ['api.cu', 'dda.cu', 'gridenc.cu', 'posenc.cu', 'tc_selftest.cu', 'render_fused.cu', 'render_train.cu', 'wgrad.cu', 'sptrilinear.cu', 'rendercnn.cu', 'optim.cu', 'posestats.cu', 'worldgen.cu']
+SOURCES = ['api.cu', 'dda.cu', 'gridenc.cu', 'posenc.cu', 'tc_selftest.cu', 'render_fused.cu', 'render_train.cu', 'wgrad.cu', 'sptrilinear.cu', 'rendercnn.cu', 'optim.cu', 'posestats.cu', 'worldgen.cu', 'modulate.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '--expt-relaxed-constexpr'] + \
              os.environ.get('SDB_NVCC_EXTRA', '').split()      # e.g. -DSDB_TIMELINE (diagnostics build)

@@ -7,6 +7,7 @@ All heavy work happens in the CUDA library; torch is used to allocate tensors, t
 modulation into the weights (tiny [256x256] elementwise products, once per style code).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -56,18 +57,83 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def modulated_weights(P, z, prefix='render_net'):
-    """Fold the style modulation of ModLinear into plain weights for ONE style code z [256]
-    (model_utils/layers.py:247-260): W' = W * alpha (per input column), bias = beta."""
+_MOD_LAYERS = (2, 3, 4, 5, 6)
+_MOD_FIELDS = ('weight', 'weight_alpha', 'bias_alpha', 'weight_beta', 'bias_beta')
+
+
+def _modulated_weights_torch(P, z, prefix='render_net'):
     p = prefix + '.'
     wh, bh = [], []
-    for k in (2, 3, 4, 5, 6):
+    for k in _MOD_LAYERS:
         n = p + 'fc_%d' % k
         alpha = torch.addmm(P[n + '.bias_alpha'].unsqueeze(0), z.unsqueeze(0), P[n + '.weight_alpha'].t())   # [1, I]
         beta = torch.addmm(P[n + '.bias_beta'].unsqueeze(0), z.unsqueeze(0), P[n + '.weight_beta'].t())      # [1, O]
         wh.append(P[n + '.weight'].unsqueeze(0) * alpha.unsqueeze(1))                                         # [1, O, I]
         bh.append(beta)
     return torch.cat(wh, 0).contiguous(), torch.cat(bh, 0).contiguous()
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _ModulateFn(torch.autograd.Function):
+    """(wh [5,O,I], bh [5,O]) = fold(z [Cz], the 25 ModLinear tensors) on the device in two launches; backward in three
+    (csrc/modulate.cu) instead of autograd's chain of small ATen nodes."""
+
+    @staticmethod
+    def forward(ctx, z, *params):
+        L = _lib.lib()
+        dev = z.device
+        O, I = params[0].shape
+        Cz = z.numel()
+        zc = z.detach().contiguous()
+        ps = [t.detach() for t in params]
+        with torch.cuda.device(dev):
+            alpha = torch.empty(5, I, dtype=torch.float32, device=dev)
+            wh = torch.empty(5, O, I, dtype=torch.float32, device=dev)
+            bh = torch.empty(5, O, dtype=torch.float32, device=dev)
+            _lib.check(L.sdb_modulate_forward(_ptr_array(ps), _ptr(zc), int(O), int(I), int(Cz), _ptr(alpha), _ptr(wh), _ptr(bh),
+                                              _stream(dev)), 'sdb_modulate_forward')
+        ctx.save_for_backward(zc, alpha, *ps)
+        ctx.dims = (int(O), int(I), int(Cz))
+        return wh, bh
+
+    @staticmethod
+    def backward(ctx, g_wh, g_bh):
+        L = _lib.lib()
+        zc, alpha, *ps = ctx.saved_tensors
+        dev = zc.device
+        O, I, Cz = ctx.dims
+        with torch.cuda.device(dev):
+            g_wh = (g_wh if g_wh is not None else torch.zeros(5, O, I, device=dev)).to(torch.float32).contiguous()
+            g_bh = (g_bh if g_bh is not None else torch.zeros(5, O, device=dev)).to(torch.float32).contiguous()
+            grads = [torch.empty_like(t) for t in ps]
+            dalpha = torch.empty(5, I, dtype=torch.float32, device=dev)
+            dz = torch.empty(Cz, dtype=torch.float32, device=dev)
+            _lib.check(L.sdb_modulate_backward(_ptr_array(ps), _ptr_array(grads), _ptr(zc), _ptr(alpha), _ptr(g_wh), _ptr(g_bh),
+                                               O, I, Cz, _ptr(dalpha), _ptr(dz), _stream(dev)), 'sdb_modulate_backward')
+        return (dz,) + tuple(grads)
+
+
+def modulated_weights(P, z, prefix='render_net'):
+    """Fold the style modulation of ModLinear into plain weights for ONE style code z [256]
+    (model_utils/layers.py:247-260): W' = W * alpha (per input column), bias = beta.  Differentiable w.r.t. the 25 tensors
+    and z; on CUDA float32 contiguous inputs one fused forward / backward (csrc/modulate.cu), otherwise the same algebra in torch
+    ops (SDB200_FUSED_MOD=0 forces that)."""
+    p = prefix + '.'
+    names = [p + 'fc_%d.%s' % (k, f) for f in _MOD_FIELDS for k in _MOD_LAYERS]
+    ts = [P[n] for n in names]
+    ok = z.is_cuda and z.dim() == 1 and os.environ.get('SDB200_FUSED_MOD', '1') != '0' and \
+        all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == z.device for t in ts + [z])
+    if ok:
+        O, I = ts[0].shape
+        Cz = z.numel()
+        ok = all(tuple(ts[l].shape) == (O, I) and tuple(ts[5 + l].shape) == (I, Cz) and tuple(ts[10 + l].shape) == (I,) and
+                 tuple(ts[15 + l].shape) == (O, Cz) and tuple(ts[20 + l].shape) == (O,) for l in range(5))
+    if not ok:
+        return _modulated_weights_torch(P, z, prefix)
+    return _ModulateFn.apply(z, *ts)
 
 
 def pack_mlp(P, z, precision=PRECISION_FP16X3, prefix='render_net'):

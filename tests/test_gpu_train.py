@@ -151,6 +151,34 @@ def test_train_sky_torch_crosscheck(scene, golden_ops, sky_impl):
         assert rel <= 1e-2, k
 
 
+def test_fused_style_modulation_matches_torch_autograd(monkeypatch):
+    """ModLinear's fold for one style code (layers.py:247-260) as one fused forward / backward (csrc/modulate.cu) against the same
+    algebra in torch ops under autograd: W', beta, and the gradients of all 25 tensors and of z."""
+    P = {k: v.to(DEV).requires_grad_(True) for k, v in oracle.make_params(seed=5, stress=True, table_entries=64).items()
+         if k.startswith('render_net.fc_') and '.' in k}
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(256, generator=g).to(DEV).requires_grad_(True)
+    gw, gb = torch.randn(5, 256, 256, generator=g).to(DEV), torch.randn(5, 256, generator=g).to(DEV)
+    res = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('SDB200_FUSED_MOD', fused)
+        for t in list(P.values()) + [z]:
+            t.grad = None
+        wh, bh = render.modulated_weights(P, z)
+        assert (wh.grad_fn is not None) and (('Modulate' in type(wh.grad_fn).__name__) == (fused == '1'))
+        ((wh * gw).sum() + (bh * gb).sum()).backward()
+        res[fused] = (wh.detach().clone(), bh.detach().clone(), z.grad.clone(),
+                      {k: v.grad.clone() for k, v in P.items() if v.grad is not None})
+    a, b = res['1'], res['0']
+    for x, y, name in ((a[0], b[0], 'wh'), (a[1], b[1], 'bh'), (a[2], b[2], 'dz')):
+        assert float((x - y).abs().max()) <= 2e-5 * float(y.abs().max()) + 1e-7, name
+    names = [k for k in b[3] if any(k.endswith(f) for f in ('.weight', '.weight_alpha', '.bias_alpha', '.weight_beta', '.bias_beta'))
+             and k.split('.')[1] in ('fc_2', 'fc_3', 'fc_4', 'fc_5', 'fc_6')]
+    assert len(names) == 25 and set(names) <= set(a[3])
+    for k in names:
+        assert float((a[3][k] - b[3][k]).abs().max()) <= 2e-5 * float(b[3][k].abs().max()) + 1e-7, k
+
+
 @pytest.mark.parametrize('betas', [(0.0, 0.999), (0.9, 0.999)])
 def test_fused_adam_step_matches_torch_adam(betas):
     """f2: sdb_adam_step == torch.optim.Adam (reference: trainer.py:297-323, scenedreamer_train.yaml:36-61) over several
