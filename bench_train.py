@@ -141,9 +141,10 @@ def main():
             zero_grads()
             flush.zero_()
         torch.cuda.synchronize()
-        fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-        tot = float(np.mean([e[0].elapsed_time(e[2]) for e in evs]))
-        return fwd, tot
+        fwds = [e[0].elapsed_time(e[1]) for e in evs]
+        tots = [e[0].elapsed_time(e[2]) for e in evs]
+        timed.last_steps = [round(t, 2) for t in tots]              # every step, for the reader: a mean hides a host hiccup
+        return float(np.median(fwds)), float(np.median(tots))
 
     if a.profile:
         import time
@@ -183,6 +184,8 @@ def main():
     line = {'metric': 'train-step per-pixel path: forward(record)+backward, 262x262 rays x 24 spp, per GPU', 'unit': 'ms',
             'fused': {'forward_ms': fwd_ms, 'backward_ms': tot_ms - fwd_ms, 'total_ms': tot_ms,
                       'msamples_per_s_fwd_bwd': samples / (tot_ms * 1e-3) / 1e6},
+            'aggregate': 'median over the timed steps (CUDA events around forward / forward+backward)',
+            'total_ms_per_step': timed.last_steps,
             'samples_per_view': samples, 'live_ray_fraction': live, 'steps': a.steps, 'data': 'synthetic',
             'l2': 'flushed between steps', 'record_bytes': int(render._lib.lib().sdb_render_train_record_bytes(1, H, W, SPP)),
             'backward_workspace_bytes': int(render._lib.lib().sdb_render_backward_workspace_bytes(1, H, W, SPP, 16, 19))}
