@@ -19,7 +19,8 @@ rendered features.  `samples_shaded_per_frame` says how many of the credited sam
 Each step renders a different pose of the 40-frame trajectory and L2 is flushed between steps (256 MiB memset outside the
 per-step CUDA events).
 Multi-GPU: weak scaling by default (every rank renders its own frames, frame f -> rank f mod N; the finished frames are
-all-gathered once per step over NCCL); `--mode strong` splits ONE frame into two row bands per rank.
+all-gathered once per step over NCCL); `--mode strong` splits ONE frame into 16-row bands dealt round-robin
+to the ranks (one banded raycast and one render launch per rank).
 Extra keys at N=1: `c4` (2160x3840x40), `c5_train_step` (bench_train.py), `reference_cuda_b200` (the reference renderer itself
 on this GPU, and the same Python with dropin/ on the path), `cpu_baseline`.
 """

@@ -34,30 +34,12 @@ def gather_frames(local, group=None):
     return out.transpose(0, 1).reshape((world * n_local,) + tuple(local.shape[1:]))
 
 
-def tile_rows_for_rank(H, rank, world_size, tile_h=8):
-    """Single-frame sharding: contiguous bands of tile rows per rank (strong scaling of one frame)."""
-    tiles = (H + tile_h - 1) // tile_h
-    per = (tiles + world_size - 1) // world_size
-    y0 = min(H, rank * per * tile_h)
-    y1 = min(H, (rank + 1) * per * tile_h)
-    return y0, y1
-
-
-def paired_bands(H, rank, world_size, tile_h=8):
-    """Single-frame sharding, balanced: the frame is cut into 2 * world_size contiguous bands of tile rows and rank r
-    shades band r AND band 2*world_size - 1 - r.  Cost per row grows roughly monotonically from the sky at the top of a
-    frame to the ground at its bottom, so pairing a band from the top with its mirror from the bottom evens the ranks out
-    (contiguous single bands left the sky-only top ranks idle: 0.1 ms against 3.3 ms of kernel time at 8 GPUs)."""
-    first = tile_rows_for_rank(H, rank, 2 * world_size, tile_h)
-    second = tile_rows_for_rank(H, 2 * world_size - 1 - rank, 2 * world_size, tile_h)
-    return [first, second]
-
-
 def cyclic_bands(H, rank, world_size, band_tiles=2, tile_h=8):
     """Single-frame sharding, balanced without knowing the cost profile: the frame is cut into thin bands of `band_tiles`
     tile rows and band b goes to rank b mod world_size.  (The cost of a row is neither flat nor monotonic -- sky at the top
     is free, near ground at the bottom terminates within a few samples, the horizon in the middle is the expensive part -- so
-    contiguous or mirrored bands leave some ranks idle: 0.1 vs 3.1 ms of kernel time at 8 GPUs.)
+    one contiguous band per rank, or a band paired with its mirror, leave some ranks idle: 0.1 vs 3.1 ms of kernel time at 8 GPUs,
+    profiles/r02_scale_n8_strong.json, r02_scale_rayslots_n8_strong.json.)
     Returns the rank's bands as (y0, y1) in frame order; every rank gets the same NUMBER of slots, trailing ones may be empty."""
     bh = band_tiles * tile_h if world_size > 1 else H          # one GPU: the frame is one band
     n_bands = (H + bh - 1) // bh

@@ -52,21 +52,6 @@ def test_partitions_are_disjoint_and_complete():
         frames = sorted(f for r in range(world) for f in sharding.frames_for_rank(40, r, world))
         assert frames == list(range(40))
         assert all(sharding.frame_owner(f, world) == f % world for f in range(40))
-        rows = [sharding.tile_rows_for_rank(570, r, world) for r in range(world)]
-        assert rows[0][0] == 0 and rows[-1][1] == 570
-        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
-        assert all(y0 % 8 == 0 for y0, _ in rows)
-
-
-def test_paired_bands_cover_the_frame_once():
-    for world in (1, 2, 4, 8):
-        for H in (570, 2190, 64, 9):
-            bands = sorted(b for r in range(world) for b in sharding.paired_bands(H, r, world) if b[1] > b[0])
-            assert bands[0][0] == 0 and bands[-1][1] == H
-            assert all(bands[i][1] == bands[i + 1][0] for i in range(len(bands) - 1))
-            # rank r owns band r and its mirror: top + bottom
-            first, second = sharding.paired_bands(H, 0, world)
-            assert first[0] == 0 and (second[1] == H or second[1] == second[0])
 
 
 def test_cyclic_bands_cover_the_frame_once():
