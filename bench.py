@@ -361,8 +361,7 @@ def run_gpu_arm(args):
             if cev is not None:
                 cev[1].record()
             if strong:                                               # slot j of rank r is band j * N + r: back into frame order
-                a = allm.reshape(world_size, 2, n_slots, band_cap, res[1])
-                maps = a.permute(1, 2, 0, 3, 4).reshape(2, -1, res[1])
+                maps = sharding.assemble_bands(allm, world_size, n_slots, band_cap)
         if want_host:                                                # D2H of the step's result
             if to_image:
                 host_rgb.copy_(maps, non_blocking=True)

@@ -50,3 +50,13 @@ def cyclic_bands(H, rank, world_size, band_tiles=2, tile_h=8):
         y0 = min(H, b * bh)
         out.append((y0, min(H, y0 + bh)))
     return out
+
+
+
+def assemble_bands(gathered, world_size, n_slots, band_rows):
+    """Inverse of cyclic_bands after the all-gather: `gathered` [world_size, C, n_slots * band_rows, W] holds, for every rank, its band
+    slots one after the other (slot j of rank r = band j * world_size + r, short / missing bands zero-padded to band_rows);
+    returns [C, n_slots * world_size * band_rows, W] in frame order (rows beyond the frame height are the padding)."""
+    C, W = gathered.shape[1], gathered.shape[-1]
+    a = gathered.reshape(world_size, C, n_slots, band_rows, W)
+    return a.permute(1, 2, 0, 3, 4).reshape(C, n_slots * world_size * band_rows, W)

@@ -54,6 +54,23 @@ def test_partitions_are_disjoint_and_complete():
         assert all(sharding.frame_owner(f, world) == f % world for f in range(40))
 
 
+def test_assemble_bands_restores_the_frame():
+    """cyclic_bands -> per-rank concatenation (as bench.py --mode strong renders it) -> all-gather layout -> assemble_bands == frame."""
+    for world in (1, 2, 4, 8):
+        for H in (570, 64, 9):
+            W = 7
+            frame = torch.arange(2 * H * W, dtype=torch.float32).reshape(2, H, W)
+            per = [sharding.cyclic_bands(H, r, world) for r in range(world)]
+            n_slots = len(per[0])
+            band_rows = 16 if world > 1 else H
+            gathered = torch.zeros(world, 2, n_slots * band_rows, W)
+            for r, bands in enumerate(per):
+                rows = torch.cat([frame[:, y0:y1] for (y0, y1) in bands if y1 > y0], 1) if any(b[1] > b[0] for b in bands) else frame[:, :0]
+                gathered[r, :, :rows.shape[1]] = rows                         # only a rank's LAST band can be short or missing
+            out = sharding.assemble_bands(gathered, world, n_slots, band_rows)
+            assert torch.equal(out[:, :H], frame)
+
+
 def test_cyclic_bands_cover_the_frame_once():
     for world in (1, 2, 4, 8):
         for H in (570, 2190, 64, 9):
