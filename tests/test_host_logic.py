@@ -178,3 +178,23 @@ def test_renderer_caches_key_on_identity_not_address(monkeypatch):
     assert r.pack_for(z) != p1
     r.invalidate()
     assert r.pack_for(z) != ('pack', len(built) - 1)
+
+
+def test_style_fold_is_modlinear_for_one_style_code():
+    """The fold the fused renderer consumes (render.modulated_weights: W' = W * alpha(z), bias beta(z)) is ModLinear's forward
+    (layers.py:247-260, restated in oracle.mod_linear) for one style code -- here the torch formulation on the CPU; the fused CUDA
+    fold (csrc/modulate.cu) is compared with this formulation, values and all gradients, in tests/test_gpu_train.py."""
+    import torch
+
+    import oracle
+    from scenedreamer_b200 import render
+    P = oracle.make_params(seed=4, stress=True, table_entries=64)
+    g = torch.Generator().manual_seed(1)
+    z = oracle.style_mlp(torch.randn(1, 128, generator=g), P)            # [1, 256]
+    x = torch.randn(1, 37, 256, generator=g)
+    wh, bh = render.modulated_weights(P, z[0])                           # CPU tensors -> the torch formulation
+    assert wh.shape == (5, 256, 256) and bh.shape == (5, 256)
+    for l, k in enumerate((2, 3, 4, 5, 6)):
+        ref = oracle.mod_linear(x, z, P, 'render_net.fc_%d' % k)
+        got = x[0] @ wh[l].t() + bh[l]
+        assert float((got - ref[0]).abs().max()) <= 1e-5 * float(ref.abs().max())
