@@ -27,3 +27,15 @@ def test_reference_arm_prints_the_contract_line():
     assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['sample'] and abs(cb['value'] - d['value']) < 1e-9
     e = d['e2e']
     assert e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0 and abs(e['value'] - d['value']) < 1e-9 and e['unit'] == d['unit']
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the reference arm like the product arm; rank 0 alone runs it and prints, the others exit 0."""
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29541', os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                        '--steps', '1', '--warmup', '0'], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.strip().splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
