@@ -1,5 +1,6 @@
 #!/bin/bash
-# gather loads in flight (SDB_GATHER_UNROLL): parity of a thin variant, then bench of each
+# gather loads in flight (SDB_GATHER_UNROLL): parity of a thin variant, then bench of each (the 4- and 1-corner variants existed for this A/B only:
+# the shipped library keeps 2 (default) and 8; profiles/r02_exp_gather_unroll.json)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 python -m scenedreamer_b200.build > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
