@@ -477,7 +477,7 @@ def run_gpu_arm(args):
             'mpix_per_s': value / spp, 'n_gpus': world_size, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dev_ms, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'value_exact_march': frames_per_step * samples_per_frame / (exact_ms * 1e-3) / 1e6,
-            'value_exact_march_note': 'same measurement with early termination off (every sample of every live tile shaded)',
+            'value_exact_march_note': 'same measurement with early termination off (every sample of every live ray shaded)',
             'samples_credited_per_frame': samples_per_frame,
             'samples_shaded_per_frame': steps_exec * 128 / band_frac,
             'samples_shaded_note': 'steps executed x 128 rows (rank 0, mean over frames).  Ray-slot kernel: only live rays occupy rows, a ray '
