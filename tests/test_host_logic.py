@@ -198,3 +198,39 @@ def test_style_fold_is_modlinear_for_one_style_code():
         ref = oracle.mod_linear(x, z, P, 'render_net.fc_%d' % k)
         got = x[0] @ wh[l].t() + bh[l]
         assert float((got - ref[0]).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_new_entry_points_refuse_bad_arguments_before_touching_the_device():
+    """Round-2 entry points (banded raycast, float16 grid tables, ModLinear fold, sp_trilinear, Adam): argument checks come before
+    any CUDA call, so they can be exercised without a GPU.  Pointers handed over here are never dereferenced."""
+    import ctypes
+    L = _lib.lib()
+    EINVAL, EUNSUPPORTED = -1, -2
+    i64x3 = ctypes.c_int64 * 3
+    f3, f2, i2, i3 = ctypes.c_float * 3, ctypes.c_float * 2, ctypes.c_int32 * 2, ctypes.c_int32 * 3
+    dummy = ctypes.c_void_p(0x1000)                                    # non-null, never read: every call below fails a check first
+    dims, strides = i64x3(8, 8, 8), i64x3(64, 8, 1)
+    o, d, u = f3(1, 1, 1), f3(0, 1, 0), f3(1, 0, 0)
+
+    def bands(band, img=(16, 8)):
+        return L.sdb_ray_voxel_intersection_perspective_bands(dummy, dims, strides, o, d, u, 10.0, f2(4, 4), i2(*img), 4, band, dummy,
+                                                              dummy, dummy, None, 0, None)
+    assert bands(None) == EINVAL                                       # no band description
+    assert bands(i3(0, 16, 8)) == EINVAL                               # overlapping bands (stride < rows)
+    assert bands(i3(-1, 8, 8)) == EINVAL and bands(i3(0, 0, 8)) == EINVAL
+    assert bands(i3(0, 8, 8), img=(0, 8)) == EINVAL                    # empty image
+    # float16 grid tables: odd C never reaches this path in the reference (grid.py:38)
+    assert L.sdb_grid_encode_forward_f16(dummy, dummy, dummy, dummy, 16, 3, 1, 4, 1.0, 16, 0, None, 0, 0, None) == EUNSUPPORTED
+    assert L.sdb_grid_encode_forward_f16(dummy, dummy, dummy, dummy, 16, 6, 2, 4, 1.0, 16, 0, None, 0, 0, None) == EUNSUPPORTED
+    assert L.sdb_grid_encode_forward_f16(None, dummy, dummy, dummy, 16, 3, 2, 4, 1.0, 16, 0, None, 0, 0, None) == EINVAL
+    assert L.sdb_grid_encode_forward_f16(dummy, dummy, dummy, dummy, 16, 3, 2, 4, 1.0, 16, 1, None, 0, 0, None) == EINVAL   # dy_dx asked, not given
+    assert L.sdb_grid_encode_backward_f16(dummy, dummy, dummy, dummy, dummy, 16, 3, 1, 4, 1.0, 16, 0, None, None, 0, 0, None) == EUNSUPPORTED
+    assert L.sdb_grid_encode_forward_f16(dummy, dummy, dummy, dummy, 0, 3, 2, 4, 1.0, 16, 0, None, 0, 0, None) == 0          # empty batch: nothing to do
+    # ModLinear fold
+    ptrs = (ctypes.c_void_p * 25)(*([0x1000] * 25))
+    assert L.sdb_modulate_forward(None, dummy, 256, 256, 256, dummy, dummy, dummy, None) == EINVAL
+    assert L.sdb_modulate_forward(ptrs, dummy, 0, 256, 256, dummy, dummy, dummy, None) == EINVAL
+    holes = (ctypes.c_void_p * 25)(*([0x1000] * 24 + [None]))
+    assert L.sdb_modulate_forward(holes, dummy, 256, 256, 256, dummy, dummy, dummy, None) == EINVAL
+    assert L.sdb_modulate_backward(ptrs, holes, dummy, dummy, dummy, dummy, 256, 256, 256, dummy, dummy, None) == EINVAL
+    assert L.sdb_modulate_backward(ptrs, ptrs, dummy, dummy, dummy, None, 256, 256, 256, dummy, dummy, None) == EINVAL
