@@ -314,18 +314,7 @@ def run_gpu_arm(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     L = _lib.lib()
 
-    def global_sky_mean(parts):
-        # single-frame sharding: the frame-global sky mean (scenedreamer.py:592-598) needs every band: one 65-float
-        # all-gather of the band sums, combined in rank order
-        part = torch.zeros(65, device=dev)
-        for avg_band, n_band in parts:
-            part[:64] += avg_band.reshape(64) * float(n_band)
-            part[64] += float(n_band)
-        if world_size == 1:
-            return (part[:64] / part[64]).reshape(1, 64)
-        allp = torch.empty(world_size, 65, device=dev)
-        dist.all_gather_into_tensor(allp, part.reshape(1, 65))
-        return (allp[:, :64].sum(0) / allp[:, 64].sum()).reshape(1, 64)
+    global_sky_mean = sharding.global_mean          # frame-global sky mean from band means: one 65-float all-gather
 
     def strong_step(cam, kev):
         """ONE frame over all ranks: this rank's bands -> [2, n_slots * band_cap, W] maps (every slot padded to band_cap rows)."""

@@ -60,3 +60,22 @@ def assemble_bands(gathered, world_size, n_slots, band_rows):
     C, W = gathered.shape[1], gathered.shape[-1]
     a = gathered.reshape(world_size, C, n_slots, band_rows, W)
     return a.permute(1, 2, 0, 3, 4).reshape(C, n_slots * world_size * band_rows, W)
+
+
+def global_mean(band_means, group=None):
+    """Frame-global mean of a per-ray quantity from per-band means: `band_means` = [(mean [C] or [1, C], number of rays)] of THIS
+    rank's bands; one all-gather of C + 1 floats per rank (the band sums and the ray count), combined in rank order on every rank.
+    Single-frame sharding needs it for the sky features: the reference averages them over the WHOLE frame (scenedreamer.py:592-598).
+    Returns [1, C]."""
+    first = band_means[0][0]
+    C = first.numel()
+    part = torch.zeros(C + 1, dtype=torch.float32, device=first.device)
+    for mean_band, n_band in band_means:
+        part[:C] += mean_band.reshape(C).to(torch.float32) * float(n_band)
+        part[C] += float(n_band)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return (part[:C] / part[C]).reshape(1, C)
+    allp = torch.empty(world, C + 1, dtype=torch.float32, device=first.device)
+    dist.all_gather_into_tensor(allp, part.reshape(1, C + 1), group=group)
+    return (allp[:, :C].sum(0) / allp[:, C].sum()).reshape(1, C)

@@ -47,6 +47,41 @@ def test_frame_sharding_and_all_gather_world2():
     assert res[0][2] and res[1][2]
 
 
+def _mean_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    H, W, C = 37, 5, 64
+    g = torch.Generator().manual_seed(3)
+    sky = torch.randn(H, W, C, generator=g)                                  # the same "frame" on every rank
+    bands = [b for b in sharding.cyclic_bands(H, rank, world, band_tiles=1, tile_h=4) if b[1] > b[0]]
+    parts = [(sky[y0:y1].reshape(-1, C).mean(0), (y1 - y0) * W) for (y0, y1) in bands]
+    got = sharding.global_mean(parts)
+    ref = sky.reshape(-1, C).mean(0)
+    q.put((rank, float((got.reshape(C) - ref).abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_mean_over_bands_world2():
+    """The frame-global sky mean of the single-frame mode: band means on two ranks -> one small all-gather -> the mean of the frame."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mean_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(err < 1e-6 for _, err in res)
+    # one process, no process group: the plain weighted mean
+    a, b = torch.ones(64), torch.zeros(64)
+    assert torch.allclose(sharding.global_mean([(a, 30), (b, 10)]), torch.full((1, 64), 0.75))
+
+
 def test_partitions_are_disjoint_and_complete():
     for world in (1, 2, 4, 8):
         frames = sorted(f for r in range(world) for f in sharding.frames_for_rank(40, r, world))
