@@ -250,14 +250,10 @@ class FrameRenderer:
     def cast_bands(self, cam, bands):
         """Several equally spaced row bands of one frame as ONE virtual image (rays are independent: the fused kernel only sees a
         list of them): one banded raycast, one sky launch -- and later one render launch -- over all of them."""
+        from scenedreamer_b200 import sharding
         o, d, u, f, c, res = cam
-        bands = [b for b in bands if b[1] > b[0]]
-        rows = sum(y1 - y0 for (y0, y1) in bands)
-        bh = bands[0][1] - bands[0][0]
-        stride = (bands[1][0] - bands[0][0]) if len(bands) > 1 else bh
-        assert all(b[0] == bands[0][0] + k * stride for k, b in enumerate(bands)) and all(b[1] - b[0] == bh for b in bands[:-1])
-        vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, [rows, res[1]], 6,
-                                                                   band=(bands[0][0], bh, stride))
+        first, bh, stride, rows = sharding.band_spec(bands)
+        vid, dep, rd = self.ops.ray_voxel_intersection_perspective(self.voxel, o, d, u, f, c, [rows, res[1]], 6, band=(first, bh, stride))
         vid, dep, rd = vid.unsqueeze(0), dep.unsqueeze(0), rd.unsqueeze(0)
         sky, sky_avg = self.render.sky_forward(rd, self.r.sky_pack_for(self.z), self.r.precision)
         return vid, dep, rd, sky, sky_avg, rows * res[1]

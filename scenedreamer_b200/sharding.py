@@ -53,6 +53,20 @@ def cyclic_bands(H, rank, world_size, band_tiles=2, tile_h=8):
 
 
 
+def band_spec(bands):
+    """(first_row, band_rows, band_stride, total_rows) of a rank's non-empty bands for the banded raycast
+    (ops.ray_voxel_intersection_perspective(..., band=...)): equally spaced bands of equal height, only the last may be shorter."""
+    bands = [b for b in bands if b[1] > b[0]]
+    if not bands:
+        raise ValueError('no rows for this rank')
+    bh = bands[0][1] - bands[0][0]
+    stride = (bands[1][0] - bands[0][0]) if len(bands) > 1 else bh
+    if any(b[0] != bands[0][0] + k * stride for k, b in enumerate(bands)) or any(b[1] - b[0] != bh for b in bands[:-1]) or \
+            bands[-1][1] - bands[-1][0] > bh or stride < bh:
+        raise ValueError('bands are not equally spaced / equally high: %r' % (bands,))
+    return bands[0][0], bh, stride, sum(b[1] - b[0] for b in bands)
+
+
 def assemble_bands(gathered, world_size, n_slots, band_rows):
     """Inverse of cyclic_bands after the all-gather: `gathered` [world_size, C, n_slots * band_rows, W] holds, for every rank, its band
     slots one after the other (slot j of rank r = band j * world_size + r, short / missing bands zero-padded to band_rows);

@@ -89,6 +89,28 @@ def test_partitions_are_disjoint_and_complete():
         assert all(sharding.frame_owner(f, world) == f % world for f in range(40))
 
 
+def test_band_spec_of_cyclic_bands():
+    for world in (1, 2, 4, 8):
+        for H in (570, 2190, 64):
+            for r in range(world):
+                bands = sharding.cyclic_bands(H, r, world)
+                if not any(b[1] > b[0] for b in bands):
+                    continue
+                first, rows, stride, total = sharding.band_spec(bands)
+                assert first == bands[0][0] and rows == (16 if world > 1 else H) or H < 16
+                assert stride == (16 * world if world > 1 and len([b for b in bands if b[1] > b[0]]) > 1 else rows)
+                # what the banded raycast computes: virtual row v -> frame row first + (v // rows) * stride + v % rows, v < total
+                covered = [first + (v // rows) * stride + v % rows for v in range(total)]
+                assert covered == [y for (y0, y1) in bands for y in range(y0, y1)]
+    import pytest
+    with pytest.raises(ValueError):
+        sharding.band_spec([(0, 16), (20, 36), (48, 64)])                  # not equally spaced
+    with pytest.raises(ValueError):
+        sharding.band_spec([(0, 16), (32, 40), (64, 80)])                  # a short band in the middle
+    with pytest.raises(ValueError):
+        sharding.band_spec([(5, 5)])
+
+
 def test_assemble_bands_restores_the_frame():
     """cyclic_bands -> per-rank concatenation (as bench.py --mode strong renders it) -> all-gather layout -> assemble_bands == frame."""
     for world in (1, 2, 4, 8):
